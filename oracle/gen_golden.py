@@ -1,0 +1,302 @@
+"""Generate golden vectors by EXECUTING THE REFERENCE (build container only; needs /root/reference).
+
+TEST INFRASTRUCTURE.  Run as a standalone process:  ``python oracle/gen_golden.py [--only tiny|arae|meto|meta]``
+
+The reference modules (``core.models.LMM``, ``core.transformer.*``) are imported from /root/reference
+with ``flash_attn`` masked (so ``core/transformer/attention.py:19-25`` picks its naive bmm path on CPU)
+and with import-time stubs for packages that are absent here and never touched by the arithmetic
+(``kiui``, ``trimesh``, ``megfile``).  ``LMM.generate`` itself runs unmodified (FSM closure, kwargs,
+``save_mesh`` tail); only ``mesh_decoder.generate`` — third-party HF ``GenerationMixin`` code that the
+installed transformers 5.5 cannot run against the reference's tuple cache (``modeling_opt.py:524``) — is
+replaced by ``hf_sample_restated`` below, a restatement of transformers==4.46.2 ``_sample``.
+
+Weights are ``edgerunner_b200.synth.synth_state_dict`` loaded with ``load_state_dict(strict=True)``: this
+also pins ``state_dict_spec`` against the reference's key schema and shapes.
+Outputs: small ``.npz`` / ``.json`` files under tests/golden/ (committed).
+"""
+
+import argparse
+import dataclasses
+import json
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = '/root/reference'
+GOLD = os.path.join(REPO, 'tests', 'golden')
+
+
+def install_stubs():
+    sys.modules['flash_attn'] = None  # force the naive attention path (CPU)
+
+    kiui = types.ModuleType('kiui')
+    kiui.lo = lambda *a, **k: None
+    kiui.seed_everything = lambda s: (torch.manual_seed(s), np.random.seed(s))
+    mu = types.ModuleType('kiui.mesh_utils')
+    mu.clean_mesh = mu.decimate_mesh = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError)
+    op = types.ModuleType('kiui.op')
+    op.recenter = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError)
+    kiui.mesh_utils, kiui.op = mu, op
+    sys.modules.update({'kiui': kiui, 'kiui.mesh_utils': mu, 'kiui.op': op})
+
+    tm = types.ModuleType('trimesh')
+
+    class Trimesh:  # holder only: the cleanup calls are third-party trimesh (parity unpinned)
+        def __init__(self, vertices=None, faces=None, **k):
+            self.vertices, self.faces = np.asarray(vertices), np.asarray(faces)
+
+        def merge_vertices(self): pass
+        def unique_faces(self): return np.ones(len(self.faces), dtype=bool)
+        def update_faces(self, m): pass
+        def fix_normals(self): pass
+
+    tm.Trimesh = Trimesh
+    sys.modules['trimesh'] = tm
+    sys.modules['megfile'] = types.ModuleType('megfile')
+
+
+def import_reference():
+    install_stubs()
+    # our repo's edgerunner_b200 (synth) + the reference's `core` / `meto` packages; NOT our own `core`
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or '.') != REPO]
+    sys.path.insert(0, os.path.join(REF, 'meto'))
+    sys.path.insert(0, os.path.join(HERE, '_ref'))      # compiled reference _meto
+    sys.path.insert(0, REF)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('er_synth', os.path.join(REPO, 'edgerunner_b200', 'synth.py'))
+    synth = importlib.util.module_from_spec(spec)
+    # synth imports core.options lazily only in tiny_options(); give it the reference's (identical fields)
+    spec.loader.exec_module(synth)
+    return synth
+
+
+def hf_sample_restated(decoder, inputs_embeds, eos_token_id, max_new_tokens, prefix_allowed_tokens_fn,
+                       do_sample=False, top_k=None, record=None, **unused):
+    """transformers==4.46.2 ``GenerationMixin._sample`` for B==1, num_beams==1, inputs_embeds-only prompt.
+
+    input_ids starts as an empty [1,0] long tensor; per step: prepare_inputs_for_generation -> forward ->
+    ``logits[:, -1, :].float()`` -> PrefixConstrainedLogitsProcessor (patched: core/utils.py:143-158) ->
+    [TopKLogitsWarper(top_k, filter=-inf, min_tokens_to_keep=1)] -> softmax+multinomial | argmax -> append ->
+    stop on EOS or len == max_new_tokens.  Returns only the new tokens."""
+    B = inputs_embeds.shape[0]
+    assert B == 1
+    input_ids = torch.ones((B, 0), dtype=torch.long)
+    past = None
+    attention_mask = torch.ones(inputs_embeds.shape[:2], dtype=torch.long)
+    while True:
+        mi = decoder.prepare_inputs_for_generation(input_ids, past_key_values=past, attention_mask=attention_mask,
+                                                   inputs_embeds=inputs_embeds, use_cache=True)
+        out = decoder(**mi, return_dict=True)
+        past = out.past_key_values
+        logits = out.logits[:, -1, :].clone().float()
+        mask = torch.full_like(logits, -math.inf)
+        allowed = prefix_allowed_tokens_fn(0, input_ids[0])
+        assert len(allowed) > 0
+        mask[0, allowed] = 0
+        scores = logits + mask
+        if do_sample:
+            k = min(top_k, scores.size(-1))
+            remove = scores < torch.topk(scores, k)[0][..., -1, None]
+            scores = scores.masked_fill(remove, -float('inf'))
+            probs = torch.softmax(scores, dim=-1)
+            nxt = torch.multinomial(probs, num_samples=1).squeeze(1)
+        else:
+            nxt = torch.argmax(scores, dim=-1)
+        if record is not None:
+            record['logits'].append(out.logits[0, -1].detach().clone())
+            record['scores'].append(scores[0].clone())
+        input_ids = torch.cat([input_ids, nxt[:, None]], dim=-1)
+        attention_mask = torch.cat([attention_mask, attention_mask.new_ones((B, 1))], dim=-1)
+        if int(nxt) == eos_token_id or input_ids.shape[1] >= max_new_tokens:
+            return input_ids
+
+
+def build_reference_model(synth, opt, seed, eos_logit):
+    from core.models import LMM
+    torch.manual_seed(0)
+    model = LMM(opt).eval()
+    sd = synth.synth_state_dict(opt, seed=seed, eos_logit=eos_logit)
+    ref_sd = model.state_dict()
+    assert list(ref_sd.keys()) == [n for n, _, _ in synth.state_dict_spec(opt)] or set(ref_sd) == set(sd), \
+        (set(ref_sd) ^ set(sd))
+    for k in ref_sd:
+        assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), (k, ref_sd[k].shape, sd[k].shape)
+    model.load_state_dict(sd, strict=True)
+    return model, sd
+
+
+class RefTokenizer:
+    """meto.Engine surface backed by the compiled reference _meto (meto/meto/__init__.py:21-50)."""
+
+    def __init__(self, bins):
+        import _meto
+        self.impl = _meto.Engine_LR_ABSCO(bins, False)
+
+    def decode(self, tokens):
+        v, f, t = self.impl.decode(list(map(int, tokens)))
+        return np.asarray(v), np.asarray(f), np.asarray(t)
+
+
+def run_generate(model, opt, cond, num_faces, max_new, mode, seed=None):
+    record = {'logits': [], 'scores': []}
+
+    def fake_generate(**kw):
+        return hf_sample_restated(model.mesh_decoder, kw['inputs_embeds'], kw['eos_token_id'], kw['max_new_tokens'],
+                                  kw['prefix_allowed_tokens_fn'], do_sample=kw.get('do_sample', False),
+                                  top_k=kw.get('top_k'), record=record)
+
+    model.mesh_decoder.generate = fake_generate
+    model.opt.generate_mode = mode
+    if seed is not None:
+        torch.manual_seed(seed)
+    with torch.no_grad():
+        meshes, toks = model.generate(cond, num_faces=num_faces, max_new_tokens=max_new,
+                                      tokenizer=RefTokenizer(opt.discrete_bins), clean=True)
+    return toks[0], torch.stack(record['logits']).numpy(), torch.stack(record['scores']).numpy(), meshes[0]
+
+
+def gen_model_goldens(synth, name, opt, steps, num_faces, sample_steps=0, tf_len=0):
+    print(f'[gen] {name}: building reference LMM ...', flush=True)
+    model, sd = build_reference_model(synth, opt, seed=0, eos_logit=-30.0)
+    cond = synth.synth_point_cloud(seed=0, n=opt.point_num)
+    out = {}
+    with torch.no_grad():
+        post = model.point_encoder(cond)
+        out['latents'] = post.mode()[0].numpy()
+        ce = model.encode_cond(cond, torch.full((1,), num_faces, dtype=torch.long))['cond_embeds'][0].numpy()
+    out['cond_embeds_head'] = ce[:4]
+    out['cond_embeds_tail'] = ce[-2:]
+    out['cond_embeds_sum'] = ce.astype(np.float64).sum(0)
+    toks, logits, scores, mesh = run_generate(model, opt, cond, num_faces, steps, 'greedy')
+    out['greedy_tokens'] = toks
+    out['greedy_logits'] = logits
+    out['mesh_vertices'] = mesh.vertices
+    out['mesh_faces'] = mesh.faces
+    print(f'[gen] {name}: greedy tokens[:16] = {toks[:16]}', flush=True)
+    if sample_steps:
+        toks, logits, scores, _ = run_generate(model, opt, cond, num_faces, sample_steps, 'sample', seed=1234)
+        out['sample_tokens'] = toks
+        out['sample_logits'] = logits
+    if tf_len:
+        # teacher-forced forward (core/models.py:147-202) on grammar-valid random tokens, dense causal
+        B = 2
+        rng = np.random.RandomState(7)
+        body = grammar_tokens(rng, tf_len, opt.discrete_bins)
+        toks_tf = np.stack([np.concatenate([[1], np.roll(body, 4 * b), [2]]) for b in range(B)])
+        P = opt.num_cond_tokens
+        labels = np.concatenate([np.full((B, P + 1), -100), toks_tf[:, 1:]], axis=1)
+        conds = torch.cat([synth.synth_point_cloud(seed=b, n=opt.point_num) for b in range(B)])
+        data = dict(conds=conds, tokens=torch.from_numpy(toks_tf).long(), labels=torch.from_numpy(labels).long(),
+                    masks=torch.ones(labels.shape, dtype=torch.bool), num_faces=torch.tensor([num_faces, 2500]),
+                    num_tokens=torch.tensor([tf_len, tf_len]))
+        with torch.no_grad():
+            res = model(data)
+        out['tf_tokens'] = toks_tf
+        out['tf_labels'] = labels
+        out['tf_num_faces'] = np.array([num_faces, 2500])
+        out['tf_loss'] = np.array([float(res['loss']), float(res['loss_ce']), float(res['loss_kl'])])
+        out['tf_logits_tail'] = res['logits'][:, -8:].numpy()
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **out)
+    print(f'[gen] wrote {name}.npz', flush=True)
+
+
+def grammar_tokens(rng, n, bins):
+    """Random FSM-valid stream (BOM + 9 coords, then L/R + 3 coords ...), already +3 offset, length n."""
+    t = [5] + list(rng.randint(6, 6 + bins, size=9))
+    while len(t) + 4 <= n:
+        if rng.rand() < 0.05 and len(t) + 10 <= n:
+            t += [5] + list(rng.randint(6, 6 + bins, size=9))
+        else:
+            t += [int(rng.choice([3, 4]))] + list(rng.randint(6, 6 + bins, size=3))
+    while len(t) < n:
+        t.append(int(rng.randint(6, 6 + bins)))
+    return np.asarray(t[:n], dtype=np.int64)
+
+
+def fixture_meshes():
+    """The inline meshes of /root/reference/meto/tests/engine.py:39-118 are rebuilt procedurally here in
+    tests/meshes.py (shared with the tests); sphere/annulus need trimesh (absent) and are replaced by an
+    icosphere / annulus generated by our own code."""
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    import meshes
+    return meshes.all_meshes()
+
+
+def gen_meto_goldens():
+    import _meto
+    out = {}
+    names = []
+    for name, (v, f) in fixture_meshes().items():
+        for bins in (512, 2048):
+            eng = _meto.Engine_LR_ABSCO(bins, False)
+            tok, order, ftype = eng.encode(v.astype(np.float32).tolist(), f.astype(np.int32).tolist())
+            dv, df, dt = eng.decode(tok)
+            key = f'{name}_{bins}'
+            names.append(key)
+            out[key + '_tokens'] = np.asarray(tok, dtype=np.int32)
+            out[key + '_order'] = np.asarray(order, dtype=np.int32)
+            out[key + '_ftype'] = np.asarray(ftype, dtype=np.int32)
+            out[key + '_dv'] = np.asarray(dv, dtype=np.float64).reshape(-1, 3)
+            out[key + '_df'] = np.asarray(df, dtype=np.int32).reshape(-1, 3)
+            out[key + '_dt'] = np.asarray(dt, dtype=np.int32)
+    # random / malformed streams for the decoder (truncations, coord where an op is expected, empty)
+    rng = np.random.RandomState(11)
+    streams = [np.zeros(0, np.int64), grammar_tokens(rng, 4001, 512) - 3, grammar_tokens(rng, 57, 512) - 3,
+               grammar_tokens(rng, 9, 512) - 3, grammar_tokens(rng, 10, 512) - 3, grammar_tokens(rng, 12, 512) - 3]
+    bad = grammar_tokens(rng, 200, 512) - 3
+    bad[50] = 300  # make sure something breaks the op/coord alternation somewhere
+    streams.append(bad)
+    eng = _meto.Engine_LR_ABSCO(512, False)
+    for i, s in enumerate(streams):
+        dv, df, dt = eng.decode([int(x) for x in s])
+        out[f'stream{i}_tokens'] = s.astype(np.int32)
+        out[f'stream{i}_dv'] = np.asarray(dv, dtype=np.float64).reshape(-1, 3)
+        out[f'stream{i}_df'] = np.asarray(df, dtype=np.int32).reshape(-1, 3)
+        out[f'stream{i}_dt'] = np.asarray(dt, dtype=np.int32)
+    out['names'] = np.asarray(names)
+    out['n_streams'] = np.asarray(len(streams))
+    np.savez_compressed(os.path.join(GOLD, 'meto.npz'), **out)
+    print('[gen] wrote meto.npz', flush=True)
+
+
+def gen_meta(synth):
+    from core.options import config_defaults
+    from core.models import LMM
+    meta = {'options': {k: dataclasses.asdict(v) for k, v in config_defaults.items()}}
+    with open(os.path.join(GOLD, 'options.json'), 'w') as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    from core.utils import quantize_num_faces
+    q = {str(n): int(quantize_num_faces(n)) for n in (-1, 0, 1, 999, 1000, 1001, 2000, 2001, 4000, 4001, 8000, 8001, 10 ** 6)}
+    with open(os.path.join(GOLD, 'quantize_num_faces.json'), 'w') as f:
+        json.dump(q, f)
+    print('[gen] wrote options.json / quantize_num_faces.json', flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--only', default='all')
+    args = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    synth = import_reference()
+    torch.set_num_threads(os.cpu_count())
+    if args.only in ('all', 'meta'):
+        gen_meta(synth)
+    if args.only in ('all', 'meto'):
+        gen_meto_goldens()
+    if args.only in ('all', 'tiny'):
+        opt = synth.tiny_options()
+        gen_model_goldens(synth, 'tiny', opt, steps=160, num_faces=1000, sample_steps=64, tf_len=40)
+    if args.only in ('all', 'arae'):
+        from core.options import config_defaults
+        opt = dataclasses.replace(config_defaults['ArAE'], generate_mode='greedy')
+        gen_model_goldens(synth, 'arae', opt, steps=40, num_faces=1000)
+
+
+if __name__ == '__main__':
+    main()
