@@ -1,0 +1,48 @@
+// Parameter block of the persistent decode kernel (see decode_kernel.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace er {
+
+struct DecodeState {   // lives in device memory; carries the token loop across launches
+    int t;             // tokens generated so far (== FSM idx)
+    int L;             // rows in the KV cache (position of the next token)
+    int counter;       // FSM: coordinate tokens still owed
+    int last_tok;      // last token fed to the model
+    int done;          // EOS seen or max_new reached
+    int pad[3];
+};
+
+struct DecodeParams {
+    // dimensions
+    int C, H, F, V, layers;
+    int S;            // KV splits per head in the attention phase (H*S <= grid)
+    int Lmax;         // V-cache rows per head
+    int nkb;          // K-cache 32-key blocks per head (ceil(Lmax/32))
+    int ks_out, ks_fc2, ks_lm;   // k-slices per row for the skinny GEMV phases
+    // decoder weights, fp16, nn.Linear layout [out][in] (q,k,v rows concatenated in that order)
+    const __half *wqkv, *bqkv, *wo, *bo, *ln1_w, *ln1_b, *w1, *b1, *w2, *b2, *ln2_w, *ln2_b;
+    const __half *lm_head, *embd, *pos;
+    // KV cache: K blocked [layer][head][key/32][d/8][key%32][8], V natural [layer][head][key][96]
+    __half *kc, *vc;
+    // cross-CTA scratch (global, read back with ld.cg)
+    __half *q16, *y1, *h1, *y2;
+    float *part;      // [H][S][100]: o[96], m, l
+    float *logits;    // [V] fp32 lm_head output before the fp16 rounding
+    DecodeState *st;
+    unsigned *bar;    // grid barrier counter (zeroed by the host before each launch)
+    // io
+    int32_t *out_ids;        // [max_new]
+    float *out_logits;       // optional [max_new][V]
+    const int32_t *forced;   // optional teacher-forcing stream [max_new]
+    int max_new, steps, mode /*0 greedy, 1 sample*/, top_k, use_fsm, eos;
+    unsigned long long seed;
+};
+
+}  // namespace er
+
+size_t er_decode_smem_bytes(const er::DecodeParams& p, int sc_keys);
+cudaError_t er_decode_launch(const er::DecodeParams& p, int grid, size_t smem, cudaStream_t stream);
+int er_decode_max_grid(size_t smem);

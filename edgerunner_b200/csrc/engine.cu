@@ -1,0 +1,501 @@
+// Engine: owns packed fp16 weights, the KV cache and workspaces; implements the C ABI of include/edgerunner_b200.h
+// by orchestrating the kernels of this directory.  No CPU fallback anywhere: every entry point launches CUDA work
+// or fails with an error string.
+#include "../../include/edgerunner_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "decode_kernel.h"
+#include "kernels.h"
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t _e = (call);                                                                              \
+        if (_e != cudaSuccess) return set_err(ER_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+#define CKL(e, call) do { (e)->launches++; CK(call); } while (0)
+
+namespace {
+
+__global__ void convert_copy_kernel(const void* src, int dtype, int rows, int cols, int src_ld, __half* dst, int dst_ld) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * dst_ld) return;
+    const int r = i / dst_ld, c = i % dst_ld;
+    float v = 0.f;
+    if (c < cols) v = dtype == ER_DTYPE_F16 ? __half2float(((const __half*)src)[(size_t)r * src_ld + c]) : ((const float*)src)[(size_t)r * src_ld + c];
+    dst[i] = __float2half_rn(v);
+}
+__global__ void init_state_kernel(er::DecodeState* st, int L) {
+    st->t = 0; st->L = L; st->counter = 0; st->last_tok = 0; st->done = 0;
+}
+__global__ void finish_decode_kernel(const er::DecodeState* st, int32_t* out_len) { *out_len = st->t; }
+__global__ void tf_losses_kernel(const float* loss_sum, const int* count, const float* kl_sum, float kl_weight, int has_kl, float* losses) {
+    const float ce = *loss_sum / (float)max(*count, 1);
+    const float kl = has_kl ? 0.5f * *kl_sum : 0.f;
+    losses[1] = ce; losses[2] = kl; losses[0] = ce + (has_kl ? kl_weight * kl : 0.f);
+}
+
+struct Slot { __half* dst; int rows, cols, dst_ld; };
+
+}  // namespace
+
+struct er_engine {
+    er_config cfg;
+    int C, H, D, F, V, NL, P, E, EH, LQ, LD, LDP;
+    int Lmax, nkb, grid, S, sc_keys;
+    size_t dec_smem;
+    long long launches = 0;
+    std::vector<void*> allocs;
+    std::map<std::string, Slot> slots;
+    std::set<std::string> loaded;
+    bool finalized = false;
+    // decoder weights
+    __half *wqkv, *bqkv, *wo, *bo, *ln1w, *ln1b, *w1, *b1, *w2, *b2, *ln2w, *ln2b, *lm_head, *embd, *pos;
+    // encoder + conditioner weights
+    __half *qe, *basis, *mlp_w, *mlp_b, *ln_w, *ln_b, *cl1w, *cl1b, *cq_w, *cq_b, *ckv_w, *ckv_b, *co_w, *co_b, *cl2w, *cl2b;
+    __half *ff0w, *ff0b, *ff2w, *ff2b, *lin_w, *lin_b, *pc_w, *pc_b, *ncw, *ncb, *enf;
+    // cache + decode scratch
+    __half *kc, *vc, *q16, *y1, *h1, *y2;
+    float *part, *logits, *cond32;
+    er::DecodeState* st;
+    unsigned* bar;
+    int32_t* ids_dev;
+    int32_t *gen_ids_dev, *gen_len_dev;   // for er_generate_host
+    float* conds_dev_buf;
+    // dense workspace
+    int maxrows;
+    float* x32; __half *x16, *qkv16, *a16, *h16;
+    float* logits_all; float* tf_acc; int* tf_cnt;
+    __half* lat16;   // [B][LQ][LDP]
+    // encoder workspace
+    __half *emb16, *pf16, *kvx16, *kvo16, *qln16, *qq16, *ea16, *ex1, *ex1ln, *eff, *egg, *ex2, *pc16;
+    int cache_rows = 0;
+    int lat_batch_cap = 1;
+};
+
+template <typename T>
+static int dev_alloc(er_engine* e, T** p, size_t n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, n * sizeof(T) + 256));
+    e->allocs.push_back(q);
+    *p = (T*)q;
+    return ER_OK;
+}
+#define ALLOC(ptr, n) do { int _r = dev_alloc(e, &(ptr), (size_t)(n)); if (_r) return _r; } while (0)
+
+extern "C" const char* er_last_error(void) { return g_err; }
+extern "C" int er_version(void) { return 100; }
+
+static void add_slot(er_engine* e, const std::string& name, __half* dst, int rows, int cols, int dst_ld = 0) {
+    e->slots[name] = Slot{dst, rows, cols, dst_ld ? dst_ld : cols};
+}
+
+extern "C" int er_create(const er_config* cfg, er_engine** out) {
+    if (!cfg || !out) return set_err(ER_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(cfg->device));
+    er_engine* e = new er_engine();
+    e->cfg = *cfg;
+    const int C = e->C = cfg->hidden_dim, H = e->H = cfg->num_heads, F = e->F = cfg->ffn_dim, V = e->V = cfg->vocab_size;
+    const int NL = e->NL = cfg->num_layers, P = e->P = cfg->num_cond_tokens;
+    e->D = C / H;
+    if (e->D != 96 || C % 8 || F % 8) { delete e; return set_err(ER_ERR_INVALID, "decoder head_dim must be 96 (got %d), C,F multiples of 8", e->D); }
+    const int E = e->E = cfg->point_hidden_dim, LQ = e->LQ = cfg->point_latent_size, LD = e->LD = cfg->point_latent_dim;
+    e->EH = cfg->point_num_heads;
+    e->LDP = (LD + 7) / 8 * 8;
+    if (cfg->has_point_encoder && (E / e->EH != 64 || E % 8)) { delete e; return set_err(ER_ERR_INVALID, "encoder head_dim must be 64"); }
+    if (P != LQ + (cfg->use_num_face_cond ? 1 : 0)) { delete e; return set_err(ER_ERR_INVALID, "num_cond_tokens %d != latent_size %d + num_face token", P, LQ); }
+    const int Lmax = e->Lmax = (cfg->max_seq_rows + 31) / 32 * 32;
+    e->nkb = Lmax / 32;
+    if (Lmax > cfg->max_positions) {}  // positions are checked per call
+    // ---- weights ----------------------------------------------------------------------------------------------------------
+    ALLOC(e->wqkv, (size_t)NL * 3 * C * C); ALLOC(e->bqkv, (size_t)NL * 3 * C);
+    ALLOC(e->wo, (size_t)NL * C * C); ALLOC(e->bo, (size_t)NL * C);
+    ALLOC(e->ln1w, (size_t)NL * C); ALLOC(e->ln1b, (size_t)NL * C);
+    ALLOC(e->w1, (size_t)NL * F * C); ALLOC(e->b1, (size_t)NL * F);
+    ALLOC(e->w2, (size_t)NL * C * F); ALLOC(e->b2, (size_t)NL * C);
+    ALLOC(e->ln2w, (size_t)NL * C); ALLOC(e->ln2b, (size_t)NL * C);
+    ALLOC(e->lm_head, (size_t)V * C); ALLOC(e->embd, (size_t)V * C); ALLOC(e->pos, (size_t)cfg->max_positions * C);
+    char nm[256];
+    for (int i = 0; i < NL; i++) {
+        const char* pj[3] = {"q_proj", "k_proj", "v_proj"};
+        for (int j = 0; j < 3; j++) {
+            snprintf(nm, sizeof nm, "mesh_decoder.model.layers.%d.self_attn.%s.weight", i, pj[j]);
+            add_slot(e, nm, e->wqkv + ((size_t)i * 3 + j) * C * C, C, C);
+            snprintf(nm, sizeof nm, "mesh_decoder.model.layers.%d.self_attn.%s.bias", i, pj[j]);
+            add_slot(e, nm, e->bqkv + ((size_t)i * 3 + j) * C, 1, C);
+        }
+        auto L = [&](const char* s) { snprintf(nm, sizeof nm, "mesh_decoder.model.layers.%d.%s", i, s); return std::string(nm); };
+        add_slot(e, L("self_attn.out_proj.weight"), e->wo + (size_t)i * C * C, C, C);
+        add_slot(e, L("self_attn.out_proj.bias"), e->bo + (size_t)i * C, 1, C);
+        add_slot(e, L("self_attn_layer_norm.weight"), e->ln1w + (size_t)i * C, 1, C);
+        add_slot(e, L("self_attn_layer_norm.bias"), e->ln1b + (size_t)i * C, 1, C);
+        add_slot(e, L("fc1.weight"), e->w1 + (size_t)i * F * C, F, C);
+        add_slot(e, L("fc1.bias"), e->b1 + (size_t)i * F, 1, F);
+        add_slot(e, L("fc2.weight"), e->w2 + (size_t)i * C * F, C, F);
+        add_slot(e, L("fc2.bias"), e->b2 + (size_t)i * C, 1, C);
+        add_slot(e, L("final_layer_norm.weight"), e->ln2w + (size_t)i * C, 1, C);
+        add_slot(e, L("final_layer_norm.bias"), e->ln2b + (size_t)i * C, 1, C);
+    }
+    add_slot(e, "mesh_decoder.lm_head.weight", e->lm_head, V, C);
+    add_slot(e, "mesh_decoder.model.embd.weight", e->embd, V, C);
+    add_slot(e, "mesh_decoder.model.embed_positions.weight", e->pos, cfg->max_positions, C);
+    ALLOC(e->pc_w, (size_t)C * e->LDP); ALLOC(e->pc_b, C); ALLOC(e->ncw, C); ALLOC(e->ncb, C);
+    add_slot(e, "proj_cond.weight", e->pc_w, C, LD, e->LDP);
+    add_slot(e, "proj_cond.bias", e->pc_b, 1, C);
+    add_slot(e, "norm_cond.weight", e->ncw, 1, C);
+    add_slot(e, "norm_cond.bias", e->ncb, 1, C);
+    if (cfg->use_num_face_cond) { ALLOC(e->enf, (size_t)10 * C); add_slot(e, "embed_num_face.weight", e->enf, 10, C); }
+    if (cfg->has_point_encoder) {
+        ALLOC(e->qe, (size_t)LQ * E); ALLOC(e->basis, 72); ALLOC(e->mlp_w, (size_t)E * 64); ALLOC(e->mlp_b, E);
+        ALLOC(e->ln_w, E); ALLOC(e->ln_b, E); ALLOC(e->cl1w, E); ALLOC(e->cl1b, E); ALLOC(e->cl2w, E); ALLOC(e->cl2b, E);
+        ALLOC(e->cq_w, (size_t)E * E); ALLOC(e->cq_b, E); ALLOC(e->ckv_w, (size_t)2 * E * E); ALLOC(e->ckv_b, 2 * E);
+        ALLOC(e->co_w, (size_t)E * E); ALLOC(e->co_b, E);
+        ALLOC(e->ff0w, (size_t)8 * E * E); ALLOC(e->ff0b, 8 * E); ALLOC(e->ff2w, (size_t)4 * E * E); ALLOC(e->ff2b, E);
+        ALLOC(e->lin_w, (size_t)e->LDP * E); ALLOC(e->lin_b, e->LDP);
+        CK(cudaMemset(e->lin_w, 0, (size_t)e->LDP * E * 2)); CK(cudaMemset(e->lin_b, 0, e->LDP * 2));
+        const std::string pe = "point_encoder.";
+        add_slot(e, pe + "query_embed", e->qe, LQ, E);
+        add_slot(e, pe + "point_embed.basis", e->basis, 3, 24);
+        add_slot(e, pe + "point_embed.mlp.weight", e->mlp_w, E, 51, 64);
+        add_slot(e, pe + "point_embed.mlp.bias", e->mlp_b, 1, E);
+        add_slot(e, pe + "ln.weight", e->ln_w, 1, E); add_slot(e, pe + "ln.bias", e->ln_b, 1, E);
+        add_slot(e, pe + "cross_att.ln1.weight", e->cl1w, 1, E); add_slot(e, pe + "cross_att.ln1.bias", e->cl1b, 1, E);
+        add_slot(e, pe + "cross_att.ln2.weight", e->cl2w, 1, E); add_slot(e, pe + "cross_att.ln2.bias", e->cl2b, 1, E);
+        add_slot(e, pe + "cross_att.att.q_proj.weight", e->cq_w, E, E); add_slot(e, pe + "cross_att.att.q_proj.bias", e->cq_b, 1, E);
+        add_slot(e, pe + "cross_att.att.k_proj.weight", e->ckv_w, E, E); add_slot(e, pe + "cross_att.att.k_proj.bias", e->ckv_b, 1, E);
+        add_slot(e, pe + "cross_att.att.v_proj.weight", e->ckv_w + (size_t)E * E, E, E); add_slot(e, pe + "cross_att.att.v_proj.bias", e->ckv_b + E, 1, E);
+        add_slot(e, pe + "cross_att.att.out_proj.weight", e->co_w, E, E); add_slot(e, pe + "cross_att.att.out_proj.bias", e->co_b, 1, E);
+        add_slot(e, pe + "cross_att.mlp.net.0.weight", e->ff0w, 8 * E, E); add_slot(e, pe + "cross_att.mlp.net.0.bias", e->ff0b, 1, 8 * E);
+        add_slot(e, pe + "cross_att.mlp.net.2.weight", e->ff2w, E, 4 * E); add_slot(e, pe + "cross_att.mlp.net.2.bias", e->ff2b, 1, E);
+        add_slot(e, pe + "linear.weight", e->lin_w, LD, E); add_slot(e, pe + "linear.bias", e->lin_b, 1, LD);
+    }
+    // ---- KV cache + decode scratch ---------------------------------------------------------------------------------------------
+    ALLOC(e->kc, (size_t)NL * H * e->nkb * 32 * 96); ALLOC(e->vc, (size_t)NL * H * Lmax * 96);
+    ALLOC(e->q16, C); ALLOC(e->y1, C); ALLOC(e->h1, F); ALLOC(e->y2, C);
+    ALLOC(e->logits, V); ALLOC(e->st, 1); ALLOC(e->bar, 4); ALLOC(e->cond32, (size_t)P * C);
+    ALLOC(e->ids_dev, 65536); ALLOC(e->gen_ids_dev, cfg->max_seq_rows + 8); ALLOC(e->gen_len_dev, 4);
+    ALLOC(e->conds_dev_buf, (size_t)(cfg->max_points > LQ * LD ? cfg->max_points * 3 : LQ * LD) + 16);
+    CK(cudaMemset(e->st, 0, sizeof(er::DecodeState)));
+    // decode launch geometry
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    e->grid = sms;
+    e->S = sms / H; if (e->S > 32) e->S = 32; if (e->S < 1) { delete e; return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
+    ALLOC(e->part, (size_t)H * e->S * 100);
+    e->sc_keys = ((e->nkb + e->S - 1) / e->S) * 32;
+    {
+        er::DecodeParams p{}; p.C = C; p.F = F; p.H = H; p.V = V; p.S = e->S;
+        e->dec_smem = er_decode_smem_bytes(p, e->sc_keys);
+        if (er_decode_max_grid(e->dec_smem) < sms) { delete e; return set_err(ER_ERR_CAPACITY, "decode kernel cannot be co-resident on %d SMs (smem %zu)", sms, e->dec_smem); }
+    }
+    // ---- dense workspace ----------------------------------------------------------------------------------------------------------
+    const int maxrows = e->maxrows = std::max(P + 4096, cfg->max_tf_rows) + 8;
+    ALLOC(e->x32, (size_t)maxrows * C); ALLOC(e->x16, (size_t)maxrows * C); ALLOC(e->qkv16, (size_t)maxrows * 3 * C);
+    ALLOC(e->a16, (size_t)maxrows * C); ALLOC(e->h16, (size_t)maxrows * F);
+    e->logits_all = nullptr;
+    if (cfg->max_tf_rows > 0) ALLOC(e->logits_all, (size_t)maxrows * V);
+    ALLOC(e->tf_acc, 4); ALLOC(e->tf_cnt, 4);
+    e->lat_batch_cap = cfg->max_tf_rows > 0 ? std::max(1, cfg->max_tf_rows / (P + 2)) : 1;
+    ALLOC(e->lat16, (size_t)e->lat_batch_cap * LQ * e->LDP); ALLOC(e->pc16, (size_t)LQ * C);
+    if (cfg->has_point_encoder) {
+        const int np = cfg->max_points;
+        ALLOC(e->emb16, (size_t)np * 64); ALLOC(e->pf16, (size_t)np * E); ALLOC(e->kvx16, (size_t)np * E); ALLOC(e->kvo16, (size_t)np * 2 * E);
+        ALLOC(e->qln16, (size_t)LQ * E); ALLOC(e->qq16, (size_t)LQ * E); ALLOC(e->ea16, (size_t)LQ * E); ALLOC(e->ex1, (size_t)LQ * E);
+        ALLOC(e->ex1ln, (size_t)LQ * E); ALLOC(e->eff, (size_t)LQ * 8 * E); ALLOC(e->egg, (size_t)LQ * 4 * E); ALLOC(e->ex2, (size_t)LQ * E);
+    }
+    CK(cudaDeviceSynchronize());
+    *out = e;
+    return ER_OK;
+}
+
+extern "C" void er_destroy(er_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : e->allocs) cudaFree(p);
+    delete e;
+}
+
+extern "C" int er_load_weight(er_engine* e, const char* name, const void* data_dev, int32_t dtype, const int64_t* shape, int32_t ndim, void* stream) {
+    if (!e || !name || !data_dev) return set_err(ER_ERR_INVALID, "null argument");
+    auto it = e->slots.find(name);
+    if (it == e->slots.end()) return set_err(ER_ERR_INVALID, "unknown state-dict key '%s'", name);
+    const Slot& s = it->second;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; i++) n *= shape[i];
+    if (n != (int64_t)s.rows * s.cols) return set_err(ER_ERR_INVALID, "shape mismatch for '%s': %lld elements, expected %d x %d", name, (long long)n, s.rows, s.cols);
+    if (dtype != ER_DTYPE_F16 && dtype != ER_DTYPE_F32) return set_err(ER_ERR_INVALID, "dtype");
+    const size_t total = (size_t)s.rows * s.dst_ld;
+    e->launches++;
+    convert_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(data_dev, dtype, s.rows, s.cols, s.cols, s.dst, s.dst_ld);
+    CK(cudaGetLastError());
+    e->loaded.insert(name);
+    e->finalized = false;
+    return ER_OK;
+}
+
+extern "C" int er_finalize_weights(er_engine* e, void* stream) {
+    if (!e) return set_err(ER_ERR_INVALID, "null engine");
+    for (auto& kv : e->slots)
+        if (!e->loaded.count(kv.first)) return set_err(ER_ERR_STATE, "weight '%s' was never loaded", kv.first.c_str());
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    e->finalized = true;
+    return ER_OK;
+}
+
+static er::GemmArgs mk_gemm(const __half* A, int lda, const __half* W, int ldw, const __half* bias, int M, int N, int K, int mode) {
+    er::GemmArgs g{};
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.M = M; g.N = N; g.K = K; g.mode = mode;
+    return g;
+}
+
+// PointEncoderEmbed.forward for one cloud -> lat16 [LQ][LDP] (point.py:186-206)
+static int encode_points(er_engine* e, const float* pts, int n, __half* lat, cudaStream_t st) {
+    const int E = e->E, LQ = e->LQ, EH = e->EH;
+    if (n > e->cfg.max_points) return set_err(ER_ERR_CAPACITY, "n_points %d > max_points %d", n, e->cfg.max_points);
+    CKL(e, er_point_embed(pts, e->basis, e->emb16, 64, n, st));
+    er::GemmArgs g = mk_gemm(e->emb16, 64, e->mlp_w, 64, e->mlp_b, n, E, 64, er::GEMM_F16);
+    g.out16 = e->pf16; g.ldo = E; CKL(e, er_gemm(g, st));
+    CKL(e, er_layernorm(nullptr, e->pf16, E, e->ln_w, e->ln_b, nullptr, e->kvx16, E, n, E, st));
+    CKL(e, er_layernorm(nullptr, e->qe, E, e->cl1w, e->cl1b, nullptr, e->qln16, E, LQ, E, st));
+    g = mk_gemm(e->qln16, E, e->cq_w, E, e->cq_b, LQ, E, E, er::GEMM_F16); g.out16 = e->qq16; g.ldo = E; CKL(e, er_gemm(g, st));
+    g = mk_gemm(e->kvx16, E, e->ckv_w, E, e->ckv_b, n, 2 * E, E, er::GEMM_F16); g.out16 = e->kvo16; g.ldo = 2 * E; CKL(e, er_gemm(g, st));
+    er::AttnArgs a{};
+    a.q = e->qq16; a.k = e->kvo16; a.v = e->kvo16 + E; a.out = e->ea16;
+    a.ldq = E; a.ldk = 2 * E; a.ldv = 2 * E; a.ldo = E; a.B = 1; a.H = EH; a.Nq = LQ; a.Nk = n; a.D = 64; a.causal = 0;
+    CKL(e, er_attention(a, st));
+    g = mk_gemm(e->ea16, E, e->co_w, E, e->co_b, LQ, E, E, er::GEMM_F16_RES16); g.out16 = e->ex1; g.ldo = E; g.res16 = e->qe; g.ldr = E; CKL(e, er_gemm(g, st));
+    CKL(e, er_layernorm(nullptr, e->ex1, E, e->cl2w, e->cl2b, nullptr, e->ex1ln, E, LQ, E, st));
+    g = mk_gemm(e->ex1ln, E, e->ff0w, E, e->ff0b, LQ, 8 * E, E, er::GEMM_F16); g.out16 = e->eff; g.ldo = 8 * E; CKL(e, er_gemm(g, st));
+    CKL(e, er_geglu(e->eff, e->egg, LQ, 4 * E, st));
+    g = mk_gemm(e->egg, 4 * E, e->ff2w, 4 * E, e->ff2b, LQ, E, 4 * E, er::GEMM_F16_RES16); g.out16 = e->ex2; g.ldo = E; g.res16 = e->ex1; g.ldr = E; CKL(e, er_gemm(g, st));
+    g = mk_gemm(e->ex2, E, e->lin_w, E, e->lin_b, LQ, e->LDP, E, er::GEMM_F16); g.out16 = lat; g.ldo = e->LDP; CKL(e, er_gemm(g, st));
+    return ER_OK;
+}
+
+// latents -> cond32 [P][C]: norm_cond(proj_cond(lat)) ++ embed_num_face[bucket]   (models.py:124,135-141)
+static int quantize_num_faces(int n) { return n <= 0 ? 0 : n <= 1000 ? 1 : n <= 2000 ? 2 : n <= 4000 ? 3 : n <= 8000 ? 4 : 5; }
+static int latents_to_cond(er_engine* e, const __half* lat, int num_faces, float* cond32, cudaStream_t st) {
+    const int C = e->C, LQ = e->LQ;
+    er::GemmArgs g = mk_gemm(lat, e->LDP, e->pc_w, e->LDP, e->pc_b, LQ, C, e->LDP, er::GEMM_F16);
+    g.out16 = e->pc16; g.ldo = C; CKL(e, er_gemm(g, st));
+    CKL(e, er_layernorm(nullptr, e->pc16, C, e->ncw, e->ncb, cond32, nullptr, C, LQ, C, st));
+    if (e->cfg.use_num_face_cond) CKL(e, er_f16_to_f32(e->enf + (size_t)quantize_num_faces(num_faces) * C, cond32 + (size_t)LQ * C, C, st));
+    return ER_OK;
+}
+
+static int encode_one(er_engine* e, const float* conds_dev, int n_points, int is_latent, int num_faces, __half* lat, float* cond32, cudaStream_t st) {
+    if (is_latent) {
+        if (n_points != e->LQ) return set_err(ER_ERR_INVALID, "latent rows %d != latent_size %d", n_points, e->LQ);
+        e->launches++;
+        convert_copy_kernel<<<(unsigned)(((size_t)e->LQ * e->LDP + 255) / 256), 256, 0, st>>>(conds_dev, ER_DTYPE_F32, e->LQ, e->LD, e->LD, lat, e->LDP);
+        CK(cudaGetLastError());
+    } else {
+        if (!e->cfg.has_point_encoder) return set_err(ER_ERR_STATE, "engine was created without a point encoder");
+        int r = encode_points(e, conds_dev, n_points, lat, st);
+        if (r) return r;
+    }
+    return latents_to_cond(e, lat, num_faces, cond32, st);
+}
+
+extern "C" int er_encode_cond(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, int32_t num_faces,
+                              float* cond_embeds_out_dev, void* latents_out_dev, void* stream) {
+    if (!e || !conds_dev) return set_err(ER_ERR_INVALID, "null argument");
+    if (!e->finalized) return set_err(ER_ERR_STATE, "weights not finalized");
+    cudaStream_t st = (cudaStream_t)stream;
+    int r = encode_one(e, conds_dev, n_points, is_latent, num_faces, e->lat16, e->cond32, st);
+    if (r) return r;
+    if (cond_embeds_out_dev) CK(cudaMemcpyAsync(cond_embeds_out_dev, e->cond32, (size_t)e->P * e->C * 4, cudaMemcpyDeviceToDevice, st));
+    if (latents_out_dev) CK(cudaMemcpy2DAsync(latents_out_dev, e->LD * 2, e->lat16, e->LDP * 2, e->LD * 2, e->LQ, cudaMemcpyDeviceToDevice, st));
+    return ER_OK;
+}
+
+// 24 x OPTDecoderLayer on M = B*N rows held in x32/x16 (modeling_opt.py:264-288, 185-232); store_kv: fill the decode cache
+static int decoder_layers(er_engine* e, int B, int N, bool store_kv, cudaStream_t st) {
+    const int C = e->C, F = e->F, H = e->H, M = B * N;
+    for (int l = 0; l < e->NL; l++) {
+        er::GemmArgs g = mk_gemm(e->x16, C, e->wqkv + (size_t)l * 3 * C * C, C, e->bqkv + (size_t)l * 3 * C, M, 3 * C, C, er::GEMM_F16);
+        g.out16 = e->qkv16; g.ldo = 3 * C; CKL(e, er_gemm(g, st));
+        if (store_kv) CKL(e, er_kv_store(e->qkv16, N, C, H, l, 0, e->Lmax, e->nkb, e->kc, e->vc, st));
+        er::AttnArgs a{};
+        a.q = e->qkv16; a.k = e->qkv16 + C; a.v = e->qkv16 + 2 * C; a.out = e->a16;
+        a.ldq = a.ldk = a.ldv = 3 * C; a.ldo = C; a.q_bs = a.k_bs = a.v_bs = (long long)N * 3 * C; a.o_bs = (long long)N * C;
+        a.B = B; a.H = H; a.Nq = N; a.Nk = N; a.D = 96; a.causal = 1;
+        CKL(e, er_attention(a, st));
+        g = mk_gemm(e->a16, C, e->wo + (size_t)l * C * C, C, e->bo + (size_t)l * C, M, C, C, er::GEMM_F32_RES32);
+        g.out32 = e->x32; g.ldo = C; g.res32 = e->x32; g.ldr = C; CKL(e, er_gemm(g, st));
+        CKL(e, er_layernorm(e->x32, nullptr, C, e->ln1w + (size_t)l * C, e->ln1b + (size_t)l * C, e->x32, e->x16, C, M, C, st));
+        g = mk_gemm(e->x16, C, e->w1 + (size_t)l * F * C, C, e->b1 + (size_t)l * F, M, F, C, er::GEMM_F16_RELU);
+        g.out16 = e->h16; g.ldo = F; CKL(e, er_gemm(g, st));
+        g = mk_gemm(e->h16, F, e->w2 + (size_t)l * C * F, F, e->b2 + (size_t)l * C, M, C, F, er::GEMM_F32_RES32);
+        g.out32 = e->x32; g.ldo = C; g.res32 = e->x32; g.ldr = C; CKL(e, er_gemm(g, st));
+        CKL(e, er_layernorm(e->x32, nullptr, C, e->ln2w + (size_t)l * C, e->ln2b + (size_t)l * C, e->x32, e->x16, C, M, C, st));
+    }
+    return ER_OK;
+}
+
+extern "C" int er_prefill(er_engine* e, const int32_t* prompt_ids_host, int32_t n_prompt, void* stream) {
+    if (!e || !prompt_ids_host || n_prompt < 1) return set_err(ER_ERR_INVALID, "bad prompt");
+    if (!e->finalized) return set_err(ER_ERR_STATE, "weights not finalized");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = e->P + n_prompt, C = e->C;
+    if (N > e->maxrows || N > e->Lmax || N > e->cfg.max_positions || n_prompt > 65536) return set_err(ER_ERR_CAPACITY, "prefix of %d rows exceeds capacity", N);
+    for (int i = 0; i < n_prompt; i++)
+        if (prompt_ids_host[i] < 0 || prompt_ids_host[i] >= e->V) return set_err(ER_ERR_INVALID, "prompt id %d out of range", prompt_ids_host[i]);
+    CK(cudaMemcpyAsync(e->ids_dev, prompt_ids_host, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, st));
+    CKL(e, er_embed_prefix(e->cond32, e->P, e->ids_dev, n_prompt, e->embd, e->pos, C, e->x32, e->x16, st));
+    int r = decoder_layers(e, 1, N, true, st);
+    if (r) return r;
+    er::GemmArgs g = mk_gemm(e->x16 + (size_t)(N - 1) * C, C, e->lm_head, C, nullptr, 1, e->V, C, er::GEMM_F32);
+    g.out32 = e->logits; g.ldo = e->V; CKL(e, er_gemm(g, st));
+    e->launches++;
+    init_state_kernel<<<1, 1, 0, st>>>(e->st, N);
+    CK(cudaGetLastError());
+    e->cache_rows = N;
+    return ER_OK;
+}
+
+static int pick_ks(int K, int rows_per_cta) {   // k-slices per row so that a CTA has >= ~2 units per warp
+    int best = 1;
+    for (int ks = 1; ks <= 16; ks++) {
+        if (K % ks || (K / ks) % 8) continue;
+        best = ks;
+        if (rows_per_cta * ks >= 32 && (K / ks) % 256 == 0) return ks;
+    }
+    for (int ks = 1; ks <= 16; ks++)
+        if (K % ks == 0 && (K / ks) % 8 == 0 && rows_per_cta * ks >= 32) return ks;
+    return best;
+}
+
+extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int32_t top_k, uint64_t seed, int32_t use_tokenizer_fsm,
+                         int32_t tokens_per_launch, int32_t* out_ids_dev, int32_t* out_len_dev, float* out_logits_dev,
+                         const int32_t* forced_ids_dev, void* stream) {
+    if (!e || !out_ids_dev || max_new_tokens < 1) return set_err(ER_ERR_INVALID, "bad argument");
+    if (e->cache_rows <= 0) return set_err(ER_ERR_STATE, "er_prefill has not run");
+    if (e->cache_rows + max_new_tokens > e->Lmax || e->cache_rows + max_new_tokens > e->cfg.max_positions)
+        return set_err(ER_ERR_CAPACITY, "cache rows %d + max_new_tokens %d exceed capacity %d", e->cache_rows, max_new_tokens, e->Lmax);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = e->C, F = e->F, V = e->V, G = e->grid;
+    er::DecodeParams p{};
+    p.C = C; p.H = e->H; p.F = F; p.V = V; p.layers = e->NL; p.S = e->S; p.Lmax = e->Lmax; p.nkb = e->nkb;
+    p.ks_out = pick_ks(C, (C + G - 1) / G); p.ks_fc2 = pick_ks(F, (C + G - 1) / G); p.ks_lm = pick_ks(C, (V + G - 1) / G);
+    const int max_units = std::max(std::max((3 * C + G - 1) / G + 1, (F + G - 1) / G + 1),
+                                   std::max(((C + G - 1) / G + 1) * std::max(p.ks_out, p.ks_fc2), ((V + G - 1) / G + 1) * p.ks_lm));
+    if (max_units > 256) return set_err(ER_ERR_CAPACITY, "model too wide for %d SMs (units %d)", G, max_units);
+    p.wqkv = e->wqkv; p.bqkv = e->bqkv; p.wo = e->wo; p.bo = e->bo; p.ln1_w = e->ln1w; p.ln1_b = e->ln1b;
+    p.w1 = e->w1; p.b1 = e->b1; p.w2 = e->w2; p.b2 = e->b2; p.ln2_w = e->ln2w; p.ln2_b = e->ln2b;
+    p.lm_head = e->lm_head; p.embd = e->embd; p.pos = e->pos;
+    p.kc = e->kc; p.vc = e->vc; p.q16 = e->q16; p.y1 = e->y1; p.h1 = e->h1; p.y2 = e->y2; p.part = e->part; p.logits = e->logits;
+    p.st = e->st; p.bar = e->bar;
+    p.out_ids = out_ids_dev; p.out_logits = out_logits_dev; p.forced = forced_ids_dev;
+    p.max_new = max_new_tokens; p.mode = mode; p.top_k = top_k > 0 ? top_k : 10; p.use_fsm = use_tokenizer_fsm; p.eos = e->cfg.eos_token_id;
+    p.seed = seed;
+    const int chunk = tokens_per_launch > 0 ? tokens_per_launch : max_new_tokens;
+    for (int done = 0; done < max_new_tokens; done += chunk) {
+        p.steps = std::min(chunk, max_new_tokens - done);
+        CK(cudaMemsetAsync(e->bar, 0, 16, st));
+        CKL(e, er_decode_launch(p, G, e->dec_smem, st));
+    }
+    if (out_len_dev) {
+        e->launches++;
+        finish_decode_kernel<<<1, 1, 0, st>>>(e->st, out_len_dev);
+        CK(cudaGetLastError());
+    }
+    e->cache_rows += max_new_tokens - 1;   // upper bound; exact value lives in the device state
+    return ER_OK;
+}
+
+extern "C" int er_generate_host(er_engine* e, const float* conds_host, int32_t n_points, int32_t is_latent, int32_t num_faces,
+                                const int32_t* resume_ids_host, int32_t n_resume, int32_t max_new_tokens, int32_t mode, int32_t top_k,
+                                uint64_t seed, int32_t use_tokenizer_fsm, int32_t* out_ids_host, int32_t* out_len_host) {
+    if (!e || !conds_host || !out_ids_host || !out_len_host) return set_err(ER_ERR_INVALID, "null argument");
+    cudaStream_t st = 0;
+    const size_t nfl = is_latent ? (size_t)e->LQ * e->LD : (size_t)n_points * 3;
+    if (!is_latent && n_points > e->cfg.max_points) return set_err(ER_ERR_CAPACITY, "n_points");
+    CK(cudaMemcpyAsync(e->conds_dev_buf, conds_host, nfl * 4, cudaMemcpyHostToDevice, st));
+    int r = er_encode_cond(e, e->conds_dev_buf, n_points, is_latent, num_faces, nullptr, nullptr, st);
+    if (r) return r;
+    std::vector<int32_t> prompt;
+    prompt.push_back(e->cfg.bos_token_id);
+    for (int i = 0; i < n_resume; i++) prompt.push_back(resume_ids_host[i]);
+    r = er_prefill(e, prompt.data(), (int)prompt.size(), st);
+    if (r) return r;
+    if (max_new_tokens > e->cfg.max_seq_rows) return set_err(ER_ERR_CAPACITY, "max_new_tokens");
+    r = er_decode(e, max_new_tokens, mode, top_k, seed, use_tokenizer_fsm, 0, e->gen_ids_dev, e->gen_len_dev, nullptr, nullptr, st);
+    if (r) return r;
+    CK(cudaMemcpyAsync(out_len_host, e->gen_len_dev, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(out_ids_host, e->gen_ids_dev, (size_t)(*out_len_host) * 4, cudaMemcpyDeviceToHost));
+    return ER_OK;
+}
+
+extern "C" int er_forward_tf(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, const int32_t* tokens_dev,
+                             const int64_t* labels_dev, const int32_t* num_faces_host, int32_t B, int32_t T, float kl_weight,
+                             float* losses_dev, float* logits_out_dev, void* stream) {
+    if (!e || !conds_dev || !tokens_dev || !labels_dev || !num_faces_host || !losses_dev) return set_err(ER_ERR_INVALID, "null argument");
+    if (!e->finalized) return set_err(ER_ERR_STATE, "weights not finalized");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = e->C, P = e->P, N = P + T, M = B * N, V = e->V;
+    if (M > e->maxrows || !e->logits_all || B > e->lat_batch_cap) return set_err(ER_ERR_CAPACITY, "teacher-forced batch of %d rows exceeds max_tf_rows", M);
+    if (N > e->cfg.max_positions) return set_err(ER_ERR_CAPACITY, "sequence longer than the position table");
+    const size_t cstride = is_latent ? (size_t)e->LQ * e->LD : (size_t)n_points * 3;
+    for (int b = 0; b < B; b++) {
+        // cond rows go straight into x32 rows [b*N, b*N+P); embed_prefix then adds positions in place
+        float* cond_rows = e->x32 + (size_t)b * N * C;
+        int r = encode_one(e, conds_dev + b * cstride, n_points, is_latent, num_faces_host[b], e->lat16 + (size_t)b * e->LQ * e->LDP, cond_rows, st);
+        if (r) return r;
+        CKL(e, er_embed_prefix(cond_rows, P, tokens_dev + (size_t)b * T, T, e->embd, e->pos, C, cond_rows, e->x16 + (size_t)b * N * C, st));
+    }
+    int r = decoder_layers(e, B, N, false, st);
+    if (r) return r;
+    er::GemmArgs g = mk_gemm(e->x16, C, e->lm_head, C, nullptr, M, V, C, er::GEMM_F32);
+    g.out32 = e->logits_all; g.ldo = V; CKL(e, er_gemm(g, st));
+    CK(cudaMemsetAsync(e->tf_acc, 0, 16, st));
+    CK(cudaMemsetAsync(e->tf_cnt, 0, 16, st));
+    for (int b = 0; b < B; b++)
+        CKL(e, er_cross_entropy(e->logits_all + (size_t)b * N * V, V, labels_dev + (size_t)b * N + 1, N - 1, V, e->tf_acc, e->tf_cnt, st));
+    const int has_kl = !is_latent;
+    if (has_kl) CKL(e, er_sum_squares(e->lat16, (size_t)B * e->LQ * e->LDP, e->tf_acc + 1, st));
+    e->launches++;
+    tf_losses_kernel<<<1, 1, 0, st>>>(e->tf_acc, e->tf_cnt, e->tf_acc + 1, kl_weight, has_kl, losses_dev);
+    CK(cudaGetLastError());
+    if (logits_out_dev) CK(cudaMemcpyAsync(logits_out_dev, e->logits_all, (size_t)M * V * 4, cudaMemcpyDeviceToDevice, st));
+    return ER_OK;
+}
+
+extern "C" int64_t er_weight_bytes_per_token(const er_engine* e) {
+    const int64_t C = e->C, F = e->F;
+    const int64_t per_layer = 4 * (C * C + C) + F * C + F + C * F + C + 4 * C;
+    return 2 * (per_layer * e->NL + (int64_t)e->V * C);
+}
+extern "C" int64_t er_kv_bytes_per_row(const er_engine* e) { return (int64_t)e->NL * 2 * e->C * 2; }
+extern "C" int32_t er_cache_rows(const er_engine* e) { return e->cache_rows; }
+extern "C" int64_t er_kernel_launches(const er_engine* e) { return e->launches; }
+
+extern "C" int er_attention_bnhd(const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev, int32_t B, int32_t Nq, int32_t Nk,
+                                 int32_t H, int32_t D, int32_t causal, void* stream) {
+    if (!q_dev || !k_dev || !v_dev || !out_dev) return set_err(ER_ERR_INVALID, "null argument");
+    if (D != 64 && D != 96) return set_err(ER_ERR_INVALID, "head_dim %d not supported (64 or 96)", D);
+    if (causal && Nq != Nk) return set_err(ER_ERR_INVALID, "causal attention needs Nq == Nk");
+    er::AttnArgs a{};
+    a.q = (const __half*)q_dev; a.k = (const __half*)k_dev; a.v = (const __half*)v_dev; a.out = (__half*)out_dev;
+    a.ldq = a.ldk = a.ldv = a.ldo = H * D;
+    a.q_bs = a.o_bs = (long long)Nq * H * D; a.k_bs = a.v_bs = (long long)Nk * H * D;
+    a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.D = D; a.causal = causal;
+    CK(er_attention(a, (cudaStream_t)stream));
+    return ER_OK;
+}

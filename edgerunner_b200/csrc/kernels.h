@@ -1,0 +1,60 @@
+// Host-callable launchers of the dense (multi-row) kernels: prefill, point encoder, teacher-forced forward.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace er {
+
+enum GemmMode {
+    GEMM_F16 = 0,        // out16 = f16(acc + bias)
+    GEMM_F16_RELU = 1,   // out16 = relu(f16(acc + bias))
+    GEMM_F16_RES16 = 2,  // out16 = f16( f16(acc + bias) + res16 )        (fp16 + fp16 residual, encoder)
+    GEMM_F32_RES32 = 3,  // out32 = res32 + f16(acc + bias)               (fp32 + fp16 residual, decoder)
+    GEMM_F32 = 4,        // out32 = acc (+ bias)                          (logits before the fp16 store)
+};
+
+struct GemmArgs {
+    const __half* A; int lda;       // [M][K]
+    const __half* W; int ldw;       // [N][K]  (nn.Linear weight)
+    const __half* bias;             // [N] or null
+    int M, N, K;
+    int mode;
+    __half* out16; float* out32; int ldo;
+    const __half* res16; const float* res32; int ldr;
+};
+
+struct AttnArgs {   // softmax(q k^T / sqrt(D)) v ; q [B][Nq][H][D], k/v [B][Nk][H][D] with element strides
+    const __half *q, *k, *v; __half* out;
+    long long q_bs, k_bs, v_bs, o_bs;   // batch strides (elements)
+    int ldq, ldk, ldv, ldo;             // row strides (elements); head h starts at h*D inside a row
+    int B, H, Nq, Nk, D, causal;
+};
+
+}  // namespace er
+
+cudaError_t er_gemm(const er::GemmArgs& g, cudaStream_t stream);
+cudaError_t er_attention(const er::AttnArgs& a, cudaStream_t stream);
+
+// ---- elementwise / row kernels (elementwise.cu) ----------------------------------------------------------------------
+// LayerNorm rows (eps 1e-5, fp16 affine params, fp32 math): in32 or in16 -> out32 (optional) and out16 (optional)
+cudaError_t er_layernorm(const float* in32, const __half* in16, int ld_in, const __half* gamma, const __half* beta,
+                         float* out32, __half* out16, int ld_out, int M, int C, cudaStream_t stream);
+// Fourier point embedding (point.py:54-63): xyz fp32 [n][3] -> A16 [n][ldo]: sin(24) | cos(24) | xyz | zero pad
+cudaError_t er_point_embed(const float* xyz, const __half* basis /*[3][24]*/, __half* out, int ldo, int n, cudaStream_t stream);
+// GEGLU (point.py:69-72): h [M][2F] -> out [M][F] = f16( a * f16(gelu_erf(g)) )
+cudaError_t er_geglu(const __half* h, __half* out, int M, int F, cudaStream_t stream);
+// Prefix embeddings (models.py:228-233 + modeling_opt.py:355-357): rows [0,P) from cond32, rows [P,P+n) = embd[ids];
+// + pos[row0 + i]; writes x32 and its fp16 copy.
+cudaError_t er_embed_prefix(const float* cond32, int P, const int32_t* ids_dev, int n_ids, const __half* embd, const __half* pos,
+                            int C, float* x32, __half* x16, cudaStream_t stream);
+// f16 -> f32 row copy (num-face embedding row appended to cond_embeds)
+cudaError_t er_f16_to_f32(const __half* src, float* dst, int n, cudaStream_t stream);
+cudaError_t er_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t stream);
+// Scatter k,v rows of qkv16 [N][3C] (positions pos0..pos0+N) into the decode kernel's KV cache layouts
+cudaError_t er_kv_store(const __half* qkv16, int N, int C, int H, int layer, int pos0, int Lmax, int nkb, __half* kc, __half* vc,
+                        cudaStream_t stream);
+// mean cross-entropy over rows with label != -100 on fp16-rounded logits (modeling_opt.py:500-505); loss_sum/count accumulate
+cudaError_t er_cross_entropy(const float* logits_pre, int ld, const int64_t* labels, int M, int V, float* loss_sum, int* count,
+                             cudaStream_t stream);
+cudaError_t er_sum_squares(const __half* x, size_t n, float* out, cudaStream_t stream);

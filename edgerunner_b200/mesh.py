@@ -1,0 +1,76 @@
+"""Minimal triangle-mesh holder used when ``trimesh`` is not installed (it is absent from the target image).
+
+Covers what ``save_mesh`` / ``infer.py`` touch: ``vertices`` / ``faces``, ``merge_vertices``, ``unique_faces`` +
+``update_faces``, ``fix_normals`` (orientation propagation per connected component) and ``export`` to .ply/.obj.
+Host-side post-processing only; the reference delegates this to third-party trimesh (parity unpinned).
+"""
+
+import numpy as np
+
+
+class SimpleMesh:
+    def __init__(self, vertices=None, faces=None, **_):
+        self.vertices = np.asarray(vertices, dtype=np.float64).reshape(-1, 3)
+        self.faces = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
+
+    def merge_vertices(self):
+        if len(self.vertices) == 0:
+            return
+        uniq, inv = np.unique(np.round(self.vertices, 8), axis=0, return_inverse=True)
+        self.vertices, self.faces = uniq, inv.reshape(-1)[self.faces]
+
+    def unique_faces(self):
+        key = np.sort(self.faces, axis=1)
+        _, first = np.unique(key, axis=0, return_index=True)
+        mask = np.zeros(len(self.faces), dtype=bool)
+        mask[first] = True
+        return mask
+
+    def update_faces(self, mask):
+        self.faces = self.faces[mask]
+
+    def fix_normals(self):
+        """Make winding consistent inside each edge-connected component (BFS over shared edges)."""
+        f = self.faces
+        if len(f) == 0:
+            return
+        edges = {}
+        for i, (a, b, c) in enumerate(f):
+            for u, v in ((a, b), (b, c), (c, a)):
+                edges.setdefault((min(u, v), max(u, v)), []).append((i, u, v))
+        seen = np.zeros(len(f), dtype=bool)
+        for start in range(len(f)):
+            if seen[start]:
+                continue
+            seen[start] = True
+            stack = [start]
+            while stack:
+                i = stack.pop()
+                a, b, c = self.faces[i]
+                for u, v in ((a, b), (b, c), (c, a)):
+                    for j, uu, vv in edges[(min(u, v), max(u, v))]:
+                        if j == i or seen[j]:
+                            continue
+                        # consistent neighbours traverse the shared edge in opposite directions
+                        ja, jb, jc = self.faces[j]
+                        dir_j = [(ja, jb), (jb, jc), (jc, ja)]
+                        if (u, v) in dir_j:
+                            self.faces[j] = self.faces[j][::-1]
+                        seen[j] = True
+                        stack.append(j)
+
+    def export(self, path):
+        ext = str(path).rsplit('.', 1)[-1].lower()
+        with open(path, 'w') as fh:
+            if ext == 'ply':
+                fh.write('ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n'
+                         'element face %d\nproperty list uchar int vertex_indices\nend_header\n' % (len(self.vertices), len(self.faces)))
+                for v in self.vertices:
+                    fh.write('%.8g %.8g %.8g\n' % tuple(v))
+                for t in self.faces:
+                    fh.write('3 %d %d %d\n' % tuple(t))
+            else:
+                for v in self.vertices:
+                    fh.write('v %.8g %.8g %.8g\n' % tuple(v))
+                for t in self.faces:
+                    fh.write('f %d %d %d\n' % tuple(t + 1))

@@ -1,0 +1,123 @@
+/*
+ * edgerunner_b200 — C ABI of the B200-native mesh-token decode path.
+ *
+ * The reference (NVlabs/EdgeRunner) has no FFI/plugin registry: its seams are Python call sites plus one pybind
+ * module.  Each entry point below names the reference interface it stands in for; the Python
+ * mirror of those interfaces (core/models.py, meto/__init__.py in this repository) binds them with ctypes, and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  `*_dev` pointers are CUDA device pointers in the
+ * current context of `cfg.device`; `stream` is a cudaStream_t passed as void* (NULL = default stream); everything is
+ * asynchronous on that stream unless the name ends in `_host`.  The caller owns every buffer it passes; the engine
+ * owns its packed weights, KV cache and workspace.  Return value: 0 = ok, negative = error, message via
+ * er_last_error() (thread-local).  One engine per device per thread; no Python GIL is ever taken.
+ */
+#ifndef EDGERUNNER_B200_H
+#define EDGERUNNER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ER_OK 0
+#define ER_ERR_INVALID (-1)
+#define ER_ERR_CUDA (-2)
+#define ER_ERR_STATE (-3)
+#define ER_ERR_CAPACITY (-4)
+
+#define ER_DTYPE_F16 0
+#define ER_DTYPE_F32 1
+
+#define ER_MODE_GREEDY 0
+#define ER_MODE_SAMPLE 1
+
+typedef struct er_engine er_engine;
+
+/* Model dimensions: the fields of core/options.py:17-148 that the path reads (core/models.py:33-99). */
+typedef struct er_config {
+    int32_t device;
+    /* mesh decoder (ShapeOPTConfig, core/transformer/modeling_opt.py:86-134) */
+    int32_t hidden_dim, num_heads, num_layers, ffn_dim, vocab_size, max_positions;
+    int32_t num_cond_tokens;      /* P: latent tokens (+1 if use_num_face_cond) */
+    int32_t use_num_face_cond;
+    int32_t bos_token_id, eos_token_id, pad_token_id;
+    /* point encoder (PointEncoderEmbed, core/transformer/point.py:172-206); has_point_encoder = 0 for point_latent */
+    int32_t has_point_encoder;
+    int32_t point_hidden_dim, point_num_heads, point_latent_size, point_latent_dim;
+    /* capacity */
+    int32_t max_seq_rows;         /* KV-cache rows per head: prefix + prompt + max_new_tokens */
+    int32_t max_points;           /* largest point cloud passed to er_encode_cond */
+    int32_t max_tf_rows;          /* rows (batch * seq) of the largest teacher-forced forward; 0 = decode only */
+} er_config;
+
+const char* er_last_error(void);
+int er_version(void);
+
+/* LMM.__init__ + .half().to(device)  (core/models.py:33-99, infer.py:41-56) */
+int er_create(const er_config* cfg, er_engine** out);
+void er_destroy(er_engine* e);
+
+/* load_state_dict: one call per tensor of the reference checkpoint schema (infer.py:44-50).
+ * `name` is the state-dict key; data may be fp16 or fp32 on the device; it is rounded to fp16 (model.half()) and
+ * re-packed into the engine's layouts.  Unknown names return ER_ERR_INVALID (strict); er_finalize_weights checks
+ * that every tensor of the schema was provided. */
+int er_load_weight(er_engine* e, const char* name, const void* data_dev, int32_t dtype, const int64_t* shape, int32_t ndim, void* stream);
+int er_finalize_weights(er_engine* e, void* stream);
+
+/* LMM.encode_cond (core/models.py:101-144) for cond_mode 'point' (is_latent = 0, conds = [n_points][3] fp32) or
+ * 'point_latent' (is_latent = 1, conds = [latent_size][latent_dim] fp32).  Result ([P][C] fp32) stays in the engine;
+ * cond_embeds_out_dev (optional) receives a copy, latents_out_dev (optional, [latent_size][latent_dim] fp16) the
+ * encoder output. */
+int er_encode_cond(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, int32_t num_faces,
+                   float* cond_embeds_out_dev, void* latents_out_dev, void* stream);
+
+/* Step 0 of generate (core/models.py:224-233 + ShapeOPT.forward on the 2050-row prefix, modeling_opt.py:464-497):
+ * prompt = BOS [+ resume ids] (host array), fills the KV cache and leaves the last row's logits in the engine. */
+int er_prefill(er_engine* e, const int32_t* prompt_ids_host, int32_t n_prompt, void* stream);
+
+/* The auto-regressive loop (HF GenerationMixin._sample as driven by core/models.py:286-303 + FSM :245-271).
+ * Generates up to max_new_tokens ids into out_ids_dev (new tokens only, EOS included), count into out_len_dev.
+ * out_logits_dev (optional, [max_new_tokens][vocab] fp32) receives the lm_head output of every step before its fp16
+ * rounding; forced_ids_dev (optional) teacher-forces the fed token (tests).  tokens_per_launch <= 0: one launch. */
+int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int32_t top_k, uint64_t seed, int32_t use_tokenizer_fsm,
+              int32_t tokens_per_launch, int32_t* out_ids_dev, int32_t* out_len_dev, float* out_logits_dev,
+              const int32_t* forced_ids_dev, void* stream);
+
+/* LMM.generate with HOST buffers (infer.py:104-106 call shape): conds_host fp32 -> ids_host; synchronises.
+ * This is the end-to-end entry measured by bench.py's `e2e`. */
+int er_generate_host(er_engine* e, const float* conds_host, int32_t n_points, int32_t is_latent, int32_t num_faces,
+                     const int32_t* resume_ids_host, int32_t n_resume, int32_t max_new_tokens, int32_t mode, int32_t top_k,
+                     uint64_t seed, int32_t use_tokenizer_fsm, int32_t* out_ids_host, int32_t* out_len_host);
+
+/* LMM.forward in eval mode (core/models.py:147-202; dense causal, no padding): batch of B samples.
+ * conds_dev [B][n_points][3] fp32, tokens_dev [B][T] int32, labels_dev [B][P+T] int64 (-100 ignored), num_faces_host [B].
+ * losses_dev[3] = {loss, loss_ce, loss_kl}; logits_out_dev (optional) [B][P+T][vocab] fp32 (pre-rounding). */
+int er_forward_tf(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, const int32_t* tokens_dev,
+                  const int64_t* labels_dev, const int32_t* num_faces_host, int32_t B, int32_t T, float kl_weight,
+                  float* losses_dev, float* logits_out_dev, void* stream);
+
+/* The op seam core/transformer/attention.py:27-62 `attention(q, k, v, causal)` for unmasked fp16 inputs:
+ * q [B][Nq][H][D], k/v [B][Nk][H][D] contiguous, out [B][Nq][H][D]; D in {64, 96}; causal requires Nq == Nk
+ * (single-query causal attention over a cache is inside er_decode).  Engine-free. */
+int er_attention_bnhd(const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev, int32_t B, int32_t Nq, int32_t Nk,
+                      int32_t H, int32_t D, int32_t causal, void* stream);
+
+/* Introspection used by bench.py / tests */
+int64_t er_weight_bytes_per_token(const er_engine* e);   /* algorithmic weight bytes one decode step reads */
+int64_t er_kv_bytes_per_row(const er_engine* e);         /* K+V bytes one cached position adds to a decode step */
+int32_t er_cache_rows(const er_engine* e);               /* rows currently in the KV cache */
+int64_t er_kernel_launches(const er_engine* e);          /* kernels launched by this engine so far */
+
+/* meto tokenizer, LR_ABSCO backend (CPU, native): replaces the pybind module `_meto`
+ * (meto/src/bindings.cpp:25-28 -> Engine_LR_ABSCO::decode, meto/include/meto/engine_lr_absco.h:223-295).
+ * tokens are already -3 shifted (provider.py:115).  Capacities: verts >= 3*(n/4+3) floats*3, faces >= (n/4+3)*3,
+ * face_type >= n/4+3.  Counts are returned through n_verts/n_faces/n_types. */
+int er_meto_decode(int32_t discrete_bins, const int32_t* tokens, int64_t n, float* verts, int32_t* faces, int32_t* face_type,
+                   int64_t* n_verts, int64_t* n_faces, int64_t* n_types);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

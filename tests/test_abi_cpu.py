@@ -1,0 +1,67 @@
+"""The C-ABI library builds, loads without a GPU, and exports every symbol include/edgerunner_b200.h declares."""
+
+import os
+import re
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(REPO, 'include', 'edgerunner_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(er_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from edgerunner_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), s
+        assert s in _lib.SIGNATURES, f'{s} has no ctypes signature'
+    assert set(_lib.SIGNATURES) == set(syms)
+    assert lib.er_version() >= 100
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from core.models import LMM
+    from edgerunner_b200 import synth
+    model = LMM(synth.tiny_options())
+    with pytest.raises(RuntimeError):
+        model.generate(torch.zeros(1, 256, 3))
+
+
+def test_state_dict_schema_matches_reference_spec():
+    """LMM.state_dict() keys/shapes == synth.state_dict_spec, which gen_golden.py pinned against the reference's LMM."""
+    from core.models import LMM
+    from core.options import config_defaults
+    from edgerunner_b200 import synth
+    opt = synth.tiny_options()
+    sd = LMM(opt).state_dict()
+    spec = synth.state_dict_spec(opt)
+    assert [n for n, _, _ in spec] == list(sd.keys())
+    for n, shape, _ in spec:
+        assert tuple(sd[n].shape) == tuple(shape), n
+    model = LMM(opt)
+    model.load_state_dict(synth.synth_state_dict(opt), strict=True)
+    assert len(synth.state_dict_spec(config_defaults['ArAE'])) == 416
+
+
+def test_no_product_import_of_oracle():
+    """The product path must never import the oracle (tier rule)."""
+    bad = []
+    for root in ('core', 'meto', 'edgerunner_b200'):
+        for dp, _, files in os.walk(os.path.join(REPO, root)):
+            for f in files:
+                if f.endswith(('.py', '.cu', '.cpp', '.h', '.cuh')):
+                    txt = open(os.path.join(dp, f)).read()
+                    if re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M) or re.search(r'#include.*oracle', txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
