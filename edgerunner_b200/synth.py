@@ -93,7 +93,7 @@ def fourier_basis() -> torch.Tensor:
 
 
 def synth_state_dict(opt, seed: int = 0, eos_logit: float | None = -30.0,
-                     dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
+                     dtype: torch.dtype = torch.float32, fp16_exact: bool = True) -> Dict[str, torch.Tensor]:
     """Seeded synthetic checkpoint in the reference key schema.
 
     ``eos_logit``: if not None, the last ``final_layer_norm`` gets weight=1, bias=1 and the EOS row
@@ -124,13 +124,17 @@ def synth_state_dict(opt, seed: int = 0, eos_logit: float | None = -30.0,
             t[opt.pad_token_id].zero_()
         else:  # pragma: no cover
             raise ValueError(kind)
+        # every value is fp16-representable: `model.half()` (infer.py:56) is then exact, so the reference's fp32 CPU
+        # run (goldens) and the fp16 GPU path start from bit-identical weights and differ by activation rounding only
+        if fp16_exact and kind != 'basis':
+            t = t.to(torch.float16).to(torch.float32)
         sd[name] = t.to(dtype).contiguous()
     if eos_logit is not None:
         last = 'mesh_decoder.model.layers.%d.final_layer_norm.' % (opt.num_layers - 1)
         sd[last + 'weight'] = torch.ones_like(sd[last + 'weight'])
         sd[last + 'bias'] = torch.ones_like(sd[last + 'bias'])
         C = opt.hidden_dim
-        sd['mesh_decoder.lm_head.weight'][opt.eos_token_id] = eos_logit / C
+        sd['mesh_decoder.lm_head.weight'][opt.eos_token_id] = float(torch.tensor(eos_logit / C).half()) if fp16_exact else eos_logit / C
     return sd
 
 
