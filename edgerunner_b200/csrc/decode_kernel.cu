@@ -48,6 +48,16 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
     __syncthreads();
 }
 
+// ---- optional phase timeline (debug / profiles): CTA `prof_cta`, thread 0 stamps %globaltimer ------------------------
+__device__ __forceinline__ void prof_stamp(const DecodeParams& p, int& slot, bool on) {
+    if (on && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.prof[slot] = t;
+    }
+    slot++;
+}
+
 // ---- block reductions (512 threads) ------------------------------------------------------------------------
 __device__ __forceinline__ float block_sum(float v, float* red) {
     v = warp_sum(v);
@@ -359,6 +369,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
     const size_t nkb = (size_t)p.nkb;                      // key blocks (32 keys) per head in the K cache
 
     for (int it = 0; it < p.steps; ++it, ++t) {
+        const bool prof_on = p.prof != nullptr && t == p.prof_token && (int)blockIdx.x == p.prof_cta;
+        int pslot = 0;
+        prof_stamp(p, pslot, prof_on);
         // ================= sample token t from the current logits =================================================
         if (p.use_fsm && t > 0) fsm_update(counter, last_tok);
         if (warp == 0) {
@@ -418,12 +431,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                     }
                 }
             }
+            prof_stamp(p, pslot, prof_on);
             grid_barrier(p.bar, epoch);
+            prof_stamp(p, pslot, prof_on);
             // ---------------- P2: single-query attention, one (head, split) per CTA ------------------------------
             {
                 attention_phase(p, layer, L, qs, sc, vred, red);
             }
+            prof_stamp(p, pslot, prof_on);
             grid_barrier(p.bar, epoch);
+            prof_stamp(p, pslot, prof_on);
             // ---------------- P3: combine splits -> attn16 ; out_proj ---------------------------------------------
             {
                 // per (head, split) weights exp(m_s - M) / sum_s exp(m_s - M) l_s
@@ -463,7 +480,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                 for (int i = tid; i < rr.r1 - rr.r0; i += kThreads)
                     p.y1[rr.r0 + i] = __float2half_rn(unit_row_sum(red_units, i, C / ku) + __half2float(bo[rr.r0 + i]));
             }
+            prof_stamp(p, pslot, prof_on);
             grid_barrier(p.bar, epoch);
+            prof_stamp(p, pslot, prof_on);
             // ---------------- P4: x = LN1(x + y1) ; h1 = relu(fc1(x)) ----------------------------------------------
             {
                 for (int i = tid; i < C; i += kThreads) {
@@ -485,7 +504,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                     p.h1[rr.r0 + i] = __float2half_rn(fmaxf(v, 0.f));
                 }
             }
+            prof_stamp(p, pslot, prof_on);
             grid_barrier(p.bar, epoch);
+            prof_stamp(p, pslot, prof_on);
             // ---------------- P5: y2 = fc2(h1) -------------------------------------------------------------------------
             {
                 if (tid == 0) {   // next layer's qkv slice (or lm_head after the last layer)
@@ -507,7 +528,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                 for (int i = tid; i < rr.r1 - rr.r0; i += kThreads)
                     p.y2[rr.r0 + i] = __float2half_rn(unit_row_sum(red_units, i, F / ku) + __half2float(b2[rr.r0 + i]));
             }
+            prof_stamp(p, pslot, prof_on);
             grid_barrier(p.bar, epoch);
+            prof_stamp(p, pslot, prof_on);
             // ---------------- x = LN2(x + y2) ------------------------------------------------------------------------------
             for (int i = tid; i < C; i += kThreads)
                 xres[i] += __half2float(__ushort_as_half(ldg_cg_u16(p.y2 + i)));
@@ -526,7 +549,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
             for (int i = tid; i < rr.r1 - rr.r0; i += kThreads) p.logits[rr.r0 + i] = unit_row_sum(red_units, i, C / ku);
         }
         L += 1;
+        prof_stamp(p, pslot, prof_on);
         grid_barrier(p.bar, epoch);
+        prof_stamp(p, pslot, prof_on);
     }
     if (blockIdx.x == 0 && tid == 0) { p.st->t = t; p.st->L = L; p.st->counter = counter; p.st->last_tok = last_tok; }
 }

@@ -39,6 +39,8 @@ struct DecodeParams {
     const int32_t *forced;   // optional teacher-forcing stream [max_new]
     int max_new, steps, mode /*0 greedy, 1 sample*/, top_k, use_fsm, eos;
     unsigned long long seed;
+    // optional phase timeline: slot 0 = token start, then (end of phase, end of barrier) x 5 per layer, + lm_head pair
+    unsigned long long *prof; int prof_token, prof_cta;
 };
 
 }  // namespace er

@@ -84,6 +84,7 @@ struct er_engine {
     // encoder workspace
     __half *emb16, *pf16, *kvx16, *kvo16, *qln16, *qq16, *ea16, *ex1, *ex1ln, *eff, *egg, *ex2, *pc16;
     int cache_rows = 0;
+    unsigned long long* prof = nullptr; int prof_token = -1, prof_cta = 0;
     int lat_batch_cap = 1;
 };
 
@@ -189,6 +190,8 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     ALLOC(e->logits, V); ALLOC(e->st, 1); ALLOC(e->bar, 4); ALLOC(e->cond32, (size_t)P * C);
     ALLOC(e->ids_dev, 65536); ALLOC(e->gen_ids_dev, cfg->max_seq_rows + 8); ALLOC(e->gen_len_dev, 4);
     ALLOC(e->conds_dev_buf, (size_t)(cfg->max_points > LQ * LD ? cfg->max_points * 3 : LQ * LD) + 16);
+    ALLOC(e->prof, 4096);
+    CK(cudaMemset(e->prof, 0, 4096 * 8));
     CK(cudaMemset(e->st, 0, sizeof(er::DecodeState)));
     // decode launch geometry
     int sms = 0;
@@ -404,6 +407,7 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.out_ids = out_ids_dev; p.out_logits = out_logits_dev; p.forced = forced_ids_dev;
     p.max_new = max_new_tokens; p.mode = mode; p.top_k = top_k > 0 ? top_k : 10; p.use_fsm = use_tokenizer_fsm; p.eos = e->cfg.eos_token_id;
     p.seed = seed;
+    p.prof = e->prof_token >= 0 ? e->prof : nullptr; p.prof_token = e->prof_token; p.prof_cta = e->prof_cta;
     const int chunk = tokens_per_launch > 0 ? tokens_per_launch : max_new_tokens;
     for (int done = 0; done < max_new_tokens; done += chunk) {
         p.steps = std::min(chunk, max_new_tokens - done);
@@ -497,5 +501,19 @@ extern "C" int er_attention_bnhd(const void* q_dev, const void* k_dev, const voi
     a.q_bs = a.o_bs = (long long)Nq * H * D; a.k_bs = a.v_bs = (long long)Nk * H * D;
     a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.D = D; a.causal = causal;
     CK(er_attention(a, (cudaStream_t)stream));
+    return ER_OK;
+}
+
+// Debug/profiling: record the phase timeline (ns, %globaltimer) of CTA `cta` while it generates token `token` of the next
+// er_decode call (token < 0 disables).  er_debug_read_timeline copies n slots back (synchronises the device).
+extern "C" int er_debug_phase_timeline(er_engine* e, int32_t token, int32_t cta) {
+    if (!e) return set_err(ER_ERR_INVALID, "null engine");
+    e->prof_token = token; e->prof_cta = cta;
+    return ER_OK;
+}
+extern "C" int er_debug_read_timeline(er_engine* e, uint64_t* out_host, int32_t n) {
+    if (!e || !out_host || n < 0 || n > 4096) return set_err(ER_ERR_INVALID, "bad argument");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out_host, e->prof, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return ER_OK;
 }

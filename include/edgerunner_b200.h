@@ -110,6 +110,11 @@ int64_t er_kv_bytes_per_row(const er_engine* e);         /* K+V bytes one cached
 int32_t er_cache_rows(const er_engine* e);               /* rows currently in the KV cache */
 int64_t er_kernel_launches(const er_engine* e);          /* kernels launched by this engine so far */
 
+/* Profiling aid (profiles/): phase timeline of one CTA for one generated token of the next er_decode call. Slots (ns):
+ * [0] token start, then for each layer 5 x (phase end, barrier end), then (lm_head end, barrier end). */
+int er_debug_phase_timeline(er_engine* e, int32_t token, int32_t cta);
+int er_debug_read_timeline(er_engine* e, uint64_t* out_host, int32_t n);
+
 /* meto tokenizer, LR_ABSCO backend (CPU, native): replaces the pybind module `_meto`
  * (meto/src/bindings.cpp:25-28 -> Engine_LR_ABSCO::decode, meto/include/meto/engine_lr_absco.h:223-295).
  * tokens are already -3 shifted (provider.py:115).  Capacities: verts >= 3*(n/4+3) floats*3, faces >= (n/4+3)*3,

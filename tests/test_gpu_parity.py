@@ -178,7 +178,9 @@ def test_sample_mode_is_grammar_valid_and_deterministic(tiny_setup):
     sc = ref['scores'].numpy()
     for t, tok in enumerate(toks):
         kth = np.sort(sc[t])[::-1][9]
-        assert sc[t, tok] >= kth - (2 * LOGIT_TOL + _fp16_ulp(kth)), (t, tok)
+        if np.isfinite(kth):        # fewer than 10 finite scores (op positions): top-k removes nothing
+            assert sc[t, tok] >= kth - (2 * LOGIT_TOL + _fp16_ulp(kth)), (t, tok)
+        assert np.isfinite(sc[t, tok])
 
 
 def test_sampler_distribution(tiny_setup):
