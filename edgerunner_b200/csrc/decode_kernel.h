@@ -21,14 +21,16 @@ struct DecodeParams {
     int S;            // KV splits per head in the attention phase (H*S <= grid)
     int Lmax;         // V-cache rows per head
     int nkb;          // K-cache 32-key blocks per head (ceil(Lmax/32))
-    int ks_out, ks_fc2, ks_lm;   // k-slices per row for the skinny GEMV phases
+    int nstage;       // shared-memory ring stages (24 KB each)
+    int sc_len;       // floats of score scratch (>= max keys per split + 33, >= V)
     // decoder weights, fp16, nn.Linear layout [out][in] (q,k,v rows concatenated in that order)
     const __half *wqkv, *bqkv, *wo, *bo, *ln1_w, *ln1_b, *w1, *b1, *w2, *b2, *ln2_w, *ln2_b;
     const __half *lm_head, *embd, *pos;
     // KV cache: K blocked [layer][head][key/32][d/8][key%32][8], V natural [layer][head][key][96]
     __half *kc, *vc;
     // cross-CTA scratch (global, read back with ld.cg)
-    __half *q16, *y1, *h1, *y2;
+    __half *q16, *y1, *h1, *y2, *attn16;
+    unsigned *head_cnt;   // [H] monotonic split-completion tickets (zeroed with the barrier counter)
     float *part;      // [H][S][100]: o[96], m, l
     float *logits;    // [V] fp32 lm_head output before the fp16 rounding
     DecodeState *st;
@@ -45,6 +47,8 @@ struct DecodeParams {
 
 }  // namespace er
 
-size_t er_decode_smem_bytes(const er::DecodeParams& p, int sc_keys);
+size_t er_decode_smem_bytes(const er::DecodeParams& p);
+int er_decode_pick_stages(const er::DecodeParams& p, size_t smem_limit);
 cudaError_t er_decode_launch(const er::DecodeParams& p, int grid, size_t smem, cudaStream_t stream);
 int er_decode_max_grid(size_t smem);
+int er_decode_read_detail(unsigned long long* out64);

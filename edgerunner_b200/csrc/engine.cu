@@ -56,7 +56,7 @@ struct Slot { __half* dst; int rows, cols, dst_ld; };
 struct er_engine {
     er_config cfg;
     int C, H, D, F, V, NL, P, E, EH, LQ, LD, LDP;
-    int Lmax, nkb, grid, S, sc_keys;
+    int Lmax, nkb, grid, S, sc_len, nstage;
     size_t dec_smem;
     long long launches = 0;
     std::vector<void*> allocs;
@@ -69,7 +69,7 @@ struct er_engine {
     __half *qe, *basis, *mlp_w, *mlp_b, *ln_w, *ln_b, *cl1w, *cl1b, *cq_w, *cq_b, *ckv_w, *ckv_b, *co_w, *co_b, *cl2w, *cl2b;
     __half *ff0w, *ff0b, *ff2w, *ff2b, *lin_w, *lin_b, *pc_w, *pc_b, *ncw, *ncb, *enf;
     // cache + decode scratch
-    __half *kc, *vc, *q16, *y1, *h1, *y2;
+    __half *kc, *vc, *q16, *y1, *h1, *y2, *attn16;
     float *part, *logits, *cond32;
     er::DecodeState* st;
     unsigned* bar;
@@ -186,8 +186,8 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     }
     // ---- KV cache + decode scratch ---------------------------------------------------------------------------------------------
     ALLOC(e->kc, (size_t)NL * H * e->nkb * 32 * 96); ALLOC(e->vc, (size_t)NL * H * Lmax * 96);
-    ALLOC(e->q16, C); ALLOC(e->y1, C); ALLOC(e->h1, F); ALLOC(e->y2, C);
-    ALLOC(e->logits, V); ALLOC(e->st, 1); ALLOC(e->bar, 4); ALLOC(e->cond32, (size_t)P * C);
+    ALLOC(e->q16, C); ALLOC(e->y1, C); ALLOC(e->h1, F); ALLOC(e->y2, C); ALLOC(e->attn16, C);
+    ALLOC(e->logits, V); ALLOC(e->st, 1); ALLOC(e->bar, 64 + 64); ALLOC(e->cond32, (size_t)P * C);
     ALLOC(e->ids_dev, 65536); ALLOC(e->gen_ids_dev, cfg->max_seq_rows + 8); ALLOC(e->gen_len_dev, 4);
     ALLOC(e->conds_dev_buf, (size_t)(cfg->max_points > LQ * LD ? cfg->max_points * 3 : LQ * LD) + 16);
     ALLOC(e->prof, 4096);
@@ -197,12 +197,17 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     e->grid = sms;
-    e->S = sms / H; if (e->S > 32) e->S = 32; if (e->S < 1) { delete e; return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
+    e->S = sms / H; if (e->S > 16) e->S = 16; if (e->S < 1) { delete e; return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
     ALLOC(e->part, (size_t)H * e->S * 100);
-    e->sc_keys = ((e->nkb + e->S - 1) / e->S) * 32;
+    e->sc_len = std::max(((e->nkb + e->S - 1) / e->S) * 32 + 64, (V + 3) / 4 * 4);
     {
-        er::DecodeParams p{}; p.C = C; p.F = F; p.H = H; p.V = V; p.S = e->S;
-        e->dec_smem = er_decode_smem_bytes(p, e->sc_keys);
+        er::DecodeParams p{}; p.C = C; p.F = F; p.H = H; p.V = V; p.S = e->S; p.sc_len = e->sc_len;
+        int smem_max = 0;
+        CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+        e->nstage = er_decode_pick_stages(p, (size_t)smem_max - 1024);
+        if (e->nstage < 2) { delete e; return set_err(ER_ERR_CAPACITY, "not enough shared memory for the decode ring (limit %d)", smem_max); }
+        p.nstage = e->nstage;
+        e->dec_smem = er_decode_smem_bytes(p);
         if (er_decode_max_grid(e->dec_smem) < sms) { delete e; return set_err(ER_ERR_CAPACITY, "decode kernel cannot be co-resident on %d SMs (smem %zu)", sms, e->dec_smem); }
     }
     // ---- dense workspace ----------------------------------------------------------------------------------------------------------
@@ -372,18 +377,6 @@ extern "C" int er_prefill(er_engine* e, const int32_t* prompt_ids_host, int32_t 
     return ER_OK;
 }
 
-static int pick_ks(int K, int rows_per_cta) {   // k-slices per row so that a CTA has >= ~2 units per warp
-    int best = 1;
-    for (int ks = 1; ks <= 16; ks++) {
-        if (K % ks || (K / ks) % 8) continue;
-        best = ks;
-        if (rows_per_cta * ks >= 32 && (K / ks) % 256 == 0) return ks;
-    }
-    for (int ks = 1; ks <= 16; ks++)
-        if (K % ks == 0 && (K / ks) % 8 == 0 && rows_per_cta * ks >= 32) return ks;
-    return best;
-}
-
 extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int32_t top_k, uint64_t seed, int32_t use_tokenizer_fsm,
                          int32_t tokens_per_launch, int32_t* out_ids_dev, int32_t* out_len_dev, float* out_logits_dev,
                          const int32_t* forced_ids_dev, void* stream) {
@@ -395,14 +388,14 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     const int C = e->C, F = e->F, V = e->V, G = e->grid;
     er::DecodeParams p{};
     p.C = C; p.H = e->H; p.F = F; p.V = V; p.layers = e->NL; p.S = e->S; p.Lmax = e->Lmax; p.nkb = e->nkb;
-    p.ks_out = pick_ks(C, (C + G - 1) / G); p.ks_fc2 = pick_ks(F, (C + G - 1) / G); p.ks_lm = pick_ks(C, (V + G - 1) / G);
-    const int max_units = std::max(std::max((3 * C + G - 1) / G + 1, (F + G - 1) / G + 1),
-                                   std::max(((C + G - 1) / G + 1) * std::max(p.ks_out, p.ks_fc2), ((V + G - 1) / G + 1) * p.ks_lm));
-    if (max_units > 256) return set_err(ER_ERR_CAPACITY, "model too wide for %d SMs (units %d)", G, max_units);
+    p.nstage = e->nstage; p.sc_len = e->sc_len;
+    // red_units holds 2 partial sums per unit of C elements: the widest phases are qkv (rows) and fc2 (rows * F/C)
+    const int max_units = std::max(std::max((3 * C + G - 1) / G + 1, (F + G - 1) / G + 1), ((C + G - 1) / G + 1) * (F / C));
+    if (2 * max_units > 256 || F % C || C % 16 || C > 1536 || (8 % (F / C)) || ((24576 / (2 * C)) % (F / C)) || e->H > 64) return set_err(ER_ERR_CAPACITY, "model shape not supported by the decode kernel on %d SMs (units %d)", G, max_units);
     p.wqkv = e->wqkv; p.bqkv = e->bqkv; p.wo = e->wo; p.bo = e->bo; p.ln1_w = e->ln1w; p.ln1_b = e->ln1b;
     p.w1 = e->w1; p.b1 = e->b1; p.w2 = e->w2; p.b2 = e->b2; p.ln2_w = e->ln2w; p.ln2_b = e->ln2b;
     p.lm_head = e->lm_head; p.embd = e->embd; p.pos = e->pos;
-    p.kc = e->kc; p.vc = e->vc; p.q16 = e->q16; p.y1 = e->y1; p.h1 = e->h1; p.y2 = e->y2; p.part = e->part; p.logits = e->logits;
+    p.kc = e->kc; p.vc = e->vc; p.attn16 = e->attn16; p.head_cnt = e->bar + 64; p.q16 = e->q16; p.y1 = e->y1; p.h1 = e->h1; p.y2 = e->y2; p.part = e->part; p.logits = e->logits;
     p.st = e->st; p.bar = e->bar;
     p.out_ids = out_ids_dev; p.out_logits = out_logits_dev; p.forced = forced_ids_dev;
     p.max_new = max_new_tokens; p.mode = mode; p.top_k = top_k > 0 ? top_k : 10; p.use_fsm = use_tokenizer_fsm; p.eos = e->cfg.eos_token_id;
@@ -411,7 +404,7 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     const int chunk = tokens_per_launch > 0 ? tokens_per_launch : max_new_tokens;
     for (int done = 0; done < max_new_tokens; done += chunk) {
         p.steps = std::min(chunk, max_new_tokens - done);
-        CK(cudaMemsetAsync(e->bar, 0, 16, st));
+        CK(cudaMemsetAsync(e->bar, 0, (64 + 64) * 4, st));
         CKL(e, er_decode_launch(p, G, e->dec_smem, st));
     }
     if (out_len_dev) {
@@ -515,5 +508,6 @@ extern "C" int er_debug_read_timeline(er_engine* e, uint64_t* out_host, int32_t 
     if (!e || !out_host || n < 0 || n > 4096) return set_err(ER_ERR_INVALID, "bad argument");
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out_host, e->prof, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (n >= 4096) er_decode_read_detail((unsigned long long*)out_host + 3968);   // gemv detail stamps in the tail of the buffer
     return ER_OK;
 }

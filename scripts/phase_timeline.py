@@ -18,30 +18,32 @@ def main():
     cond = synth.synth_point_cloud(0, opt.point_num)
     res = {}
     NL = opt.num_layers
-    nslots = 1 + NL * 10 + 2
-    names = ['qkv', 'attn', 'out_proj', 'ln1+fc1', 'fc2']
+    nslots = 1 + NL * 16 + 2
+    segs = ['res+LN2', 'qkv_gemv', 'qkv_epi', 'B1', 'attn', 'B2', 'combine', 'out_proj', 'B3', 'res+LN1', 'fc1', 'B4', 'h1_load', 'fc2', 'B5']
     for tok in tokens:
-        for cta in (0, 73, 147):
+        for cta in (0, 147):
             eng.encode_cond(cond[0].cuda(), 4000); eng.prefill([1])
             eng.lib.er_debug_phase_timeline(eng.h, tok, cta)
             eng.decode(tok + 4, mode='greedy')
-            buf = (C.c_uint64 * nslots)()
-            eng.lib.er_debug_read_timeline(eng.h, buf, nslots)
-            ts = np.array(list(buf), dtype=np.float64)
-            d = np.diff(ts) / 1e3   # us
-            # d[0] = sample+embed -> end of P1(layer0) is slot1.. ; per layer: phase i end = slot 1+10l+2i, barrier end = +1
-            per = {n: [] for n in names}; bar = {n: [] for n in names}
-            for l in range(NL):
-                for i, n in enumerate(names):
-                    a = 1 + 10 * l + 2 * i
-                    start = ts[a - 1]
-                    per[n].append((ts[a] - start) / 1e3); bar[n].append((ts[a + 1] - ts[a]) / 1e3)
+            buf = (C.c_uint64 * 4096)()
+            eng.lib.er_debug_read_timeline(eng.h, buf, 4096)
+            ts = np.array(list(buf)[:nslots], dtype=np.float64)
+            det = list(buf)[3968:3968 + 64]
+            nd = int(det[63])
+            if nd: print('fc1 layer5 thread0 detail (us since entry):', [round((x - det[0]) / 1e3, 2) for x in det[:nd]], flush=True)
+            ahead = np.array(list(buf)[2048:2048 + nslots], dtype=np.float64)
+            acc = {n: [] for n in segs}
+            for l in range(1, NL):          # skip layer 0 (its first segment includes sample + embed)
+                pb = 1 + 16 * l
+                prev = ts[pb - 2]           # B5 of the previous layer (slot pb-16+14)
+                for i, n in enumerate(segs):
+                    acc[n].append((ts[pb + i] - prev) / 1e3); prev = ts[pb + i]
+            waits = [ts[1 + 16 * l + 15] / 1e3 for l in range(1, NL)]
+            ah = {n: round(float(np.mean([ahead[1 + 16 * l + i] for l in range(1, NL)])), 1) for i, n in enumerate(segs)}
             key = f'token{tok}_cta{cta}'
-            res[key] = {'L': 2050 + tok, 'total_us': (ts[-1] - ts[0]) / 1e3,
-                        'phase_us_mean': {n: float(np.mean(per[n][1:])) for n in names},
-                        'barrier_wait_us_mean': {n: float(np.mean(bar[n][1:])) for n in names},
-                        'lm_head_us': (ts[-2] - ts[-3]) / 1e3, 'lm_barrier_us': (ts[-1] - ts[-2]) / 1e3,
-                        'layer0_first_phase_us(incl sample+embed)': per['qkv'][0]}
+            res[key] = {'L': 2050 + tok, 'ring_wait_us_per_layer(thread0)': float(np.mean(waits)), 'producer_stages_ahead_at_end_of_segment': ah, 'token_us': (ts[2 + 16 * NL] - ts[0]) / 1e3, 'layer_us': float(sum(np.mean(acc[n]) for n in segs)),
+                        'segments_us_mean': {n: round(float(np.mean(acc[n])), 2) for n in segs},
+                        'lm_head_us': (ts[1 + 16 * NL] - ts[16 * NL - 1]) / 1e3, 'lm_barrier_us': (ts[2 + 16 * NL] - ts[1 + 16 * NL]) / 1e3}
             print(key, json.dumps(res[key]), flush=True)
     eng.lib.er_debug_phase_timeline(eng.h, -1, 0)
     os.makedirs(os.path.dirname(out_path) or '.', exist_ok=True)
