@@ -31,13 +31,13 @@
 
 namespace er {
 
-constexpr int kConsumerWarps = 16;
+constexpr int kConsumerWarps = 14;               // 7 owner pairs, one per ring stage; 15 warps total -> 128 registers/thread
 constexpr int kConsumers = kConsumerWarps * 32;   // 512 compute threads
 constexpr int kThreads = kConsumers + 32;         // + one producer warp
 constexpr int HD = 96;                            // decoder head_dim (ArAE: 1536 / 16)
 constexpr int HV = HD / 8;                        // 16-byte vectors per head row (12)
 constexpr int kStageBytes = 24576;                // 8 weight rows of 1536 fp16 = 4 K blocks = 128 V rows
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 7;                    // == kConsumerWarps / 2: stage s is processed by warp pair s
 constexpr int kKBlockBytes = HV * 32 * 16;        // 6144: one 32-key block of the blocked K cache
 constexpr int kMaxUnits = 256;
 
@@ -64,25 +64,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ int g_detail_arm;               // profiling aid: when 1, thread 0 logs %globaltimer inside gemv_job into g_detail
-__device__ unsigned long long g_detail[64];
-__device__ int g_dbg;                     // timing experiments: bit0 skip GEMV math, bit1 skip attention math (results invalid)
-__device__ unsigned long long g_wait_ns;   // profiling aid: time thread 0 of the profiled CTA spent waiting for ring data
-__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, bool timed) {
-    if (timed && threadIdx.x == 0) {
-        uint32_t ok;   // non-blocking probe (try_wait may suspend inside the instruction)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return;
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-        while (!mbar_try_wait(bar, parity)) {}
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        g_wait_ns += t1 - t0;
-    } else {
-        while (!mbar_try_wait(bar, parity)) {}
-    }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -156,8 +137,18 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // x = LayerNorm(xres + y) in place (fp32 statistics, eps 1e-5, fp16 affine params); also emits the fp16 copy used as the next
 // GEMV input.  y is the fp16 phase output other CTAs just published (read at L2); round_first: the residual add of the first
 // layer of a decode step is an fp16 + fp16 add.  One block reduction (sum and sum of squares), 2 barriers.
-__device__ __noinline__ void residual_layer_norm(float* xres, __half* x16, const __half* y, bool round_first, const __half* __restrict__ g,
-                                                 const __half* __restrict__ b, int C, float* red) {
+struct LnParams { float g[4], b[4]; };                      // this thread's affine parameters (elements tid + j*512)
+__device__ __forceinline__ LnParams ln_load(const __half* __restrict__ g, const __half* __restrict__ b, int C) {
+    LnParams lp;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = threadIdx.x + j * kConsumers;
+        lp.g[j] = (i < C) ? __half2float(g[i]) : 0.f;
+        lp.b[j] = (i < C) ? __half2float(b[i]) : 0.f;
+    }
+    return lp;
+}
+__device__ __noinline__ void residual_layer_norm(float* xres, __half* x16, const __half* y, bool round_first, const LnParams lp, int C, float* red) {
     constexpr int PER = 4;                                  // supports C <= 4 * 512
     float v[PER];
     float s = 0.f, q = 0.f;
@@ -172,7 +163,7 @@ __device__ __noinline__ void residual_layer_norm(float* xres, __half* x16, const
         }
     }
     s = warp_sum(s); q = warp_sum(q);
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red[16 + (threadIdx.x >> 5)] = q; }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red[16 + (threadIdx.x >> 5)] = q; }   // kConsumerWarps <= 16
     cbar();
     float ts = 0.f, tq = 0.f;
 #pragma unroll
@@ -184,7 +175,7 @@ __device__ __noinline__ void residual_layer_norm(float* xres, __half* x16, const
     for (int j = 0; j < PER; j++) {
         const int i = threadIdx.x + j * kConsumers;
         if (i < C) {
-            const float yv = (v[j] - mean) * rstd * __half2float(g[i]) + __half2float(b[i]);
+            const float yv = (v[j] - mean) * rstd * lp.g[j] + lp.b[j];
             xres[i] = yv;
             x16[i] = __float2half_rn(yv);
         }
@@ -222,6 +213,20 @@ struct Ring {          // passed by value (registers): shared-space addresses of
     __device__ __forceinline__ uint32_t fullb(uint32_t s) const { return full + s * 8; }
     __device__ __forceinline__ uint32_t emptyb(uint32_t s) const { return empty + s * 8; }
 };
+
+// Consumer-side ring cursor.  Every consumer warp advances it identically over every stage of every job, but a stage is
+// PROCESSED by one warp pair only: ring stage s belongs to warp pair s (nstage <= kConsumerWarps / 2).  Different pairs therefore work on different
+// stages at the same time (up to `nstage` of them), which overlaps the per-stage dependency chains (barrier wait, smem
+// latency, shuffle reduction) instead of running all 16 warps in lockstep over one stage.
+struct Cursor {
+    uint32_t it, stage, parity;
+    __device__ __forceinline__ void advance(int nstage) {
+        ++it;
+        if (++stage == (uint32_t)nstage) { stage = 0; parity ^= 1; }
+    }
+    __device__ __forceinline__ bool mine(int warp) const { return stage == (uint32_t)(warp >> 1); }
+};
+constexpr int kOwnersPerStage = 2;   // warps arriving on a stage's empty barrier
 
 // ---- producer: stream one contiguous byte range through the ring ---------------------------------------------------------------------
 // returns false if the consumers raised `stop` (EOS) while we were waiting for a free stage
@@ -276,24 +281,56 @@ __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, 
 }
 
 // ---- consumer: GEMV over one streamed weight slice ------------------------------------------------------------------------------------
-// The slice is n_units units of C fp16 (a row of K = nu_row * C elements is nu_row consecutive units).  A warp takes
-// half-units (C/2 elements) hu = warp, warp+16, ... of every stage; because 16 and the units-per-stage are multiples of
-// nu_row, the x slice a warp needs is the same for every half-unit it ever touches in this job: it lives in registers.
+// The slice is n_units units of C fp16 (a row of K = nu_row * C elements is nu_row consecutive units).  The stage's owner
+// pair splits every unit in two halves (warp parity = half); each warp walks the units of the stage two at a time (independent
+// accumulator chains).  XREG: nu_row == 1, the x half this warp needs is the same for every unit -> registers.
 // NVL = 16-byte vectors per lane per half-unit (3 for C = 1536).  Partial sums go to red_units[unit*2 + half].
 template <int NVL>
-__device__ __forceinline__ void gemv_job_t(const Ring r, uint32_t& it, int n_units, int nu_row, int C, uint32_t xin_s, float* red_units) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ float half_unit_dot(uint32_t wb, const float (*xr)[8], uint32_t xb, bool xreg, int lane, int hv) {
+    uint4 wv[NVL], xv[NVL];
+#pragma unroll
+    for (int j = 0; j < NVL; j++) {
+        const int v = lane + 32 * j;
+        wv[j] = (v < hv) ? lds128(wb + v * 16) : make_uint4(0, 0, 0, 0);
+        if (!xreg) xv[j] = (v < hv) ? lds128(xb + v * 16) : make_uint4(0, 0, 0, 0);
+    }
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < NVL; j++) {
+        float x[8];
+        if (xreg) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = xr[j][e];
+        } else {
+            float2 f;
+            f = h2f2(xv[j].x); x[0] = f.x; x[1] = f.y;
+            f = h2f2(xv[j].y); x[2] = f.x; x[3] = f.y;
+            f = h2f2(xv[j].z); x[4] = f.x; x[5] = f.y;
+            f = h2f2(xv[j].w); x[6] = f.x; x[7] = f.y;
+        }
+        float2 f; float a0, a1;
+        f = h2f2(wv[j].x); a0 = f.x * x[0];           a1 = f.y * x[1];
+        f = h2f2(wv[j].y); a0 = fmaf(f.x, x[2], a0);  a1 = fmaf(f.y, x[3], a1);
+        f = h2f2(wv[j].z); a0 = fmaf(f.x, x[4], a0);  a1 = fmaf(f.y, x[5], a1);
+        f = h2f2(wv[j].w); a0 = fmaf(f.x, x[6], a0);  a1 = fmaf(f.y, x[7], a1);
+        tot += a0 + a1;
+    }
+    return tot;
+}
+template <int NVL>
+__device__ __forceinline__ void gemv_job_t(const Ring r, Cursor& cur, int n_units, int nu_row, int C, uint32_t xin_s, float* red_units) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = warp & 1;
     const int upstage = kStageBytes / (2 * C);
     const int hv = C >> 4;                                   // 16-byte vectors per half-unit
     const int nch = (n_units + upstage - 1) / upstage;
+    const bool xreg = (nu_row == 1);
     float xr[NVL][8];
-    {
-        const uint32_t xb = xin_s + (uint32_t)(((warp >> 1) % nu_row) * C + (warp & 1) * (C >> 1)) * 2;
+    if (xreg) {
+        const uint32_t xb = xin_s + (uint32_t)half * C;      // bytes: half * (C/2 elements) * 2
 #pragma unroll
         for (int j = 0; j < NVL; j++) {
             const int v = lane + 32 * j;
-            uint4 xv = make_uint4(0, 0, 0, 0);
-            if (v < hv) xv = lds128(xb + v * 16);
+            const uint4 xv = (v < hv) ? lds128(xb + v * 16) : make_uint4(0, 0, 0, 0);
             float2 f;
             f = h2f2(xv.x); xr[j][0] = f.x; xr[j][1] = f.y;
             f = h2f2(xv.y); xr[j][2] = f.x; xr[j][3] = f.y;
@@ -301,53 +338,38 @@ __device__ __forceinline__ void gemv_job_t(const Ring r, uint32_t& it, int n_uni
             f = h2f2(xv.w); xr[j][6] = f.x; xr[j][7] = f.y;
         }
     }
-    const bool det = (threadIdx.x == 0) && g_detail_arm;
-    int di = 0;
-    auto stampd = [&]() { if (det && di < 60) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); g_detail[di++] = t; } };
-    stampd();
-    for (int c = 0; c < nch; ++c, ++it) {
-        const uint32_t s = it % r.nstage, par = (it / r.nstage) & 1;
-        mbar_wait_timed(r.fullb(s), par, true);
-        stampd();
+    for (int c = 0; c < nch; ++c, cur.advance(r.nstage)) {
+        if (!cur.mine(warp)) continue;
+        mbar_wait(r.fullb(cur.stage), cur.parity);
         const int here = min(upstage, n_units - c * upstage);
-        const uint32_t st = r.stage(s);
-        for (int hu = warp; hu < ((g_dbg & 1) ? 0 : 2 * here); hu += kConsumerWarps) {
-            const uint32_t wb = st + (uint32_t)(hu >> 1) * 2 * C + (uint32_t)(hu & 1) * C;
-            uint4 wv[NVL];
+        const uint32_t st = r.stage(cur.stage) + (uint32_t)half * C;
+        for (int u = 0; u < here; u += 2) {
+            const int gu = c * upstage + u;
+            const bool two = (u + 1 < here);
+            const uint32_t xb0 = xin_s + (uint32_t)((gu % nu_row) * C) * 2 + (uint32_t)half * C;
+            const uint32_t xb1 = xin_s + (uint32_t)(((gu + 1) % nu_row) * C) * 2 + (uint32_t)half * C;
+            float t0 = half_unit_dot<NVL>(st + (uint32_t)u * 2 * C, xr, xb0, xreg, lane, hv);
+            float t1 = two ? half_unit_dot<NVL>(st + (uint32_t)(u + 1) * 2 * C, xr, xb1, xreg, lane, hv) : 0.f;
 #pragma unroll
-            for (int j = 0; j < NVL; j++) {
-                const int v = lane + 32 * j;
-                wv[j] = (v < hv) ? lds128(wb + v * 16) : make_uint4(0, 0, 0, 0);
+            for (int o = 16; o > 0; o >>= 1) {
+                t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+                t1 += __shfl_xor_sync(0xffffffffu, t1, o);
             }
-            float acc[NVL];
-#pragma unroll
-            for (int j = 0; j < NVL; j++) {
-                float2 f; float a0, a1;
-                f = h2f2(wv[j].x); a0 = f.x * xr[j][0];           a1 = f.y * xr[j][1];
-                f = h2f2(wv[j].y); a0 = fmaf(f.x, xr[j][2], a0);  a1 = fmaf(f.y, xr[j][3], a1);
-                f = h2f2(wv[j].z); a0 = fmaf(f.x, xr[j][4], a0);  a1 = fmaf(f.y, xr[j][5], a1);
-                f = h2f2(wv[j].w); a0 = fmaf(f.x, xr[j][6], a0);  a1 = fmaf(f.y, xr[j][7], a1);
-                acc[j] = a0 + a1;
+            if (lane == 0) {
+                red_units[gu * 2 + half] = t0;
+                if (two) red_units[(gu + 1) * 2 + half] = t1;
             }
-            float tot = acc[0];
-#pragma unroll
-            for (int j = 1; j < NVL; j++) tot += acc[j];
-            tot = warp_sum(tot);
-            if (lane == 0) red_units[(c * upstage + (hu >> 1)) * 2 + (hu & 1)] = tot;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(r.emptyb(s));
-        stampd();
+        if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
     }
     cbar();
-    stampd();
-    if (det) { g_detail[63] = di; g_detail_arm = 0; }
 }
-__device__ __noinline__ void gemv_job(const Ring r, uint32_t& it, int n_units, int nu_row, int C, uint32_t xin_s, float* red_units) {
+__device__ __noinline__ void gemv_job(const Ring r, Cursor& cur, int n_units, int nu_row, int C, uint32_t xin_s, float* red_units) {
     const int nvl = ((C >> 4) + 31) >> 5;
-    if (nvl == 3) gemv_job_t<3>(r, it, n_units, nu_row, C, xin_s, red_units);
-    else if (nvl == 2) gemv_job_t<2>(r, it, n_units, nu_row, C, xin_s, red_units);
-    else gemv_job_t<1>(r, it, n_units, nu_row, C, xin_s, red_units);
+    if (nvl == 3) gemv_job_t<3>(r, cur, n_units, nu_row, C, xin_s, red_units);
+    else if (nvl == 2) gemv_job_t<2>(r, cur, n_units, nu_row, C, xin_s, red_units);
+    else gemv_job_t<1>(r, cur, n_units, nu_row, C, xin_s, red_units);
 }
 __device__ __forceinline__ float row_sum(const float* red_units, int local_row, int nu_row) {
     float s = 0.f;
@@ -462,7 +484,7 @@ __device__ __forceinline__ float dot_k8(const uint4 kv, const float4 qa, const f
     f = h2f2(kv.w); acc = fmaf(f.x, qb.z, acc); acc = fmaf(f.y, qb.w, acc);
     return acc;
 }
-__device__ __noinline__ void attention_phase(const DecodeParams& p, const Ring r, uint32_t& it, int layer, int L, float* qs,
+__device__ __noinline__ void attention_phase(const DecodeParams& p, const Ring r, Cursor& cur, int layer, int L, float* qs,
                                              float* sc, float* vred, float* red, int* s_flag) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     AttnRange a;
@@ -483,14 +505,13 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, const Ring r
         {
             const int nb = a.b1 - a.b0;
             const int nch = (nb + 3) >> 2;
-            for (int c = 0; c < nch; ++c, ++it) {
-                const uint32_t s = it % r.nstage, par = (it / r.nstage) & 1;
-                mbar_wait_timed(r.fullb(s), par, true);
+            for (int c = 0; c < nch; ++c, cur.advance(r.nstage)) {
+                if (!cur.mine(warp)) continue;
+                mbar_wait(r.fullb(cur.stage), cur.parity);
                 const int here = min(4, nb - c * 4);
-                for (int bb = 0; bb < ((g_dbg & 2) ? 0 : here); ++bb) {
+                for (int bb = (warp & 1); bb < here; bb += 2) {            // the owner pair splits the stage's blocks
                     const int blk = c * 4 + bb;
-                    if ((blk & (kConsumerWarps - 1)) != warp) continue;
-                    const uint32_t kb = r.stage(s) + (uint32_t)bb * kKBlockBytes + lane * 16;
+                    const uint32_t kb = r.stage(cur.stage) + (uint32_t)bb * kKBlockBytes + lane * 16;
                     uint4 kv[HV];
 #pragma unroll
                     for (int j = 0; j < HV; j++) kv[j] = lds128(kb + j * 512);
@@ -506,7 +527,7 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, const Ring r
                     lmax = fmaxf(lmax, sv);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(r.emptyb(s));
+                if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
             }
         }
         // ---- the new key: q . k_L straight from the cache line P1 just wrote (visible after the grid barrier) ----
@@ -534,18 +555,18 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, const Ring r
         const int sub = lane / HV, vec = lane % HV;            // lanes 0..23: 2 rows x 12 vectors; lanes 24..31 idle
         {
             const int nch = (nold + 127) >> 7;
-            for (int c = 0; c < nch; ++c, ++it) {
-                const uint32_t s = it % r.nstage, par = (it / r.nstage) & 1;
-                mbar_wait_timed(r.fullb(s), par, true);
+            for (int c = 0; c < nch; ++c, cur.advance(r.nstage)) {
+                if (!cur.mine(warp)) continue;
+                mbar_wait(r.fullb(cur.stage), cur.parity);
                 const int here = min(128, nold - c * 128);
-                if (lane < 2 * HV && !(g_dbg & 2)) {
-                    const uint32_t st = r.stage(s) + vec * 16;
+                if (lane < 2 * HV) {
+                    const uint32_t st = r.stage(cur.stage) + vec * 16;
                     const uint32_t pc = sc_s + c * 512;           // old key k0 + c*128 + row sits at slot c*128 + row (k0 is block aligned)
-                    int row = warp * 2 + sub;
-                    for (; row + 32 < here; row += 64) {          // two rows in flight
+                    int row = (warp & 1) * 2 + sub;                // the owner pair interleaves row pairs: rows 4i + 2*(warp&1) + sub
+                    for (; row + 4 < here; row += 8) {             // two rows in flight
                         const uint4 v0 = lds128(st + (uint32_t)row * (HD * 2));
-                        const uint4 v1 = lds128(st + (uint32_t)(row + 32) * (HD * 2));
-                        const float p0 = lds32(pc + row * 4), p1 = lds32(pc + row * 4 + 128);
+                        const uint4 v1 = lds128(st + (uint32_t)(row + 4) * (HD * 2));
+                        const float p0 = lds32(pc + row * 4), p1 = lds32(pc + row * 4 + 16);
                         float2 f;
                         f = h2f2(v0.x); o[0] = fmaf(p0, f.x, o[0]); o[1] = fmaf(p0, f.y, o[1]);
                         f = h2f2(v0.y); o[2] = fmaf(p0, f.x, o[2]); o[3] = fmaf(p0, f.y, o[3]);
@@ -556,7 +577,7 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, const Ring r
                         f = h2f2(v1.z); o[4] = fmaf(p1, f.x, o[4]); o[5] = fmaf(p1, f.y, o[5]);
                         f = h2f2(v1.w); o[6] = fmaf(p1, f.x, o[6]); o[7] = fmaf(p1, f.y, o[7]);
                     }
-                    for (; row < here; row += 32) {
+                    for (; row < here; row += 4) {
                         const uint4 v0 = lds128(st + (uint32_t)row * (HD * 2));
                         const float p0 = lds32(pc + row * 4);
                         float2 f;
@@ -567,7 +588,7 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, const Ring r
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(r.emptyb(s));
+                if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
             }
         }
         if (lane < 2 * HV) {
@@ -635,8 +656,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
     ring.nstage = p.nstage;
     unsigned char* q = smem_raw + (size_t)p.nstage * kStageBytes;
     ring.full = s_addr(q);
-    ring.empty = ring.full + kMaxStages * 8;
-    float* xres = reinterpret_cast<float*>(q + 2 * kMaxStages * 8);   // [C]   residual stream (fp32)
+    ring.empty = ring.full + 8 * 8;
+    float* xres = reinterpret_cast<float*>(q + 2 * 8 * 8);   // [C]   residual stream (fp32)
     float* red_units = xres + C;                                      // [kMaxUnits]
     float* red = red_units + kMaxUnits;                               // [32]
     float* qs = red + 32;                                             // [96] query of this CTA's head (fp32)
@@ -651,7 +672,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < p.nstage; i++) { mbar_init(ring.fullb(i), 1); mbar_init(ring.emptyb(i), kConsumerWarps); }
+        for (int i = 0; i < p.nstage; i++) { mbar_init(ring.fullb(i), 1); mbar_init(ring.emptyb(i), kOwnersPerStage); }
         s_stop = 0;
         s_cons_it = 0;
         s_prod_it = 0;
@@ -666,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
     } else {
         // ===== consumers =====
         unsigned epoch = 0;
-        uint32_t it = 0;
+        Cursor cur{0u, 0u, 0u};
         const uint32_t xin_s = s_addr(xin);
         int t = p.st->t, L = p.st->L, counter = p.st->counter, last_tok = p.st->last_tok;
         const bool done0 = p.st->done != 0;
@@ -692,7 +713,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
             last_tok = fed;
             if ((fed == p.eos) || (t + 1 >= p.max_new)) {
                 if (blockIdx.x == 0 && tid == 0) { p.st->done = 1; p.st->t = t + 1; p.st->L = L; p.st->counter = counter; p.st->last_tok = last_tok; }
-                if (tid == 0) { s_cons_it = it; __threadfence_block(); s_stop = 1; }
+                if (tid == 0) { s_cons_it = cur.it; __threadfence_block(); s_stop = 1; }
                 state_written = true;
                 break;
             }
@@ -708,17 +729,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
 
             for (int layer = 0; layer < p.layers; ++layer) {
                 const int pb = 1 + 16 * layer;
-                if (prof_on && tid == 0) g_wait_ns = 0;
                 // ---------------- P1: q,k,v = x16 @ Wqkv^T + b ; KV append in place ----------------------------------------------
                 {
                     RowRange rr = cta_rows(3 * C);
-                    prof_stamp(p, pb + 0, prof_on, it, &s_prod_it);
-                    gemv_job(ring, it, rr.r1 - rr.r0, 1, C, xin_s, red_units);
-                    prof_stamp(p, pb + 1, prof_on, it, &s_prod_it);
-                    const __half* bq = p.bqkv + (size_t)layer * 3 * C;
+                    prof_stamp(p, pb + 0, prof_on, cur.it, &s_prod_it);
+                    const float bias = (tid < rr.r1 - rr.r0) ? __half2float(p.bqkv[(size_t)layer * 3 * C + rr.r0 + tid]) : 0.f;   // in flight during the GEMV
+                    gemv_job(ring, cur, rr.r1 - rr.r0, 1, C, xin_s, red_units);
+                    prof_stamp(p, pb + 1, prof_on, cur.it, &s_prod_it);
                     for (int i = tid; i < rr.r1 - rr.r0; i += kConsumers) {
                         const int r = rr.r0 + i;
-                        const __half hv = __float2half_rn(row_sum(red_units, i, 1) + __half2float(bq[r]));
+                        const __half hv = __float2half_rn(row_sum(red_units, i, 1) + bias);
                         if (r < C) {
                             p.q16[r] = hv;
                         } else if (r < 2 * C) {
@@ -731,46 +751,45 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                         }
                     }
                 }
-                prof_stamp(p, pb + 2, prof_on, it, &s_prod_it);
+                prof_stamp(p, pb + 2, prof_on, cur.it, &s_prod_it);
                 grid_barrier(p.bar, epoch);
-                prof_stamp(p, pb + 3, prof_on, it, &s_prod_it);
+                prof_stamp(p, pb + 3, prof_on, cur.it, &s_prod_it);
                 // ---------------- P2: attention -----------------------------------------------------------------------------------------
-                attention_phase(p, ring, it, layer, L, qs, sc, vred, red, &s_flag);
-                prof_stamp(p, pb + 4, prof_on, it, &s_prod_it);
+                attention_phase(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag);
+                prof_stamp(p, pb + 4, prof_on, cur.it, &s_prod_it);
                 grid_barrier(p.bar, epoch);
-                prof_stamp(p, pb + 5, prof_on, it, &s_prod_it);
+                prof_stamp(p, pb + 5, prof_on, cur.it, &s_prod_it);
                 // ---------------- P3: combine splits -> attn16 ; out_proj ---------------------------------------------------------
                 {
                     for (int i = tid; i < C / 8; i += kConsumers)
                         reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.attn16) + i);
                     cbar();
                     RowRange rr = cta_rows(C);
-                    prof_stamp(p, pb + 6, prof_on, it, &s_prod_it);
-                    gemv_job(ring, it, rr.r1 - rr.r0, 1, C, xin_s, red_units);
-                    const __half* bo = p.bo + (size_t)layer * C;
+                    prof_stamp(p, pb + 6, prof_on, cur.it, &s_prod_it);
+                    const float bias = (tid < rr.r1 - rr.r0) ? __half2float(p.bo[(size_t)layer * C + rr.r0 + tid]) : 0.f;
+                    gemv_job(ring, cur, rr.r1 - rr.r0, 1, C, xin_s, red_units);
                     for (int i = tid; i < rr.r1 - rr.r0; i += kConsumers)
-                        p.y1[rr.r0 + i] = __float2half_rn(row_sum(red_units, i, 1) + __half2float(bo[rr.r0 + i]));
+                        p.y1[rr.r0 + i] = __float2half_rn(row_sum(red_units, i, 1) + bias);
                 }
-                prof_stamp(p, pb + 7, prof_on, it, &s_prod_it);
+                const LnParams lp1 = ln_load(p.ln1_w + (size_t)layer * C, p.ln1_b + (size_t)layer * C, C);   // lands while we wait at the barrier
+                prof_stamp(p, pb + 7, prof_on, cur.it, &s_prod_it);
                 grid_barrier(p.bar, epoch);
-                prof_stamp(p, pb + 8, prof_on, it, &s_prod_it);
+                prof_stamp(p, pb + 8, prof_on, cur.it, &s_prod_it);
                 // ---------------- P4: x = LN1(x + y1) ; h1 = relu(fc1(x)) -----------------------------------------------------------
                 {
-                    residual_layer_norm(xres, xin, p.y1, layer == 0, p.ln1_w + (size_t)layer * C, p.ln1_b + (size_t)layer * C, C, red);
+                    residual_layer_norm(xres, xin, p.y1, layer == 0, lp1, C, red);
                     RowRange rr = cta_rows(F);
-                    prof_stamp(p, pb + 9, prof_on, it, &s_prod_it);
-                    if (prof_on && tid == 0 && layer == 5) g_detail_arm = 1;
-                    cbar();
-                    gemv_job(ring, it, rr.r1 - rr.r0, 1, C, xin_s, red_units);
-                    const __half* b1 = p.b1 + (size_t)layer * F;
+                    prof_stamp(p, pb + 9, prof_on, cur.it, &s_prod_it);
+                    const float bias = (tid < rr.r1 - rr.r0) ? __half2float(p.b1[(size_t)layer * F + rr.r0 + tid]) : 0.f;
+                    gemv_job(ring, cur, rr.r1 - rr.r0, 1, C, xin_s, red_units);
                     for (int i = tid; i < rr.r1 - rr.r0; i += kConsumers) {
-                        const float v = round_f16(row_sum(red_units, i, 1) + __half2float(b1[rr.r0 + i]));
+                        const float v = round_f16(row_sum(red_units, i, 1) + bias);
                         p.h1[rr.r0 + i] = __float2half_rn(fmaxf(v, 0.f));
                     }
                 }
-                prof_stamp(p, pb + 10, prof_on, it, &s_prod_it);
+                prof_stamp(p, pb + 10, prof_on, cur.it, &s_prod_it);
                 grid_barrier(p.bar, epoch);
-                prof_stamp(p, pb + 11, prof_on, it, &s_prod_it);
+                prof_stamp(p, pb + 11, prof_on, cur.it, &s_prod_it);
                 // ---------------- P5: y2 = fc2(h1) -----------------------------------------------------------------------------------------
                 {
                     for (int i = tid; i < F / 8; i += kConsumers)
@@ -778,23 +797,23 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                     cbar();
                     RowRange rr = cta_rows(C);
                     const int nu_row = F / C;
-                    prof_stamp(p, pb + 12, prof_on, it, &s_prod_it);
-                    gemv_job(ring, it, (rr.r1 - rr.r0) * nu_row, nu_row, C, xin_s, red_units);
-                    const __half* b2 = p.b2 + (size_t)layer * C;
+                    prof_stamp(p, pb + 12, prof_on, cur.it, &s_prod_it);
+                    const float bias = (tid < rr.r1 - rr.r0) ? __half2float(p.b2[(size_t)layer * C + rr.r0 + tid]) : 0.f;
+                    gemv_job(ring, cur, (rr.r1 - rr.r0) * nu_row, nu_row, C, xin_s, red_units);
                     for (int i = tid; i < rr.r1 - rr.r0; i += kConsumers)
-                        p.y2[rr.r0 + i] = __float2half_rn(row_sum(red_units, i, nu_row) + __half2float(b2[rr.r0 + i]));
+                        p.y2[rr.r0 + i] = __float2half_rn(row_sum(red_units, i, nu_row) + bias);
                 }
-                prof_stamp(p, pb + 13, prof_on, it, &s_prod_it);
+                const LnParams lp2 = ln_load(p.ln2_w + (size_t)layer * C, p.ln2_b + (size_t)layer * C, C);
+                prof_stamp(p, pb + 13, prof_on, cur.it, &s_prod_it);
                 grid_barrier(p.bar, epoch);
-                prof_stamp(p, pb + 14, prof_on, it, &s_prod_it);
-                if (prof_on && tid == 0) p.prof[pb + 15] = g_wait_ns;
+                prof_stamp(p, pb + 14, prof_on, cur.it, &s_prod_it);
                 // ---------------- x = LN2(x + y2) ------------------------------------------------------------------------------------------
-                residual_layer_norm(xres, xin, p.y2, false, p.ln2_w + (size_t)layer * C, p.ln2_b + (size_t)layer * C, C, red);
+                residual_layer_norm(xres, xin, p.y2, false, lp2, C, red);
             }
             // ================= lm_head: logits_pre = fp16(x) @ W^T (fp32 value before the fp16 store) ================
             {
                 RowRange rr = cta_rows(V);
-                gemv_job(ring, it, rr.r1 - rr.r0, 1, C, xin_s, red_units);
+                gemv_job(ring, cur, rr.r1 - rr.r0, 1, C, xin_s, red_units);
                 for (int i = tid; i < rr.r1 - rr.r0; i += kConsumers) p.logits[rr.r0 + i] = row_sum(red_units, i, 1);
             }
             L += 1;
@@ -813,7 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
 size_t er_decode_small_smem_bytes(const er::DecodeParams& p) {
     const int C = p.C, F = p.F;
     size_t fl = (size_t)C + er::kMaxUnits + 32 + er::HD + 2 * er::kConsumerWarps * er::HD + (size_t)p.sc_len;
-    return 2 * er::kMaxStages * 8 + fl * 4 + (size_t)(F > C ? F : C) * 2 + 128;
+    return 2 * 8 * 8 + fl * 4 + (size_t)(F > C ? F : C) * 2 + 128;
 }
 size_t er_decode_smem_bytes(const er::DecodeParams& p) { return (size_t)p.nstage * er::kStageBytes + er_decode_small_smem_bytes(p); }
 int er_decode_pick_stages(const er::DecodeParams& p, size_t smem_limit) {
@@ -824,17 +843,11 @@ int er_decode_pick_stages(const er::DecodeParams& p, size_t smem_limit) {
 }
 
 cudaError_t er_decode_launch(const er::DecodeParams& p, int grid, size_t smem, cudaStream_t stream) {
-    {
-        static int dbg = -1;
-        if (dbg < 0) { const char* e = getenv("ER_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; cudaMemcpyToSymbol(er::g_dbg, &dbg, sizeof(int)); }
-    }
     cudaError_t e = cudaFuncSetAttribute(er::decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&p};
     return cudaLaunchCooperativeKernel((const void*)er::decode_persistent_kernel, dim3(grid), dim3(er::kThreads), args, smem, stream);
 }
-
-int er_decode_read_detail(unsigned long long* out64) { return (int)cudaMemcpyFromSymbol(out64, er::g_detail, 64 * 8); }
 
 int er_decode_max_grid(size_t smem) {
     int dev = 0, sms = 0, per = 0;

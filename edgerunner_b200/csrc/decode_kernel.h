@@ -51,4 +51,3 @@ size_t er_decode_smem_bytes(const er::DecodeParams& p);
 int er_decode_pick_stages(const er::DecodeParams& p, size_t smem_limit);
 cudaError_t er_decode_launch(const er::DecodeParams& p, int grid, size_t smem, cudaStream_t stream);
 int er_decode_max_grid(size_t smem);
-int er_decode_read_detail(unsigned long long* out64);

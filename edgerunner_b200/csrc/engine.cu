@@ -508,6 +508,5 @@ extern "C" int er_debug_read_timeline(er_engine* e, uint64_t* out_host, int32_t 
     if (!e || !out_host || n < 0 || n > 4096) return set_err(ER_ERR_INVALID, "bad argument");
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out_host, e->prof, (size_t)n * 8, cudaMemcpyDeviceToHost));
-    if (n >= 4096) er_decode_read_detail((unsigned long long*)out_host + 3968);   // gemv detail stamps in the tail of the buffer
     return ER_OK;
 }

@@ -28,9 +28,6 @@ def main():
             buf = (C.c_uint64 * 4096)()
             eng.lib.er_debug_read_timeline(eng.h, buf, 4096)
             ts = np.array(list(buf)[:nslots], dtype=np.float64)
-            det = list(buf)[3968:3968 + 64]
-            nd = int(det[63])
-            if nd: print('fc1 layer5 thread0 detail (us since entry):', [round((x - det[0]) / 1e3, 2) for x in det[:nd]], flush=True)
             ahead = np.array(list(buf)[2048:2048 + nslots], dtype=np.float64)
             acc = {n: [] for n in segs}
             for l in range(1, NL):          # skip layer 0 (its first segment includes sample + embed)
