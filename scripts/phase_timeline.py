@@ -28,6 +28,9 @@ def main():
             buf = (C.c_uint64 * 4096)()
             eng.lib.er_debug_read_timeline(eng.h, buf, 4096)
             ts = np.array(list(buf)[:nslots], dtype=np.float64)
+            att = np.array(list(buf)[2048:2048 + 148], dtype=np.float64) / 1e3
+            last = np.array(list(buf)[2048 + 256:2048 + 256 + 148])
+            print('attention phase per CTA (us), layer 5: min %.2f median %.2f max %.2f; by split:' % (att[:144].min(), np.median(att[:144]), att[:144].max()), [round(float(att[s::9][:16].mean()), 2) for s in range(9)], 'last-arrivers mean %.2f others %.2f' % (att[:144][last[:144] == 1].mean(), att[:144][last[:144] == 0].mean()), flush=True)
             ahead = np.array(list(buf)[2048:2048 + nslots], dtype=np.float64)
             acc = {n: [] for n in segs}
             for l in range(1, NL):          # skip layer 0 (its first segment includes sample + embed)
@@ -36,9 +39,9 @@ def main():
                 for i, n in enumerate(segs):
                     acc[n].append((ts[pb + i] - prev) / 1e3); prev = ts[pb + i]
             waits = [ts[1 + 16 * l + 15] / 1e3 for l in range(1, NL)]
-            ah = {n: round(float(np.mean([ahead[1 + 16 * l + i] for l in range(1, NL)])), 1) for i, n in enumerate(segs)}
+            ah = {n: round(float(np.mean([ahead[1 + 16 * l + i] - ahead[1 + 16 * l + i - 1] for l in range(1, NL)])), 1) for i, n in enumerate(segs)}
             key = f'token{tok}_cta{cta}'
-            res[key] = {'L': 2050 + tok, 'ring_wait_us_per_layer(thread0)': float(np.mean(waits)), 'producer_stages_ahead_at_end_of_segment': ah, 'token_us': (ts[2 + 16 * NL] - ts[0]) / 1e3, 'layer_us': float(sum(np.mean(acc[n]) for n in segs)),
+            res[key] = {'L': 2050 + tok, 'ring_wait_us_per_layer(thread0)': float(np.mean(waits)), 'failed_try_waits_thread0_per_segment': ah, 'token_us': (ts[2 + 16 * NL] - ts[0]) / 1e3, 'layer_us': float(sum(np.mean(acc[n]) for n in segs)),
                         'segments_us_mean': {n: round(float(np.mean(acc[n])), 2) for n in segs},
                         'lm_head_us': (ts[1 + 16 * NL] - ts[16 * NL - 1]) / 1e3, 'lm_barrier_us': (ts[2 + 16 * NL] - ts[1 + 16 * NL]) / 1e3}
             print(key, json.dumps(res[key]), flush=True)
