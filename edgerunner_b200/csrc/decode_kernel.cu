@@ -34,7 +34,11 @@
 
 namespace er {
 
-constexpr int kConsumerWarps = 8;
+#ifndef ER_CONSUMER_WARPS
+#define ER_CONSUMER_WARPS 8
+#endif
+constexpr int kConsumerWarps = ER_CONSUMER_WARPS;   // 8 or 16
+constexpr int kUnitDiv = kConsumerWarps / 8;      // a weight unit is C / kUnitDiv fp16 (one unit per warp per 24 KB stage when C = 1536)
 constexpr int kConsumers = kConsumerWarps * 32;   // 256 compute threads
 constexpr int kThreads = kConsumers + 32;         // + one producer warp
 constexpr int HD = 96;                            // decoder head_dim (ArAE: 1536 / 16)
@@ -42,7 +46,7 @@ constexpr int HV = HD / 8;                        // 16-byte vectors per head ro
 constexpr int kStageBytes = 24576;                // 8 weight rows of 1536 fp16 = 4 K blocks = 128 V rows
 constexpr int kMaxStages = 8;
 constexpr int kKBlockBytes = HV * 32 * 16;        // 6144: one 32-key block of the blocked K cache
-constexpr int kMaxUnits = 64;                     // weight units (C fp16 each) a CTA owns in one phase
+constexpr int kMaxUnits = 64 * kUnitDiv;          // weight units a CTA owns in one phase
 constexpr int kPartStride = kMaxUnits + 1;        // lane-partial matrix [32][kPartStride] (odd stride: conflict-free both ways)
 
 // ---- shared-memory / mbarrier / TMA bulk copy primitives (32-bit shared-space addresses -> LDS / SYNCS / UBLKCP) ----
@@ -243,12 +247,13 @@ __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, 
 template <int NVL>
 __device__ __forceinline__ Cursor gemv_job_t(const Ring r, Cursor cur, int n_units, int nu_row, int C, uint32_t xin_s, uint32_t part_s) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int upstage = kStageBytes / (2 * C);
-    const int nvec = C >> 3;                                 // 16-byte vectors per unit
+    const int ubytes = 2 * C / kUnitDiv;                     // bytes per unit
+    const int upstage = kStageBytes / ubytes;
+    const int nvec = ubytes >> 4;                            // 16-byte vectors per unit
     const int nch = (n_units + upstage - 1) / upstage;
     float xr[NVL][8];
     {
-        const uint32_t xb = xin_s + (uint32_t)((warp % nu_row) * C) * 2;
+        const uint32_t xb = xin_s + (uint32_t)((warp % nu_row) * ubytes);
 #pragma unroll
         for (int j = 0; j < NVL; j++) {
             const int v = lane + 32 * j;
@@ -266,11 +271,13 @@ __device__ __forceinline__ Cursor gemv_job_t(const Ring r, Cursor cur, int n_uni
         const int here = min(upstage, n_units - c * upstage);
         const uint32_t st = r.stage(cur.stage);
         for (int u = warp; u < here; u += kConsumerWarps) {
-            const uint32_t wb = st + (uint32_t)u * 2 * C;
+            const uint32_t wb = st + (uint32_t)u * ubytes;
             uint4 wv[NVL];
-            if (NVL == 6) {   // C == 1536: all 192 vectors present, loads batched 3 + 3
+            if (NVL == 6 && nvec == 192) {   // C == 1536, full rows: loads batched 3 + 3
                 lds128x3(wb + lane * 16, wv[0], wv[1], wv[2]);
                 lds128x3(wb + lane * 16 + 1536, wv[3 % NVL], wv[4 % NVL], wv[5 % NVL]);
+            } else if (NVL == 3 && nvec == 96) {   // C == 1536, half rows
+                lds128x3(wb + lane * 16, wv[0], wv[1 % NVL], wv[2 % NVL]);
             } else {
 #pragma unroll
                 for (int j = 0; j < NVL; j++) {
@@ -298,8 +305,8 @@ __device__ __forceinline__ Cursor gemv_job_t(const Ring r, Cursor cur, int n_uni
 }
 // (the cursor travels by value so that it stays in registers across the call)
 __device__ __noinline__ Cursor gemv_job(const Ring r, Cursor cur, int n_units, int nu_row, int C, uint32_t xin_s, uint32_t part_s) {
-    if (C == 1536) return gemv_job_t<6>(r, cur, n_units, nu_row, C, xin_s, part_s);
-    const int nvl = ((C >> 3) + 31) >> 5;
+    if (C == 1536) return gemv_job_t<6 / kUnitDiv>(r, cur, n_units, nu_row, C, xin_s, part_s);
+    const int nvl = ((C / kUnitDiv >> 3) + 31) >> 5;
     if (nvl <= 1) return gemv_job_t<1>(r, cur, n_units, nu_row, C, xin_s, part_s);
     if (nvl == 2) return gemv_job_t<2>(r, cur, n_units, nu_row, C, xin_s, part_s);
     if (nvl <= 4) return gemv_job_t<4>(r, cur, n_units, nu_row, C, xin_s, part_s);
@@ -364,11 +371,11 @@ __device__ __noinline__ void residual_layer_norm(uint32_t xres_s, uint32_t x16_s
         s += __shfl_xor_sync(0xffffffffu, s, o);
         q += __shfl_xor_sync(0xffffffffu, q, o);
     }
-    if ((t & 31) == 0) { red[t >> 5] = s; red[8 + (t >> 5)] = q; }
+    if ((t & 31) == 0) { red[t >> 5] = s; red[16 + (t >> 5)] = q; }
     cbar();
     float ts = 0.f, tq = 0.f;
 #pragma unroll
-    for (int i = 0; i < kConsumerWarps; i++) { ts += red[i]; tq += red[8 + i]; }
+    for (int i = 0; i < kConsumerWarps; i++) { ts += red[i]; tq += red[16 + i]; }
     const float mean = ts * inv_c;
     const float var = fmaxf(tq * inv_c - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
@@ -570,9 +577,9 @@ __device__ __noinline__ Cursor attention_phase(const DecodeParams& p, const Ring
         // merge the warp maxima; fw[w] rescales keys normalised by warp w
 #pragma unroll
         for (int w = 0; w < kConsumerWarps; w++) M = fmaxf(M, red[w]);
-        if (tid < kConsumerWarps) red[16 + tid] = (red[tid] == -INFINITY) ? 0.f : exp2f((red[tid] - M) * cl2);
+        if (tid < kConsumerWarps) red[32 + tid] = (red[tid] == -INFINITY) ? 0.f : exp2f((red[tid] - M) * cl2);
         cbar();
-        const uint32_t fw_s = s_addr(red + 16);
+        const uint32_t fw_s = s_addr(red + 32);
         // ---- V pass (also accumulates the softmax denominator on the vec == 0 lanes) ----
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float lsum = 0.f;
@@ -603,7 +610,7 @@ __device__ __noinline__ Cursor attention_phase(const DecodeParams& p, const Ring
         if (lane < 2 * HV) {
 #pragma unroll
             for (int e = 0; e < 8; e++) vred[(warp * 2 + sub) * HD + vec * 8 + e] = o[e];
-            if (vec == 0) red[32 + warp * 2 + sub] = lsum;
+            if (vec == 0) red[64 + warp * 2 + sub] = lsum;
         }
         cbar();
     }
@@ -614,14 +621,14 @@ __device__ __noinline__ Cursor attention_phase(const DecodeParams& p, const Ring
         if (nk > 0) {
 #pragma unroll 4
             for (int g = 0; g < 2 * kConsumerWarps; g++) acc += vred[g * HD + tid];
-            if (a.is_new) acc = fmaf(sc[new_slot] * red[16], __half2float(__ushort_as_half(vnew)), acc);   // new key: normalised by warp 0
+            if (a.is_new) acc = fmaf(sc[new_slot] * red[32], __half2float(__ushort_as_half(vnew)), acc);   // new key: normalised by warp 0
         }
         outp[tid] = acc;
     } else if (tid == HD) {
         float l = 0.f;
         if (nk > 0) {
-            for (int g = 0; g < 2 * kConsumerWarps; g++) l += red[32 + g];
-            if (a.is_new) l += sc[new_slot] * red[16];
+            for (int g = 0; g < 2 * kConsumerWarps; g++) l += red[64 + g];
+            if (a.is_new) l += sc[new_slot] * red[32];
         }
         outp[HD] = (nk > 0) ? M * rsqrtf((float)HD) : -INFINITY;        // max in softmax (scaled) units
         outp[HD + 1] = l;
@@ -674,8 +681,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
     ring.empty = ring.full + kMaxStages * 8;
     float* xres = reinterpret_cast<float*>(q + 2 * kMaxStages * 8);   // [C]   residual stream (fp32)
     float* part = xres + C;                                           // [32][kPartStride] GEMV lane partials
-    float* red = part + 32 * kPartStride;                             // [64] block-reduction scratch
-    float* qs = red + 64;                                             // [96] query of this CTA's head (fp32)
+    float* red = part + 32 * kPartStride;                             // [128] block-reduction scratch
+    float* qs = red + 128;                                            // [96] query of this CTA's head (fp32)
     float* vred = qs + HD;                                            // [16*96] V-pass cross-warp reduction
     float* sc = vred + 2 * kConsumerWarps * HD;                       // [sc_len] scores / sampler scratch
     __half* xin = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(sc + p.sc_len) + 15) & ~uintptr_t(15));   // [max(C,F)] GEMV input (fp16)
@@ -707,7 +714,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
         const bool done0 = p.st->done != 0;
         bool state_written = done0;
         const size_t nkb = (size_t)p.nkb;
-        const int nu_fc2 = F / C;
+        const int nu_fc2 = (F / C) * kUnitDiv;      // units per fc2 row
+        const int nu1 = kUnitDiv;                   // units per row of the C-wide phases
         for (int iter = 0; iter < p.steps && !done0; ++iter, ++t) {
             const bool prof_on = p.prof != nullptr && t == p.prof_token && (int)blockIdx.x == p.prof_cta;
             prof_stamp(p, 0, prof_on);
@@ -749,13 +757,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                     const RowRange rr = cta_rows(3 * C);
                     const int nr = rr.r1 - rr.r0;
                     prof_stamp(p, pb + 0, prof_on);
-                    const float bias = (tid < nr) ? __half2float(p.bqkv[(size_t)layer * 3 * C + rr.r0 + tid]) : 0.f;   // in flight during the GEMV
-                    cur = gemv_job(ring, cur, nr, 1, C, xin_s, part_s);
+                    const int nu = nr * nu1;
+                    const bool own = tid < nu && (tid % nu1) == 0;
+                    const float bias = own ? __half2float(p.bqkv[(size_t)layer * 3 * C + rr.r0 + tid / nu1]) : 0.f;   // in flight during the GEMV
+                    cur = gemv_job(ring, cur, nu, nu1, C, xin_s, part_s);
                     prof_stamp(p, pb + 1, prof_on);
-                    if (warp * 32 < nr) {
-                        const float sum = reduce_rows(part_s, nr, 1);
-                        if (tid < nr) {
-                            const int r = rr.r0 + tid;
+                    if (warp * 32 < nu) {
+                        const float sum = reduce_rows(part_s, nu, nu1);
+                        if (own) {
+                            const int r = rr.r0 + tid / nu1;
                             const __half hv = __float2half_rn(sum + bias);
                             if (r < C) {
                                 p.q16[r] = hv;
@@ -794,11 +804,13 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                     const RowRange rr = cta_rows(C);
                     const int nr = rr.r1 - rr.r0;
                     prof_stamp(p, pb + 6, prof_on);
-                    const float bias = (tid < nr) ? __half2float(p.bo[(size_t)layer * C + rr.r0 + tid]) : 0.f;
-                    cur = gemv_job(ring, cur, nr, 1, C, xin_s, part_s);
-                    if (warp * 32 < nr) {
-                        const float sum = reduce_rows(part_s, nr, 1);
-                        if (tid < nr) p.y1[rr.r0 + tid] = __float2half_rn(sum + bias);
+                    const int nu = nr * nu1;
+                    const bool own = tid < nu && (tid % nu1) == 0;
+                    const float bias = own ? __half2float(p.bo[(size_t)layer * C + rr.r0 + tid / nu1]) : 0.f;
+                    cur = gemv_job(ring, cur, nu, nu1, C, xin_s, part_s);
+                    if (warp * 32 < nu) {
+                        const float sum = reduce_rows(part_s, nu, nu1);
+                        if (own) p.y1[rr.r0 + tid / nu1] = __float2half_rn(sum + bias);
                     }
                 }
                 const LnParams lp1 = ln_load(p.ln1_w + (size_t)layer * C, p.ln1_b + (size_t)layer * C, C);   // lands while we wait at the barrier
@@ -811,11 +823,13 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                     const RowRange rr = cta_rows(F);
                     const int nr = rr.r1 - rr.r0;
                     prof_stamp(p, pb + 9, prof_on);
-                    const float bias = (tid < nr) ? __half2float(p.b1[(size_t)layer * F + rr.r0 + tid]) : 0.f;
-                    cur = gemv_job(ring, cur, nr, 1, C, xin_s, part_s);
-                    if (warp * 32 < nr) {
-                        const float sum = reduce_rows(part_s, nr, 1);
-                        if (tid < nr) p.h1[rr.r0 + tid] = __float2half_rn(fmaxf(round_f16(sum + bias), 0.f));
+                    const int nu = nr * nu1;
+                    const bool own = tid < nu && (tid % nu1) == 0;
+                    const float bias = own ? __half2float(p.b1[(size_t)layer * F + rr.r0 + tid / nu1]) : 0.f;
+                    cur = gemv_job(ring, cur, nu, nu1, C, xin_s, part_s);
+                    if (warp * 32 < nu) {
+                        const float sum = reduce_rows(part_s, nu, nu1);
+                        if (own) p.h1[rr.r0 + tid / nu1] = __float2half_rn(fmaxf(round_f16(sum + bias), 0.f));
                     }
                 }
                 prof_stamp(p, pb + 10, prof_on);
@@ -847,10 +861,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
             {
                 const RowRange rr = cta_rows(V);
                 const int nr = rr.r1 - rr.r0;
-                cur = gemv_job(ring, cur, nr, 1, C, xin_s, part_s);
-                if (warp * 32 < nr) {
-                    const float sum = reduce_rows(part_s, nr, 1);
-                    if (tid < nr) p.logits[rr.r0 + tid] = sum;
+                const int nu = nr * nu1;
+                cur = gemv_job(ring, cur, nu, nu1, C, xin_s, part_s);
+                if (warp * 32 < nu) {
+                    const float sum = reduce_rows(part_s, nu, nu1);
+                    if (tid < nu && (tid % nu1) == 0) p.logits[rr.r0 + tid / nu1] = sum;
                 }
             }
             L += 1;
@@ -868,7 +883,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
 // ---- host launcher -------------------------------------------------------------------------------------------------------------------------
 size_t er_decode_small_smem_bytes(const er::DecodeParams& p) {
     const int C = p.C, F = p.F;
-    size_t fl = (size_t)C + 32 * er::kPartStride + 64 + er::HD + 2 * er::kConsumerWarps * er::HD + (size_t)p.sc_len;
+    size_t fl = (size_t)C + 32 * er::kPartStride + 128 + er::HD + 2 * er::kConsumerWarps * er::HD + (size_t)p.sc_len;
     return 2 * er::kMaxStages * 8 + fl * 4 + (size_t)(F > C ? F : C) * 2 + 128;
 }
 size_t er_decode_smem_bytes(const er::DecodeParams& p) { return (size_t)p.nstage * er::kStageBytes + er_decode_small_smem_bytes(p); }

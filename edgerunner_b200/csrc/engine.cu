@@ -391,7 +391,7 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.nstage = e->nstage; p.sc_len = e->sc_len;
     // red_units holds 2 partial sums per unit of C elements: the widest phases are qkv (rows) and fc2 (rows * F/C)
     const int max_units = std::max(std::max((3 * C + G - 1) / G + 1, (F + G - 1) / G + 1), ((C + G - 1) / G + 1) * (F / C));
-    if (max_units > 64 || F % C || C % 16 || C > 1536 || (8 % (F / C)) || ((24576 / (2 * C)) % (F / C)) || e->H > 64) return set_err(ER_ERR_CAPACITY, "model shape not supported by the decode kernel on %d SMs (units %d)", G, max_units);
+    if (max_units > 64 || (C / 2) % 8 || F % C || C % 16 || C > 1536 || (8 % (F / C)) || ((24576 / (2 * C)) % (F / C)) || e->H > 64) return set_err(ER_ERR_CAPACITY, "model shape not supported by the decode kernel on %d SMs (units %d)", G, max_units);
     p.wqkv = e->wqkv; p.bqkv = e->bqkv; p.wo = e->wo; p.bo = e->bo; p.ln1_w = e->ln1w; p.ln1_b = e->ln1b;
     p.w1 = e->w1; p.b1 = e->b1; p.w2 = e->w2; p.b2 = e->b2; p.ln2_w = e->ln2w; p.ln2_b = e->ln2b;
     p.lm_head = e->lm_head; p.embd = e->embd; p.pos = e->pos;
