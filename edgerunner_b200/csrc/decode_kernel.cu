@@ -38,14 +38,17 @@ namespace er {
 #define ER_CONSUMER_WARPS 8
 #endif
 constexpr int kConsumerWarps = ER_CONSUMER_WARPS;   // 8 or 16
-constexpr int kUnitDiv = kConsumerWarps / 8;      // a weight unit is C / kUnitDiv fp16 (one unit per warp per 24 KB stage when C = 1536)
+constexpr int kUnitDiv = 1;                       // a weight unit is one K-slice of C fp16
+static_assert(kConsumerWarps == 8, "the GEMV consumers assume 8 warps (one K-eighth / one unit per warp)");
 constexpr int kConsumers = kConsumerWarps * 32;   // 256 compute threads
 constexpr int kThreads = kConsumers + 32;         // + one producer warp
 constexpr int HD = 96;                            // decoder head_dim (ArAE: 1536 / 16)
 constexpr int HV = HD / 8;                        // 16-byte vectors per head row (12)
-constexpr int kStageBytes = 24576;                // 8 weight rows of 1536 fp16 = 4 K blocks = 128 V rows
+constexpr int kStageBytes = 24704;                // 8 padded weight units of (1536 + 8) fp16; also holds 4 K blocks / 128 V rows
+constexpr int kKVChunk = 24576;                   // bytes per stage of the K / V jobs (4 K blocks = 128 V rows)
 constexpr int kMaxStages = 8;
 constexpr int kKBlockBytes = HV * 32 * 16;        // 6144: one 32-key block of the blocked K cache
+constexpr int kLastSplitHandicap = 7;             // see attn_range()
 constexpr int kMaxUnits = 64 * kUnitDiv;          // weight units a CTA owns in one phase
 constexpr int kPartStride = kMaxUnits + 1;        // lane-partial matrix [32][kPartStride] (odd stride: conflict-free both ways)
 
@@ -165,7 +168,9 @@ __device__ __forceinline__ bool attn_range(const DecodeParams& p, int L, AttnRan
     a.h = blockIdx.x / p.S;
     const int s = blockIdx.x % p.S;
     const int nblk = (L + 31) >> 5;                  // blocks holding old keys 0..L-1
-    const int bps = (nblk + p.S - 1) / p.S;
+    // the last split also owns the new key and (being the last to finish) usually merges the head: that fixed work is worth
+    // about p.split_handicap (<= kLastSplitHandicap) blocks of streaming, so it gets that many fewer blocks
+    const int bps = (nblk + p.split_handicap + p.S - 1) / p.S;
     a.b0 = min(s * bps, nblk);
     a.b1 = min(a.b0 + bps, nblk);
     a.k0 = a.b0 * 32;
@@ -191,14 +196,14 @@ struct Cursor {        // ring position; producer and every consumer warp advanc
 
 // ---- producer: stream one contiguous byte range through the ring ---------------------------------------------------------------------
 // returns false if the consumers raised `stop` (EOS) while we were waiting for a free stage
-__device__ __forceinline__ bool produce(const Ring r, Cursor& cur, const void* base, size_t bytes, volatile int* stop) {
+__device__ __forceinline__ bool produce(const Ring r, Cursor& cur, const void* base, size_t bytes, uint32_t chunk, volatile int* stop) {
     const char* src = reinterpret_cast<const char*>(base);
-    for (size_t off = 0; off < bytes; off += kStageBytes, cur.advance(r.nstage)) {
+    for (size_t off = 0; off < bytes; off += chunk, cur.advance(r.nstage)) {
         while (!mbar_try_wait(r.emptyb(cur.stage), cur.parity ^ 1)) {
             if (*stop) return false;
         }
         if (*stop) return false;
-        const uint32_t n = (uint32_t)(bytes - off < (size_t)kStageBytes ? bytes - off : (size_t)kStageBytes);
+        const uint32_t n = (uint32_t)(bytes - off < (size_t)chunk ? bytes - off : (size_t)chunk);
         mbar_arrive_expect_tx(r.fullb(cur.stage), n);
         bulk_g2s(r.stage(cur.stage), src + off, n, r.fullb(cur.stage));
     }
@@ -213,25 +218,32 @@ __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, 
     const int n_fwd = min(p.steps, p.max_new - 1 - t);
     Cursor cur{0u, 0u, 0u};
     bool ok = true;
+    // decode weights live in `wdec` as units of C fp16 padded to `ustride` (bank-conflict-free ldmatrix rows); per layer:
+    // [3C qkv rows][C out_proj rows][F fc1 rows][C fc2 rows x F/C units]; after the layers: V lm_head rows.
+    const size_t ub = (size_t)p.ustride * 2;
+    const uint32_t wchunk = (uint32_t)(p.upstage * ub);
+    const int nuf = F / C;
+    const size_t UL = (size_t)4 * C + 2 * (size_t)F;
     for (int pass = 0; pass < n_fwd && ok; ++pass, ++L) {
         for (int layer = 0; layer < p.layers && ok; ++layer) {
+            const __half* wl = p.wdec + (size_t)layer * UL * p.ustride;
             RowRange rr = cta_rows(3 * C);
-            ok = produce(r, cur, p.wqkv + ((size_t)layer * 3 * C + rr.r0) * C, (size_t)(rr.r1 - rr.r0) * C * 2, stop);
+            ok = produce(r, cur, wl + (size_t)rr.r0 * p.ustride, (size_t)(rr.r1 - rr.r0) * ub, wchunk, stop);
             AttnRange a;
             if (ok && attn_range(p, L, a)) {
                 const __half* kbase = p.kc + (((size_t)layer * H + a.h) * p.nkb + a.b0) * (size_t)(HV * 256);
-                ok = produce(r, cur, kbase, (size_t)(a.b1 - a.b0) * kKBlockBytes, stop);
+                ok = produce(r, cur, kbase, (size_t)(a.b1 - a.b0) * kKBlockBytes, kKVChunk, stop);
                 const __half* vbase = p.vc + (((size_t)layer * H + a.h) * p.Lmax + a.k0) * HD;
-                if (ok) ok = produce(r, cur, vbase, (size_t)(a.k1 - a.k0) * HD * 2, stop);
+                if (ok) ok = produce(r, cur, vbase, (size_t)(a.k1 - a.k0) * HD * 2, kKVChunk, stop);
             }
             rr = cta_rows(C);
-            if (ok) ok = produce(r, cur, p.wo + ((size_t)layer * C + rr.r0) * C, (size_t)(rr.r1 - rr.r0) * C * 2, stop);
+            if (ok) ok = produce(r, cur, wl + ((size_t)3 * C + rr.r0) * p.ustride, (size_t)(rr.r1 - rr.r0) * ub, wchunk, stop);
             RowRange rf = cta_rows(F);
-            if (ok) ok = produce(r, cur, p.w1 + ((size_t)layer * F + rf.r0) * C, (size_t)(rf.r1 - rf.r0) * C * 2, stop);
-            if (ok) ok = produce(r, cur, p.w2 + ((size_t)layer * C + rr.r0) * F, (size_t)(rr.r1 - rr.r0) * F * 2, stop);
+            if (ok) ok = produce(r, cur, wl + ((size_t)4 * C + rf.r0) * p.ustride, (size_t)(rf.r1 - rf.r0) * ub, wchunk, stop);
+            if (ok) ok = produce(r, cur, wl + ((size_t)4 * C + F + (size_t)rr.r0 * nuf) * p.ustride, (size_t)(rr.r1 - rr.r0) * nuf * ub, wchunk, stop);
         }
         RowRange rv = cta_rows(p.V);
-        if (ok) ok = produce(r, cur, p.lm_head + (size_t)rv.r0 * C, (size_t)(rv.r1 - rv.r0) * C * 2, stop);
+        if (ok) ok = produce(r, cur, p.wdec + ((size_t)p.layers * UL + rv.r0) * p.ustride, (size_t)(rv.r1 - rv.r0) * ub, wchunk, stop);
     }
     if (!ok) {
         // EOS: the consumers stopped at stage *cons_it; every copy we issued beyond it must land before the CTA may exit
@@ -245,15 +257,14 @@ __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, 
 // unit it ever touches in this job and lives in registers.  No cross-lane reduction here: lane partials go to part[lane][unit]
 // and are summed per output row by reduce_rows() after the job.  NVL = 16-byte vectors per lane per unit (6 for C = 1536).
 template <int NVL>
-__device__ __forceinline__ Cursor gemv_job_t(const Ring r, Cursor cur, int n_units, int nu_row, int C, uint32_t xin_s, uint32_t part_s) {
+__device__ __forceinline__ Cursor gemv_job_t(const Ring r, Cursor cur, int n_units, int nu_row, int C, int ustride, int upstage, uint32_t xin_s, uint32_t part_s) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ubytes = 2 * C / kUnitDiv;                     // bytes per unit
-    const int upstage = kStageBytes / ubytes;
-    const int nvec = ubytes >> 4;                            // 16-byte vectors per unit
+    const int ubytes = ustride * 2;                          // bytes per (padded) unit
+    const int nvec = C >> 3;                                 // 16-byte vectors of payload per unit
     const int nch = (n_units + upstage - 1) / upstage;
     float xr[NVL][8];
     {
-        const uint32_t xb = xin_s + (uint32_t)((warp % nu_row) * ubytes);
+        const uint32_t xb = xin_s + (uint32_t)((warp % nu_row) * C) * 2;
 #pragma unroll
         for (int j = 0; j < NVL; j++) {
             const int v = lane + 32 * j;
@@ -273,17 +284,10 @@ __device__ __forceinline__ Cursor gemv_job_t(const Ring r, Cursor cur, int n_uni
         for (int u = warp; u < here; u += kConsumerWarps) {
             const uint32_t wb = st + (uint32_t)u * ubytes;
             uint4 wv[NVL];
-            if (NVL == 6 && nvec == 192) {   // C == 1536, full rows: loads batched 3 + 3
-                lds128x3(wb + lane * 16, wv[0], wv[1], wv[2]);
-                lds128x3(wb + lane * 16 + 1536, wv[3 % NVL], wv[4 % NVL], wv[5 % NVL]);
-            } else if (NVL == 3 && nvec == 96) {   // C == 1536, half rows
-                lds128x3(wb + lane * 16, wv[0], wv[1 % NVL], wv[2 % NVL]);
-            } else {
 #pragma unroll
-                for (int j = 0; j < NVL; j++) {
-                    const int v = lane + 32 * j;
-                    wv[j] = (v < nvec) ? lds128(wb + v * 16) : make_uint4(0, 0, 0, 0);
-                }
+            for (int j = 0; j < NVL; j++) {
+                const int v = lane + 32 * j;
+                wv[j] = (v < nvec) ? lds128(wb + v * 16) : make_uint4(0, 0, 0, 0);
             }
             float tot = 0.f;
 #pragma unroll
@@ -303,24 +307,109 @@ __device__ __forceinline__ Cursor gemv_job_t(const Ring r, Cursor cur, int n_uni
     cbar();
     return cur;
 }
-// (the cursor travels by value so that it stays in registers across the call)
-__device__ __noinline__ Cursor gemv_job(const Ring r, Cursor cur, int n_units, int nu_row, int C, uint32_t xin_s, uint32_t part_s) {
-    if (C == 1536) return gemv_job_t<6 / kUnitDiv>(r, cur, n_units, nu_row, C, xin_s, part_s);
-    const int nvl = ((C / kUnitDiv >> 3) + 31) >> 5;
-    if (nvl <= 1) return gemv_job_t<1>(r, cur, n_units, nu_row, C, xin_s, part_s);
-    if (nvl == 2) return gemv_job_t<2>(r, cur, n_units, nu_row, C, xin_s, part_s);
-    if (nvl <= 4) return gemv_job_t<4>(r, cur, n_units, nu_row, C, xin_s, part_s);
-    return gemv_job_t<5>(r, cur, n_units, nu_row, C, xin_s, part_s);
+
+// ---- tensor-core GEMV (C % 256 == 0): one stage = 8 weight units = the 8 columns of an m16n8k16 B operand -------------------------
+// The CUDA-core loop above needs ~17 instructions per 16 weights per lane (fp16->fp32 converts + FMAs) and is issue/latency
+// bound at 8 warps.  Here each warp owns 1/8 of the K range of ALL 8 units of a stage: ldmatrix.x4 pulls two k16 steps of the
+// 8 unit rows (rows are padded to C+8 fp16 in HBM, so the 8 row addresses hit distinct banks), mma.sync accumulates
+// x . W^T in fp32 (fp16 products are exact; same numerics class as the cuBLAS GEMV the reference calls).  The A operand
+// carries x: row m holds the x slice of unit column m % nu_row (a K = nu_row * C row spans nu_row consecutive units), kept in
+// registers for the whole phase.  The wanted outputs D[n % nu_row][n] are written as per-warp partials to part[warp][unit].
+// KS = k16 steps per warp (C / 128).
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
-// Sum the 32 lane partials of each unit and the nu_row (1, 2, 4 or 8) units of each output row; thread t owns unit t.
+__device__ __forceinline__ void mma_16816(float* d, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a0), "r"(a2), "r"(a2), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+// six / three / ... ldmatrix.x4 issued back to back in one asm statement (two k16 steps each, 64 bytes apart)
+template <int N>
+__device__ __forceinline__ void ldmatrix_batch(uint32_t addr, uint32_t (*b)[4]) {
+#pragma unroll
+    for (int i = 0; i < N; i++) ldmatrix_x4(addr + i * 64, b[i][0], b[i][1], b[i][2], b[i][3]);
+}
+template <>
+__device__ __forceinline__ void ldmatrix_batch<6>(uint32_t addr, uint32_t (*b)[4]) {
+    asm volatile(
+        "ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%24];\n\t"
+        "ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%4,%5,%6,%7}, [%24+64];\n\t"
+        "ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%8,%9,%10,%11}, [%24+128];\n\t"
+        "ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%12,%13,%14,%15}, [%24+192];\n\t"
+        "ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%16,%17,%18,%19}, [%24+256];\n\t"
+        "ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%20,%21,%22,%23}, [%24+320];"
+        : "=r"(b[0][0]), "=r"(b[0][1]), "=r"(b[0][2]), "=r"(b[0][3]), "=r"(b[1][0]), "=r"(b[1][1]), "=r"(b[1][2]), "=r"(b[1][3]),
+          "=r"(b[2][0]), "=r"(b[2][1]), "=r"(b[2][2]), "=r"(b[2][3]), "=r"(b[3][0]), "=r"(b[3][1]), "=r"(b[3][2]), "=r"(b[3][3]),
+          "=r"(b[4][0]), "=r"(b[4][1]), "=r"(b[4][2]), "=r"(b[4][3]), "=r"(b[5][0]), "=r"(b[5][1]), "=r"(b[5][2]), "=r"(b[5][3])
+        : "r"(addr));
+}
+template <int KS>
+__device__ __forceinline__ Cursor gemv_job_mma(const Ring r, Cursor cur, int n_units, int nu_row, int C, int ustride, uint32_t xin_s, uint32_t part_s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ubytes = ustride * 2;
+    const int nch = (n_units + 7) >> 3;
+    const int k0 = warp * (C >> 3);                          // this warp's K range: [k0, k0 + C/8)
+    uint32_t xa[KS][2];                                      // A fragments (rows g and g+8 carry the same x slice)
+    {
+        const uint32_t xb = xin_s + (uint32_t)((g % nu_row) * C + k0 + 2 * t) * 2;
+#pragma unroll
+        for (int s = 0; s < KS; s++) { xa[s][0] = lds_u32(xb + s * 32); xa[s][1] = lds_u32(xb + s * 32 + 16); }
+    }
+    // D[row g][cols 2t, 2t+1]: column n is wanted from row n % nu_row — decided once, not per stage
+    const bool w0 = g == ((2 * t) % nu_row), w1 = g == ((2 * t + 1) % nu_row);
+    const uint32_t row_off = (uint32_t)(lane & 7) * ubytes + (uint32_t)(k0 + (lane >> 3) * 8) * 2;
+    const uint32_t pw = part_s + (uint32_t)warp * kPartStride * 4 + (uint32_t)(2 * t) * 4;
+    int left = n_units;
+    for (int c = 0; c < nch; ++c, left -= 8, cur.advance(r.nstage)) {
+        mbar_wait(r.fullb(cur.stage), cur.parity);
+        uint32_t b[KS / 2][4];
+        ldmatrix_batch<KS / 2>(r.stage(cur.stage) + row_off, b);
+        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};      // two independent accumulator chains
+#pragma unroll
+        for (int s2 = 0; s2 < KS / 2; s2++) {
+            mma_16816(d0, xa[2 * s2][0], xa[2 * s2][1], b[s2][0], b[s2][1]);
+            mma_16816(d1, xa[2 * s2 + 1][0], xa[2 * s2 + 1][1], b[s2][2], b[s2][3]);
+        }
+        if (w0 && 2 * t < left) sts32(pw + (uint32_t)c * 32, d0[0] + d1[0]);
+        if (w1 && 2 * t + 1 < left) sts32(pw + (uint32_t)c * 32 + 4, d0[1] + d1[1]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
+    }
+    cbar();
+    return cur;
+}
+// (the cursor travels by value so that it stays in registers across the call)
+struct GemvCfg { int C, ustride, upstage, use_mma; };     // by value: stays in registers (a reference to the kernel params would be LDL traffic)
+__device__ __noinline__ Cursor gemv_job(const Ring r, Cursor cur, int n_units, int nu_row, const GemvCfg gc, uint32_t xin_s, uint32_t part_s) {
+    const int C = gc.C;
+    if (gc.use_mma) {
+        if (C == 1536) return gemv_job_mma<12>(r, cur, n_units, nu_row, C, gc.ustride, xin_s, part_s);
+        if (C == 768) return gemv_job_mma<6>(r, cur, n_units, nu_row, C, gc.ustride, xin_s, part_s);
+        if (C == 1024) return gemv_job_mma<8>(r, cur, n_units, nu_row, C, gc.ustride, xin_s, part_s);
+        if (C == 512) return gemv_job_mma<4>(r, cur, n_units, nu_row, C, gc.ustride, xin_s, part_s);
+        return gemv_job_mma<2>(r, cur, n_units, nu_row, C, gc.ustride, xin_s, part_s);   // C == 256
+    }
+    const int nvl = ((C >> 3) + 31) >> 5;
+    if (nvl <= 1) return gemv_job_t<1>(r, cur, n_units, nu_row, C, gc.ustride, gc.upstage, xin_s, part_s);
+    if (nvl == 2) return gemv_job_t<2>(r, cur, n_units, nu_row, C, gc.ustride, gc.upstage, xin_s, part_s);
+    if (nvl <= 4) return gemv_job_t<4>(r, cur, n_units, nu_row, C, gc.ustride, gc.upstage, xin_s, part_s);
+    return gemv_job_t<6>(r, cur, n_units, nu_row, C, gc.ustride, gc.upstage, xin_s, part_s);
+}
+// Sum the partials of each unit (32 lanes on the CUDA-core path, 8 warps on the tensor-core path) and the nu_row (1, 2, 4 or 8) units of each output row; thread t owns unit t.
 // Returns the row sum on threads with t % nu_row == 0 (row t / nu_row); every thread of a participating warp must call it.
-__device__ __forceinline__ float reduce_rows(uint32_t part_s, int n_units, int nu_row) {
+__device__ __forceinline__ float reduce_rows(uint32_t part_s, int n_units, int nu_row, int nparts) {
     const int t = threadIdx.x;
     float s = 0.f;
     if (t < n_units) {
         const uint32_t pb = part_s + (uint32_t)t * 4;
 #pragma unroll 8
-        for (int l = 0; l < 32; l++) s += lds32(pb + (uint32_t)l * kPartStride * 4);
+        for (int l = 0; l < nparts; l++) s += lds32(pb + (uint32_t)l * kPartStride * 4);
     }
     for (int o = 1; o < nu_row; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
@@ -716,6 +805,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
         const size_t nkb = (size_t)p.nkb;
         const int nu_fc2 = (F / C) * kUnitDiv;      // units per fc2 row
         const int nu1 = kUnitDiv;                   // units per row of the C-wide phases
+        const int nparts = p.use_mma ? kConsumerWarps : 32;
+        const GemvCfg gc{p.C, p.ustride, p.upstage, p.use_mma};
         for (int iter = 0; iter < p.steps && !done0; ++iter, ++t) {
             const bool prof_on = p.prof != nullptr && t == p.prof_token && (int)blockIdx.x == p.prof_cta;
             prof_stamp(p, 0, prof_on);
@@ -760,10 +851,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                     const int nu = nr * nu1;
                     const bool own = tid < nu && (tid % nu1) == 0;
                     const float bias = own ? __half2float(p.bqkv[(size_t)layer * 3 * C + rr.r0 + tid / nu1]) : 0.f;   // in flight during the GEMV
-                    cur = gemv_job(ring, cur, nu, nu1, C, xin_s, part_s);
+                    cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
                     prof_stamp(p, pb + 1, prof_on);
                     if (warp * 32 < nu) {
-                        const float sum = reduce_rows(part_s, nu, nu1);
+                        const float sum = reduce_rows(part_s, nu, nu1, nparts);
                         if (own) {
                             const int r = rr.r0 + tid / nu1;
                             const __half hv = __float2half_rn(sum + bias);
@@ -807,9 +898,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                     const int nu = nr * nu1;
                     const bool own = tid < nu && (tid % nu1) == 0;
                     const float bias = own ? __half2float(p.bo[(size_t)layer * C + rr.r0 + tid / nu1]) : 0.f;
-                    cur = gemv_job(ring, cur, nu, nu1, C, xin_s, part_s);
+                    cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
                     if (warp * 32 < nu) {
-                        const float sum = reduce_rows(part_s, nu, nu1);
+                        const float sum = reduce_rows(part_s, nu, nu1, nparts);
                         if (own) p.y1[rr.r0 + tid / nu1] = __float2half_rn(sum + bias);
                     }
                 }
@@ -826,9 +917,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                     const int nu = nr * nu1;
                     const bool own = tid < nu && (tid % nu1) == 0;
                     const float bias = own ? __half2float(p.b1[(size_t)layer * F + rr.r0 + tid / nu1]) : 0.f;
-                    cur = gemv_job(ring, cur, nu, nu1, C, xin_s, part_s);
+                    cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
                     if (warp * 32 < nu) {
-                        const float sum = reduce_rows(part_s, nu, nu1);
+                        const float sum = reduce_rows(part_s, nu, nu1, nparts);
                         if (own) p.h1[rr.r0 + tid / nu1] = __float2half_rn(fmaxf(round_f16(sum + bias), 0.f));
                     }
                 }
@@ -844,9 +935,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                     const int nr = rr.r1 - rr.r0, nu = nr * nu_fc2;
                     prof_stamp(p, pb + 12, prof_on);
                     const float bias = (tid < nu && (tid % nu_fc2) == 0) ? __half2float(p.b2[(size_t)layer * C + rr.r0 + tid / nu_fc2]) : 0.f;
-                    cur = gemv_job(ring, cur, nu, nu_fc2, C, xin_s, part_s);
+                    cur = gemv_job(ring, cur, nu, nu_fc2, gc, xin_s, part_s);
                     if (warp * 32 < nu) {
-                        const float sum = reduce_rows(part_s, nu, nu_fc2);
+                        const float sum = reduce_rows(part_s, nu, nu_fc2, nparts);
                         if (tid < nu && (tid % nu_fc2) == 0) p.y2[rr.r0 + tid / nu_fc2] = __float2half_rn(sum + bias);
                     }
                 }
@@ -862,9 +953,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                 const RowRange rr = cta_rows(V);
                 const int nr = rr.r1 - rr.r0;
                 const int nu = nr * nu1;
-                cur = gemv_job(ring, cur, nu, nu1, C, xin_s, part_s);
+                cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
                 if (warp * 32 < nu) {
-                    const float sum = reduce_rows(part_s, nu, nu1);
+                    const float sum = reduce_rows(part_s, nu, nu1, nparts);
                     if (tid < nu && (tid % nu1) == 0) p.logits[rr.r0 + tid / nu1] = sum;
                 }
             }
@@ -894,6 +985,7 @@ int er_decode_pick_stages(const er::DecodeParams& p, size_t smem_limit) {
     return n > er::kMaxStages ? er::kMaxStages : n;
 }
 int er_decode_max_units() { return er::kMaxUnits; }
+int er_decode_stage_bytes() { return er::kStageBytes; }
 
 cudaError_t er_decode_launch(const er::DecodeParams& p, int grid, size_t smem, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(er::decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -26,6 +26,9 @@ struct DecodeParams {
     // decoder weights, fp16, nn.Linear layout [out][in] (q,k,v rows concatenated in that order)
     const __half *wqkv, *bqkv, *wo, *bo, *ln1_w, *ln1_b, *w1, *b1, *w2, *b2, *ln2_w, *ln2_b;
     const __half *lm_head, *embd, *pos;
+    // the same decoder weights re-packed for the decode stream: units of C fp16 padded to `ustride` (see decode_kernel.cu)
+    const __half *wdec; int ustride, upstage, use_mma;
+    int split_handicap;   // K blocks the last KV split gives up (it also owns the new key and usually merges the head)
     // KV cache: K blocked [layer][head][key/32][d/8][key%32][8], V natural [layer][head][key][96]
     __half *kc, *vc;
     // cross-CTA scratch (global, read back with ld.cg)
@@ -51,3 +54,4 @@ size_t er_decode_smem_bytes(const er::DecodeParams& p);
 int er_decode_pick_stages(const er::DecodeParams& p, size_t smem_limit);
 cudaError_t er_decode_launch(const er::DecodeParams& p, int grid, size_t smem, cudaStream_t stream);
 int er_decode_max_grid(size_t smem);
+int er_decode_stage_bytes();

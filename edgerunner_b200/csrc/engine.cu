@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -49,6 +50,19 @@ __global__ void tf_losses_kernel(const float* loss_sum, const int* count, const 
     losses[1] = ce; losses[2] = kl; losses[0] = ce + (has_kl ? kl_weight * kl : 0.f);
 }
 
+// row-major W[rows][K] -> decode units: unit (row * K/C + q) holds W[row][q*C .. (q+1)*C) followed by (ustride - C) zeros
+__global__ void pack_units_kernel(const __half* src, int rows, int K, int C, __half* dst, int ustride) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte vector of the destination each
+    const int vpu = ustride >> 3;
+    const size_t total = (size_t)rows * (K / C) * vpu;
+    if (i >= total) return;
+    const size_t unit = i / vpu; const int v = i % vpu;
+    const size_t row = unit / (K / C); const int q = unit % (K / C);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (v * 8 < C) val = *reinterpret_cast<const uint4*>(src + row * K + (size_t)q * C + v * 8);
+    *reinterpret_cast<uint4*>(dst + unit * ustride + v * 8) = val;
+}
+
 struct Slot { __half* dst; int rows, cols, dst_ld; };
 
 }  // namespace
@@ -65,6 +79,7 @@ struct er_engine {
     bool finalized = false;
     // decoder weights
     __half *wqkv, *bqkv, *wo, *bo, *ln1w, *ln1b, *w1, *b1, *w2, *b2, *ln2w, *ln2b, *lm_head, *embd, *pos;
+    __half* wdec; int ustride, upstage, use_mma;   // decode-stream copy of the decoder weights (padded units)
     // encoder + conditioner weights
     __half *qe, *basis, *mlp_w, *mlp_b, *ln_w, *ln_b, *cl1w, *cl1b, *cq_w, *cq_b, *ckv_w, *ckv_b, *co_w, *co_b, *cl2w, *cl2b;
     __half *ff0w, *ff0b, *ff2w, *ff2b, *lin_w, *lin_b, *pc_w, *pc_b, *ncw, *ncb, *enf;
@@ -130,6 +145,11 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     ALLOC(e->w2, (size_t)NL * C * F); ALLOC(e->b2, (size_t)NL * C);
     ALLOC(e->ln2w, (size_t)NL * C); ALLOC(e->ln2b, (size_t)NL * C);
     ALLOC(e->lm_head, (size_t)V * C); ALLOC(e->embd, (size_t)V * C); ALLOC(e->pos, (size_t)cfg->max_positions * C);
+    e->ustride = C + 8;
+    e->use_mma = (C % 256 == 0) ? 1 : 0;
+    if (const char* v = getenv("ER_DECODE_GEMV")) { if (!strcmp(v, "cuda")) e->use_mma = 0; }   // ablation switch: CUDA-core GEMV consumers
+    e->upstage = e->use_mma ? 8 : er_decode_stage_bytes() / (e->ustride * 2) / 8 * 8;   // multiple of 8 (and so of F/C)
+    ALLOC(e->wdec, ((size_t)NL * (4 * (size_t)C + 2 * (size_t)F) + V) * e->ustride + 64);
     char nm[256];
     for (int i = 0; i < NL; i++) {
         const char* pj[3] = {"q_proj", "k_proj", "v_proj"};
@@ -199,7 +219,7 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     e->grid = sms;
     e->S = sms / H; if (e->S > 16) e->S = 16; if (e->S < 1) { delete e; return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
     ALLOC(e->part, (size_t)H * e->S * 100);
-    e->sc_len = std::max(((e->nkb + e->S - 1) / e->S) * 32 + 64, (V + 3) / 4 * 4);
+    e->sc_len = std::max(((e->nkb + 7 + e->S - 1) / e->S) * 32 + 64, (V + 3) / 4 * 4);   // 7 = kLastSplitHandicap (decode_kernel.cu)
     {
         er::DecodeParams p{}; p.C = C; p.F = F; p.H = H; p.V = V; p.S = e->S; p.sc_len = e->sc_len;
         int smem_max = 0;
@@ -260,6 +280,25 @@ extern "C" int er_finalize_weights(er_engine* e, void* stream) {
     if (!e) return set_err(ER_ERR_INVALID, "null engine");
     for (auto& kv : e->slots)
         if (!e->loaded.count(kv.first)) return set_err(ER_ERR_STATE, "weight '%s' was never loaded", kv.first.c_str());
+    // decode-stream copy: pack every decoder matrix into padded units (see decode_kernel.cu)
+    {
+        cudaStream_t st = (cudaStream_t)stream;
+        const int C = e->C, F = e->F, us = e->ustride;
+        const size_t UL = (size_t)4 * C + 2 * (size_t)F;
+        auto pack = [&](const __half* src, int rows, int K, size_t unit0) -> cudaError_t {
+            const size_t total = (size_t)rows * (K / C) * (us >> 3);
+            e->launches++;
+            pack_units_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, rows, K, C, e->wdec + unit0 * us, us);
+            return cudaGetLastError();
+        };
+        for (int l = 0; l < e->NL; l++) {
+            CK(pack(e->wqkv + (size_t)l * 3 * C * C, 3 * C, C, l * UL));
+            CK(pack(e->wo + (size_t)l * C * C, C, C, l * UL + 3 * (size_t)C));
+            CK(pack(e->w1 + (size_t)l * F * C, F, C, l * UL + 4 * (size_t)C));
+            CK(pack(e->w2 + (size_t)l * C * F, C, F, l * UL + 4 * (size_t)C + F));
+        }
+        CK(pack(e->lm_head, e->V, C, (size_t)e->NL * UL));
+    }
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     e->finalized = true;
     return ER_OK;
@@ -391,10 +430,13 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.nstage = e->nstage; p.sc_len = e->sc_len;
     // red_units holds 2 partial sums per unit of C elements: the widest phases are qkv (rows) and fc2 (rows * F/C)
     const int max_units = std::max(std::max((3 * C + G - 1) / G + 1, (F + G - 1) / G + 1), ((C + G - 1) / G + 1) * (F / C));
-    if (max_units > 64 || (C / 2) % 8 || F % C || C % 16 || C > 1536 || (8 % (F / C)) || ((24576 / (2 * C)) % (F / C)) || e->H > 64) return set_err(ER_ERR_CAPACITY, "model shape not supported by the decode kernel on %d SMs (units %d)", G, max_units);
+    if (max_units > 64 || F % C || C % 16 || C > 1536 || (8 % (F / C)) || (e->upstage % (F / C)) || e->H > 64) return set_err(ER_ERR_CAPACITY, "model shape not supported by the decode kernel on %d SMs (units %d)", G, max_units);
     p.wqkv = e->wqkv; p.bqkv = e->bqkv; p.wo = e->wo; p.bo = e->bo; p.ln1_w = e->ln1w; p.ln1_b = e->ln1b;
     p.w1 = e->w1; p.b1 = e->b1; p.w2 = e->w2; p.b2 = e->b2; p.ln2_w = e->ln2w; p.ln2_b = e->ln2b;
     p.lm_head = e->lm_head; p.embd = e->embd; p.pos = e->pos;
+    p.wdec = e->wdec; p.ustride = e->ustride; p.upstage = e->upstage; p.use_mma = e->use_mma;
+    p.split_handicap = 4;
+    if (const char* v = getenv("ER_SPLIT_HANDICAP")) p.split_handicap = std::max(0, std::min(7, atoi(v)));
     p.kc = e->kc; p.vc = e->vc; p.attn16 = e->attn16; p.head_cnt = e->bar + 64; p.q16 = e->q16; p.y1 = e->y1; p.h1 = e->h1; p.y2 = e->y2; p.part = e->part; p.logits = e->logits;
     p.st = e->st; p.bar = e->bar;
     p.out_ids = out_ids_dev; p.out_logits = out_logits_dev; p.forced = forced_ids_dev;

@@ -239,6 +239,38 @@ def test_attention_seam_matches_torch():
         assert (out.float() - ref).abs().max().item() < 4e-3
 
 
+# ---- mid-size configuration: hidden 768 (C % 256 == 0) takes the tensor-core GEMV path of the decode kernel -------------------
+
+@pytest.fixture(scope='module')
+def mid_setup():
+    from edgerunner_b200.engine import Engine
+    from oracle.er_oracle import Oracle
+    opt = synth.tiny_options(hidden_dim=768, num_heads=8, num_layers=3)
+    sd = synth.synth_state_dict(opt, seed=3, eos_logit=-30.0)
+    eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=300, max_points=opt.point_num)
+    eng.load_state_dict(sd)
+    return opt, sd, eng, Oracle(opt, sd, mode='ledger'), synth.synth_point_cloud(1, opt.point_num)
+
+
+def test_mid_tensor_core_gemv_path(mid_setup):
+    opt, sd, eng, orc, cond = mid_setup
+    T = 120
+    eng.encode_cond(cond[0].cuda(), 3000)
+    eng.prefill([1])
+    out = eng.decode(T, mode='greedy', want_logits=True)
+    assert len(out['tokens']) == T
+    ref = orc.generate(cond, 3000, max_new_tokens=T, generate_mode='greedy', forced_tokens=list(out['tokens']))
+    d = (out['logits_pre'].cpu() - ref['logits_pre']).abs()
+    assert d.max().item() <= 4e-3 and d.mean().item() <= 6e-4, (d.max().item(), d.mean().item())
+    _check_ids(out['tokens'], ref, 4e-3)
+    # chunked launches stay bit-identical on this path too
+    eng.encode_cond(cond[0].cuda(), 3000)
+    eng.prefill([1])
+    out2 = eng.decode(T, mode='greedy', tokens_per_launch=17, want_logits=True)
+    np.testing.assert_array_equal(out2['tokens'], out['tokens'])
+    assert torch.equal(out2['logits_pre'], out['logits_pre'])
+
+
 # ---- full-size ArAE preset (BASELINE configs[0]/[1] weights and cloud) ------------------------------------------------------
 
 @pytest.fixture(scope='module')
