@@ -310,6 +310,10 @@ def main():
                'd2h_bytes_per_step': int(len(toks) * 4 + 4), 'ms_per_step': dt / args.steps * 1e3,
                'api': 'core.models.LMM.generate(cond, num_faces, max_new_tokens, tokenizer, clean=True) incl. meto detokenize + mesh clean-up'}
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------------------------------
