@@ -1,0 +1,230 @@
+// Native meto tokenizer, LR_ABSCO backend, ENCODE side (mesh -> token stream) behind the C ABI.
+//
+// Stands in for the pybind module `_meto` of the reference on the training-data side:
+//   Mesh::Mesh                 meto/include/meto/mesh.h:172-278     (quantise, half-edges, twins, boundary marks, ordering heuristics)
+//   Engine_LR_ABSCO::encode    meto/include/meto/engine_lr_absco.h:66-220 (EdgeBreaker-style traversal, L / R / BOM ops + absolute coords)
+// Same token stream, face order and face types as the reference, bit for bit (tests/test_meto_cpu.py against goldens produced by the
+// compiled reference).  Differences by design: index-based flat arrays instead of a pointer graph (no per-element new/delete), the
+// traversal is ITERATIVE with an explicit stack of pending sub-meshes (the reference recurses once per face: stack depth = faces per
+// sub-mesh), a sorted edge table instead of std::map for twin lookup, re-entrant (no engine-held state).
+//
+// Ordering rules that must be reproduced exactly because they decide the token stream:
+//   * vertex quantiser  min(int((x + 1) * bins / 2), bins - 1) in float arithmetic (mesh.h:31-35);
+//   * a face's three half-edges are std::sort'ed with "boundary edge first, then by distance between the two opposite vertices"
+//     (mesh.h:116-121; the comparator is not a strict weak order for two boundary edges — we call std::sort with the same predicate
+//     on the same initial order, which is what the reference does);
+//   * faces are sorted by centre (y, z, x), connected components are labelled by BFS in that order, then faces are sorted again by
+//     (component, centre) (mesh.h:235-277).
+#include "../../include/edgerunner_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <queue>
+#include <utility>
+#include <vector>
+
+namespace {
+
+enum : int32_t { kLeft = 0, kRight = 1, kBegin = 2, kNumOps = 3 };
+
+struct QVert { int x, y, z; int mark; };
+struct HalfEdge {
+    int v, s, e;      // opposite vertex, start, end (vertex ids)
+    int face;
+    int next, prev;   // half-edge ids inside the face
+    int twin;         // opposite half-edge id or -1
+};
+struct Face {
+    int he[3];        // half-edge ids in heuristic order (he[0] starts a sub-mesh)
+    int vid[3];
+    float cx, cy, cz;
+    int index;        // position in the input triangle list
+    int comp;
+    int mark;
+};
+
+inline int quantise(float x, int bins) { return std::min(int((x + 1) * bins / 2), bins - 1); }
+
+struct Builder {
+    std::vector<QVert> V;
+    std::vector<HalfEdge> H;
+    std::vector<Face> F;
+    std::vector<int> order;     // face ids in traversal-start order (after the two sorts)
+
+    float opp_dist(int h) const {   // |v(h) - v(twin(h))| on the integer grid, float arithmetic like the reference
+        const QVert& a = V[H[h].v];
+        const QVert& b = V[H[H[h].twin].v];
+        const float dx = float(b.x - a.x), dy = float(b.y - a.y), dz = float(b.z - a.z);
+        return std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    bool he_less(int a, int b) const {
+        if (H[a].twin < 0) return true;
+        if (H[b].twin < 0) return false;
+        return opp_dist(a) < opp_dist(b);
+    }
+    bool face_less(int a, int b) const {
+        const Face &f = F[a], &g = F[b];
+        if (f.comp != g.comp) return f.comp < g.comp;
+        return f.cy < g.cy || (f.cy == g.cy && f.cz < g.cz) || (f.cy == g.cy && f.cz == g.cz && f.cx < g.cx);
+    }
+
+    void build(const float* verts, int64_t nv, const int32_t* tris, int64_t nf, int bins) {
+        V.resize(nv);
+        for (int64_t i = 0; i < nv; ++i)
+            V[i] = QVert{quantise(verts[3 * i], bins), quantise(verts[3 * i + 1], bins), quantise(verts[3 * i + 2], bins), 0};
+        H.resize(3 * nf);
+        F.resize(nf);
+        // edge table: (min, max, half-edge id) sorted by key, ties in creation order == the order std::map would have met them
+        struct EdgeRef { int a, b, h; };
+        std::vector<EdgeRef> edges(3 * nf);
+        for (int64_t f = 0; f < nf; ++f) {
+            Face& fc = F[f];
+            fc.index = (int)f; fc.comp = -1; fc.mark = 0;
+            for (int j = 0; j < 3; ++j) {
+                const int h = int(3 * f + j);
+                HalfEdge& e = H[h];
+                e.v = tris[3 * f + j]; e.s = tris[3 * f + (j + 1) % 3]; e.e = tris[3 * f + (j + 2) % 3];
+                e.face = (int)f; e.next = int(3 * f + (j + 1) % 3); e.prev = int(3 * f + (j + 2) % 3); e.twin = -1;
+                fc.he[j] = h; fc.vid[j] = e.v;
+                edges[h] = EdgeRef{std::min(e.s, e.e), std::max(e.s, e.e), h};
+            }
+            const QVert &a = V[fc.vid[0]], &b = V[fc.vid[1]], &c = V[fc.vid[2]];
+            fc.cx = float(float(a.x + b.x + c.x) / 3.0); fc.cy = float(float(a.y + b.y + c.y) / 3.0); fc.cz = float(float(a.z + b.z + c.z) / 3.0);
+        }
+        std::stable_sort(edges.begin(), edges.end(), [](const EdgeRef& x, const EdgeRef& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+        for (size_t i = 0; i < edges.size();) {
+            size_t j = i;
+            while (j < edges.size() && edges[j].a == edges[i].a && edges[j].b == edges[i].b) ++j;
+            // first two half-edges of an edge become twins; a third (non-manifold) one stays a border edge, like the reference
+            if (j - i >= 2) { H[edges[i].h].twin = edges[i + 1].h; H[edges[i + 1].h].twin = edges[i].h; }
+            i = j;
+        }
+        // boundary vertices start out "visited"; then order each face's half-edges
+        for (int64_t f = 0; f < nf; ++f) {
+            for (int j = 0; j < 3; ++j) {
+                const HalfEdge& e = H[F[f].he[j]];
+                if (e.twin < 0) { V[e.s].mark = 1; V[e.e].mark = 1; }
+            }
+            std::sort(F[f].he, F[f].he + 3, [this](int a, int b) { return he_less(a, b); });
+        }
+        order.resize(nf);
+        for (int64_t f = 0; f < nf; ++f) order[f] = (int)f;
+        std::sort(order.begin(), order.end(), [this](int a, int b) { return face_less(a, b); });
+        int ncomp = 0;
+        for (int64_t i = 0; i < nf; ++i) {
+            if (F[order[i]].comp != -1) continue;
+            ++ncomp;
+            std::queue<int> q;
+            q.push(order[i]);
+            while (!q.empty()) {
+                const int f = q.front(); q.pop();
+                if (F[f].comp != -1) continue;
+                F[f].comp = ncomp;
+                for (int j = 0; j < 3; ++j) {
+                    const int tw = H[F[f].he[j]].twin;
+                    if (tw >= 0 && F[H[tw].face].comp == -1) q.push(H[tw].face);
+                }
+            }
+        }
+        std::sort(order.begin(), order.end(), [this](int a, int b) { return face_less(a, b); });
+    }
+
+    void flip(int f) {   // reverse the orientation of a face: swap start/end and next/prev of its three half-edges
+        for (int j = 0; j < 3; ++j) {
+            HalfEdge& e = H[F[f].he[j]];
+            std::swap(e.s, e.e);
+            std::swap(e.next, e.prev);
+        }
+    }
+};
+
+struct Emitter {
+    int32_t *tok, *ord, *typ;
+    int64_t nt = 0, no = 0, ny = 0;
+    void coord(const QVert& v) { tok[nt++] = v.x + kNumOps; tok[nt++] = v.y + kNumOps; tok[nt++] = v.z + kNumOps; }
+};
+
+}  // namespace
+
+extern "C" int er_meto_encode(int32_t discrete_bins, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces,
+                              int32_t* tokens, int32_t* face_order, int32_t* face_type, int64_t* n_tokens) {
+    if (discrete_bins <= 0 || n_verts < 0 || n_faces < 0 || (n_faces > 0 && (!verts || !faces)) || !tokens || !face_order || !face_type || !n_tokens)
+        return ER_ERR_INVALID;
+    for (int64_t i = 0; i < 3 * n_faces; ++i)
+        if (faces[i] < 0 || faces[i] >= n_verts) return ER_ERR_INVALID;   // the reference would read out of bounds
+    Builder m;
+    m.build(verts, n_verts, faces, n_faces, discrete_bins);
+    Emitter out{tokens, face_order, face_type};
+    std::vector<int> pending;   // sub-meshes still to be opened (LIFO == the reference's recursion order)
+    auto visited_face = [&](int h) { return m.F[m.H[h].face].mark != 0; };
+    for (int64_t i = 0; i < n_faces; ++i) {
+        if (m.F[m.order[i]].mark) continue;
+        pending.push_back(m.F[m.order[i]].he[0]);
+        while (!pending.empty()) {
+            int c = pending.back();
+            pending.pop_back();
+            if (visited_face(c)) continue;                    // hole / handle: the face was reached another way
+            // ---- open a sub-mesh at gate c: BOM + three absolute vertices ----
+            out.tok[out.nt++] = kBegin;
+            out.coord(m.V[m.H[c].v]); out.coord(m.V[m.H[c].s]); out.coord(m.V[m.H[c].e]);
+            m.V[m.H[c].s].mark = 1; m.V[m.H[c].e].mark = 1;
+            bool first = true;
+            for (;;) {                                        // one iteration per face (the reference recurses here)
+                HalfEdge& hc = m.H[c];
+                m.F[hc.face].mark = 1;
+                out.ord[out.no++] = m.F[hc.face].index;
+                if (!first) {
+                    const HalfEdge& tw = m.H[hc.twin];       // the gate we came through
+                    if (!(hc.s == tw.e && hc.e == tw.s)) m.flip(hc.face);   // inconsistent orientation: repair it
+                    out.coord(m.V[m.H[c].v]);
+                }
+                first = false;
+                const HalfEdge& h = m.H[c];                   // (re-read: flip may have changed next / prev)
+                const bool tip_seen = m.V[h.v].mark != 0;
+                const int left_gate = m.H[h.prev].twin, right_gate = m.H[h.next].twin;
+                const bool left_seen = left_gate < 0 || visited_face(left_gate);
+                const bool right_seen = right_gate < 0 || visited_face(right_gate);
+                if (!tip_seen) {                              // "C": new vertex, continue to the right
+                    m.V[h.v].mark = 1;
+                    out.tok[out.nt++] = kLeft; out.typ[out.ny++] = kLeft;
+                    c = right_gate;
+                } else if (left_seen && right_seen) {         // "E": this strip ends
+                    out.typ[out.ny++] = kBegin;
+                    break;
+                } else if (left_seen) {
+                    out.tok[out.nt++] = kLeft; out.typ[out.ny++] = kLeft;
+                    c = right_gate;
+                } else if (right_seen) {
+                    out.tok[out.nt++] = kRight; out.typ[out.ny++] = kRight;
+                    c = left_gate;
+                } else {                                      // "S": split — walk the shorter boundary loop first
+                    int len_left = 0, len_right = 0;
+                    for (int cur = right_gate;;) {
+                        ++len_left;
+                        cur = m.H[cur].next;
+                        while (m.H[cur].twin >= 0 && !visited_face(m.H[cur].twin)) cur = m.H[m.H[cur].twin].next;
+                        if (cur == right_gate) break;
+                    }
+                    for (int cur = left_gate;;) {
+                        ++len_right;
+                        cur = m.H[cur].prev;
+                        while (m.H[cur].twin >= 0 && !visited_face(m.H[cur].twin)) cur = m.H[m.H[cur].twin].prev;
+                        if (cur == left_gate) break;
+                    }
+                    if (len_left < len_right) {
+                        out.tok[out.nt++] = kLeft; out.typ[out.ny++] = kLeft;
+                        pending.push_back(left_gate);
+                        c = right_gate;
+                    } else {
+                        out.tok[out.nt++] = kRight; out.typ[out.ny++] = kRight;
+                        pending.push_back(right_gate);
+                        c = left_gate;
+                    }
+                }
+            }
+        }
+    }
+    *n_tokens = out.nt;
+    return ER_OK;
+}

@@ -122,6 +122,15 @@ int er_debug_read_timeline(er_engine* e, uint64_t* out_host, int32_t n);
 int er_meto_decode(int32_t discrete_bins, const int32_t* tokens, int64_t n, float* verts, int32_t* faces, int32_t* face_type,
                    int64_t* n_verts, int64_t* n_faces, int64_t* n_types);
 
+/* meto tokenizer, LR_ABSCO backend, ENCODE side (CPU, native): replaces `_meto.Engine_LR_ABSCO.encode`
+ * (meto/src/bindings.cpp:25-28 -> Mesh::Mesh, meto/include/meto/mesh.h:172-278, and Engine_LR_ABSCO::encode,
+ * meto/include/meto/engine_lr_absco.h:66-220), the tokenizer call of the training-data path (core/provider.py:69-106).
+ * verts [n_verts][3] float32 in [-1, 1], faces [n_faces][3] vertex indices.  Outputs (caller-allocated): tokens, capacity
+ * >= 10*n_faces, in the _meto alphabet (0 L, 1 R, 2 BOM, coords +3); face_order [n_faces] = input index of each face in
+ * emission order; face_type [n_faces] (0 L, 1 R, 2 end-of-strip).  Returns ER_ERR_INVALID for out-of-range vertex indices. */
+int er_meto_encode(int32_t discrete_bins, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces,
+                   int32_t* tokens, int32_t* face_order, int32_t* face_type, int64_t* n_tokens);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,9 +1,10 @@
 """``meto`` — mesh tokenizer package, drop-in for ``/root/reference/meto/meto/__init__.py``.
 
 ``Engine(discrete_bins, verbose=False, backend='LR_ABSCO')`` keeps the reference's surface (:21-50):
+``encode(vertices [V,3], faces [F,3]) -> (tokens, face_order, face_type)``,
 ``decode(tokens[N] int) -> (vertices float64 [V,3], faces int [F,3], face_type)`` and the ``num_tokens`` /
-``num_base_tokens`` / ``num_special_tokens`` attributes.  The implementation is the native C-ABI function
-``er_meto_decode`` of libedgerunner_b200 (no pybind, no per-element Python objects).
+``num_base_tokens`` / ``num_special_tokens`` attributes.  The implementation is the pair of native C-ABI functions
+``er_meto_encode`` / ``er_meto_decode`` of libedgerunner_b200 (no pybind, no per-element Python objects).
 """
 
 import ctypes as C
@@ -41,7 +42,21 @@ class Engine:
         return verts[:nv.value].astype(np.float64), faces[:nf.value].astype(np.int64), ftype[:nt.value].astype(np.int64)
 
     def encode(self, vertices, faces):
-        raise NotImplementedError('meto encode (training-data side) is the next row of the scope table (SURVEY.md §8f.1)')
+        """Mesh -> (tokens, face_order, face_type) as int arrays, reference meto/meto/__init__.py:40-45.
+        vertices are expected in [-1, 1] (normalize_mesh), faces are triangles of vertex indices."""
+        v = np.ascontiguousarray(np.asarray(vertices, dtype=np.float32).reshape(-1, 3))   # pybind narrows to float the same way
+        f = np.ascontiguousarray(np.asarray(faces).reshape(-1, 3), dtype=np.int32)
+        nv, nf = v.shape[0], f.shape[0]
+        if nf and (f.min() < 0 or f.max() >= nv):
+            raise ValueError('meto.encode: face index out of range')
+        tok = np.empty(max(10 * nf, 1), dtype=np.int32)
+        order = np.empty(max(nf, 1), dtype=np.int32)
+        ftype = np.empty(max(nf, 1), dtype=np.int32)
+        nt = C.c_int64()
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        _lib.check(self._lib.er_meto_encode(self.discrete_bins, p(v, C.c_float), nv, p(f, C.c_int32), nf, p(tok, C.c_int32),
+                                            p(order, C.c_int32), p(ftype, C.c_int32), C.byref(nt)))
+        return tok[:nt.value].astype(np.int64), order[:nf].astype(np.int64), ftype[:nf].astype(np.int64)
 
 
 def normalize_mesh(vertices, bound=0.95):

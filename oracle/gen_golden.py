@@ -245,6 +245,20 @@ def gen_meto_goldens():
             out[key + '_dv'] = np.asarray(dv, dtype=np.float64).reshape(-1, 3)
             out[key + '_df'] = np.asarray(df, dtype=np.int32).reshape(-1, 3)
             out[key + '_dt'] = np.asarray(dt, dtype=np.int32)
+    # encode-only stress cases (coarse bins force ties between face centres and coincident quantised vertices)
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    import meshes
+    enc_names = []
+    for name, (v, f) in meshes.stress_meshes().items():
+        for bins in (8, 64, 512):
+            eng = _meto.Engine_LR_ABSCO(bins, False)
+            tok, order, ftype = eng.encode(v.astype(np.float32).tolist(), f.astype(np.int32).tolist())
+            key = f'{name}_{bins}'
+            enc_names.append(key)
+            out[key + '_tokens'] = np.asarray(tok, dtype=np.int16)
+            out[key + '_order'] = np.asarray(order, dtype=np.int16)
+            out[key + '_ftype'] = np.asarray(ftype, dtype=np.int8)
+    out['enc_names'] = np.asarray(enc_names)
     # random / malformed streams for the decoder (truncations, coord where an op is expected, empty)
     rng = np.random.RandomState(11)
     streams = [np.zeros(0, np.int64), grammar_tokens(rng, 4001, 512) - 3, grammar_tokens(rng, 57, 512) - 3,

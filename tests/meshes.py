@@ -150,3 +150,34 @@ def all_meshes():
         'annulus': annulus(), 'two_components': two_components(), 'non_manifold': non_manifold(),
         'random_soup': random_soup(),
     }
+
+
+def stress_meshes(count=24):
+    """Harder tokenizer inputs: holes, flipped faces, shuffled face order, duplicate faces, coincident vertices,
+    degenerate triangles, pure random (heavily non-manifold) soups.  Deterministic per index."""
+    out = {}
+    for seed in range(count):
+        r = np.random.RandomState(100 + seed)
+        kind = seed % 6
+        if kind == 0:
+            v, f = random_soup(seed, n=60)
+        elif kind == 1:
+            v, f = icosphere(3)
+            f = f[r.rand(len(f)) > 0.1]
+            fl = r.rand(len(f)) < 0.3
+            f[fl] = f[fl][:, ::-1]
+        elif kind == 2:
+            v, f = torus(20, 12)
+            f = f[r.permutation(len(f))]
+        elif kind == 3:
+            v = r.uniform(-0.95, 0.95, (30, 3)).astype(np.float32)
+            f = r.randint(0, 30, (80, 3)).astype(np.int32)
+        elif kind == 4:
+            v, f = grid(6, 6, wavy=False)
+            f = np.concatenate([f, f[:10], f[5:9][:, ::-1]])
+            v = np.concatenate([v, v[:5]])
+        else:
+            v, f = grid(30, 30)
+            f = f[r.rand(len(f)) > 0.05]
+        out[f'stress{seed}'] = (np.ascontiguousarray(v, dtype=np.float32), np.ascontiguousarray(f, dtype=np.int32))
+    return out

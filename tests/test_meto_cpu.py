@@ -81,3 +81,106 @@ def test_save_mesh_tail(golden_dir):
     mesh = save_mesh(g['greedy_tokens'], opt, tokenizer=Engine(opt.discrete_bins), clean=False)
     np.testing.assert_array_equal(np.asarray(mesh.vertices), g['mesh_vertices'])
     np.testing.assert_array_equal(np.asarray(mesh.faces), g['mesh_faces'])
+
+
+# ------------------------------------------------------------------ encode (training-data side) ------------------------------------------------------------------
+
+def test_encode_matches_reference_goldens(golden_dir):
+    """er_meto_encode vs token streams / face order / face types recorded from the compiled reference (bit-exact)."""
+    import meshes
+    from meto import Engine
+    g = np.load(os.path.join(golden_dir, 'meto.npz'))
+    fixtures = dict(meshes.all_meshes())
+    fixtures.update(meshes.stress_meshes())
+    n = 0
+    for key in list(g['names']) + list(g['enc_names']):
+        key = str(key)
+        name, bins = key.rsplit('_', 1)
+        v, f = fixtures[name]
+        tok, order, ftype = Engine(int(bins)).encode(v, f)
+        assert tok.dtype == np.int64
+        np.testing.assert_array_equal(tok, g[key + '_tokens'], err_msg=key)
+        np.testing.assert_array_equal(order, g[key + '_order'], err_msg=key)
+        np.testing.assert_array_equal(ftype, g[key + '_ftype'], err_msg=key)
+        n += 1
+    assert n >= 100
+
+
+def test_encode_live_against_compiled_reference():
+    """Fresh random meshes against oracle/_ref/_meto when it is present (built by oracle/Makefile from the reference sources)."""
+    import sys
+    ref_dir = os.path.join(REPO, 'oracle', '_ref')
+    sys.path.insert(0, ref_dir)
+    try:
+        import _meto
+    except ImportError:
+        pytest.skip('compiled reference tokenizer not built (oracle/_ref)')
+    finally:
+        sys.path.remove(ref_dir)
+    import meshes
+    from meto import Engine
+    rng = np.random.RandomState(2024)
+    for it in range(40):
+        nx, ny = rng.randint(2, 14, size=2)
+        v, f = meshes.grid(int(nx), int(ny))
+        v = v + rng.uniform(-0.03, 0.03, v.shape).astype(np.float32)
+        f = f[rng.rand(len(f)) > rng.uniform(0, 0.3)]
+        fl = rng.rand(len(f)) < rng.uniform(0, 0.5)
+        f[fl] = f[fl][:, ::-1]
+        f = f[rng.permutation(len(f))]
+        if it % 5 == 0:                                     # some outright garbage connectivity
+            f = np.concatenate([f, rng.randint(0, len(v), (7, 3)).astype(np.int32)])
+        v = np.clip(v, -1, 1)
+        bins = int(rng.choice([4, 32, 256, 512, 1024]))
+        rt, ro, rf = _meto.Engine_LR_ABSCO(bins, False).encode(v.tolist(), f.tolist())
+        tok, order, ftype = Engine(bins).encode(v, f)
+        np.testing.assert_array_equal(tok, rt, err_msg=f'iter {it}')
+        np.testing.assert_array_equal(order, ro, err_msg=f'iter {it}')
+        np.testing.assert_array_equal(ftype, rf, err_msg=f'iter {it}')
+
+
+def test_encode_decode_round_trip():
+    """Size-independent properties: every face is emitted once; decode(encode(mesh)) reproduces each input face's quantised
+    corner set, in emission order (the reference's own round-trip check, meto/tests/engine.py:120-150)."""
+    import meshes
+    from meto import Engine
+    bins = 512
+    for name, (v, f) in {**meshes.all_meshes(), 'icosphere4': meshes.icosphere(4)}.items():
+        eng = Engine(bins)
+        tok, order, ftype = eng.encode(v, f)
+        assert sorted(order.tolist()) == list(range(len(f))), name
+        assert len(ftype) == len(f)
+        assert (tok == 2).sum() == (ftype == 2).sum(), name          # one BOM per strip end
+        assert len(tok) == 4 * len(f) + 6 * (tok == 2).sum(), name   # 10 tokens for a strip's first face, 4 for the others
+        dv, df, dt = eng.decode(tok)
+        assert len(df) == len(f), name
+        np.testing.assert_array_equal(dt, ftype, err_msg=name)
+        q = np.minimum(((v.astype(np.float32) + 1) * bins / 2).astype(np.int32), bins - 1)
+        dq = np.floor((dv + 1) / 2 * bins).astype(np.int32)
+        for k in range(len(f)):
+            want = sorted(map(tuple, q[f[order[k]]]))
+            got = sorted(map(tuple, dq[df[k]]))
+            assert want == got, (name, k)
+
+
+def test_encode_long_strip_is_iterative():
+    """200k-face strip: the reference recurses once per face; the native traversal must not depend on stack depth."""
+    import meshes
+    from meto import Engine
+    n = 200_000
+    i = np.arange(n + 2)
+    v = np.stack([np.linspace(-0.95, 0.95, n + 2), (i % 2) * 0.1, np.zeros(n + 2)], 1).astype(np.float32)
+    k = np.arange(n)
+    f = np.where((k % 2 == 0)[:, None], np.stack([k, k + 1, k + 2], 1), np.stack([k + 1, k, k + 2], 1)).astype(np.int32)
+    tok, order, ftype = Engine(2048).encode(v, f)
+    assert len(order) == n and sorted(order.tolist()) == list(range(n))
+    assert len(tok) == 4 * n + 6 * (tok == 2).sum()
+
+
+def test_encode_rejects_bad_indices():
+    from meto import Engine
+    v = np.zeros((3, 3), np.float32)
+    with pytest.raises(ValueError):
+        Engine(512).encode(v, np.array([[0, 1, 3]]))
+    tok, order, ftype = Engine(512).encode(v, np.zeros((0, 3), np.int32))
+    assert len(tok) == 0 and len(order) == 0 and len(ftype) == 0
