@@ -53,7 +53,7 @@ def load():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f'edgerunner_b200: {LIB_PATH} is missing - run `python -m edgerunner_b200.build` '
                                '(there is no CPU / PyTorch fallback for this path)')
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(os.environ.get('ER_LIB', LIB_PATH))   # ER_LIB: A/B a differently built copy of the same library (scripts/)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args

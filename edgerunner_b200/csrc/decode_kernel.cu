@@ -142,6 +142,134 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
     cbar();
 }
 
+// ---- flagged exchange between CTAs ("LL" words) -----------------------------------------------------------------------------------
+// A grid barrier costs ~2.5 us here (drain the CTA's stores for the release, one atomic, one polled acquire) and the data it
+// guards is then fetched with one more L2 round trip.  Every vector that crosses CTAs inside a token is instead published as
+// 8-byte words {payload, flag} with single-copy-atomic 64-bit stores; a reader polls the words it needs until each carries the
+// flag of the current (token, layer).  Arrival of the data IS the synchronisation: one store + one load on the critical path,
+// no fences.  Reuse is safe without further handshakes: a vector written in phase k is read by every CTA before that CTA writes
+// its phase k+1 output, and nobody can complete the poll of phase k+1 (hence reach phase k+2, let alone phase k of the next
+// layer) before all of those outputs exist.  Flags are unique per request (t * layers + layer + 1); the host zeroes the words
+// before each launch.  One real grid barrier per token remains (after lm_head): it also orders the K/V rows appended with
+// plain stores before the next token's bulk copies.
+constexpr int kSpinLimit = 1 << 22;   // ~ seconds; a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void ll_store(unsigned long long* ptr, uint32_t data, uint32_t flag) {
+    const unsigned long long v = ((unsigned long long)flag << 32) | data;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint2 ll_load(const unsigned long long* ptr) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
+    return make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+}
+__device__ __forceinline__ uint4 ll_load2(const unsigned long long* ptr) {   // two consecutive words (16-byte aligned)
+    unsigned long long a, b;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(ptr) : "memory");
+    return make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+}
+// Arrival hint.  148 CTAs x 256 threads polling every word of a 24 KB vector delay the very stores they wait for (measured: 3.3 us
+// from the last publish to the last fetch).  So each publishing warp also adds its word count to a per-(vector, layer) counter
+// with a relaxed reduction; readers spin on that ONE word with one lane per warp and only then fetch the vector.  The counter
+// carries no ordering (no fence): the flags in the data words remain the only thing correctness rests on, a fetch that comes
+// too early simply retries the words still missing.  Counters are zeroed by the host before each launch; after the launch's
+// (iter+1)-th token the layer's counter reads (iter+1) * words.
+__device__ __forceinline__ void hint_add(unsigned* counter, unsigned n) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(n) : "memory");
+}
+__device__ __forceinline__ void hint_wait(const unsigned* counter, unsigned target) {   // all lanes of the warp call it
+    if ((threadIdx.x & 31) == 0) {
+        int spins = 0;
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if ((int)(v - target) >= 0) break;
+            if (++spins > kSpinLimit) asm volatile("trap;");
+        }
+    }
+    __syncwarp();
+}
+// Poll up to N words per thread (bit j of `mask`: word j wanted).  Must be called by ALL lanes of a warp (mask 0 = nothing wanted).
+// All loads of a round are in flight together.  After `rounds` unsuccessful rounds the warp stops hammering the L2 with 32 x N
+// loads per round: one lane that still misses a word spins on that word alone and the others wait for it at a warp barrier.
+template <int N, typename AddrFn>
+__device__ __forceinline__ void ll_poll(uint32_t (&out)[N], uint32_t mask, uint32_t flag, int rounds, AddrFn addr) {
+    int spins = 0;
+    for (;;) {
+        uint2 v[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) if ((mask >> j) & 1u) v[j] = ll_load(addr(j));
+#pragma unroll
+        for (int j = 0; j < N; j++) if (((mask >> j) & 1u) && v[j].y == flag) { out[j] = v[j].x; mask &= ~(1u << j); }
+        const uint32_t missing = __ballot_sync(0xffffffffu, mask != 0u);
+        if (!missing) break;
+        if (++spins > kSpinLimit) asm volatile("trap;");
+        if (spins >= rounds) {
+            if ((int)(threadIdx.x & 31) == __ffs(missing) - 1) {
+                const unsigned long long* w = addr(__ffs(mask) - 1);
+                int sp2 = 0;
+                while (ll_load(w).y != flag) { if (++sp2 > kSpinLimit) asm volatile("trap;"); }
+            }
+            __syncwarp();
+        }
+    }
+}
+// same with 16-byte loads: N double-words, out[2j], out[2j+1]
+template <int N, typename AddrFn>
+__device__ __forceinline__ void ll_poll2(uint32_t (&out)[2 * N], uint32_t mask, uint32_t flag, int rounds, AddrFn addr) {
+    int spins = 0;
+    for (;;) {
+        uint4 v[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) if ((mask >> j) & 1u) v[j] = ll_load2(addr(j));
+#pragma unroll
+        for (int j = 0; j < N; j++)
+            if (((mask >> j) & 1u) && v[j].y == flag && v[j].w == flag) { out[2 * j] = v[j].x; out[2 * j + 1] = v[j].z; mask &= ~(1u << j); }
+        const uint32_t missing = __ballot_sync(0xffffffffu, mask != 0u);
+        if (!missing) break;
+        if (++spins > kSpinLimit) asm volatile("trap;");
+        if (spins >= rounds) {
+            if ((int)(threadIdx.x & 31) == __ffs(missing) - 1) {
+                const unsigned long long* w = addr(__ffs(mask) - 1);
+                int sp2 = 0;
+                for (;;) {
+                    const uint4 t4 = ll_load2(w);
+                    if (t4.y == flag && t4.w == flag) break;
+                    if (++sp2 > kSpinLimit) asm volatile("trap;");
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+// fetch a whole published fp16 vector (ndw double-words = 4 fp16 each, <= 6 per thread) into shared memory
+__device__ __noinline__ void ll_fetch(const unsigned long long* src, uint32_t dst_s, int ndw, uint32_t flag, int rounds, const unsigned* hint, unsigned target) {
+    const int tid = threadIdx.x;
+    if (hint) hint_wait(hint, target);
+    uint32_t w[12];
+    uint32_t mask = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) mask |= (tid + kConsumers * j < ndw) ? (1u << j) : 0u;
+    const uint32_t want = mask;
+    ll_poll2<6>(w, mask, flag, rounds, [&](int j) { return src + 2 * (tid + kConsumers * j); });
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+        if ((want >> j) & 1u)
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(dst_s + (uint32_t)(tid + kConsumers * j) * 8), "r"(w[2 * j]), "r"(w[2 * j + 1]) : "memory");
+}
+// a consumer thread holding the fp16 output of row (r0 + tid / nu_row) on threads with tid % nu_row == 0 publishes row pairs;
+// every lane of a publishing warp must call it
+__device__ __forceinline__ void ll_publish_rows(unsigned long long* dst, int r0, int nu, int nu_row, __half hv, uint32_t flag, unsigned* hint) {
+    const uint32_t mine = __half_as_ushort(hv);
+    const uint32_t other = __shfl_down_sync(0xffffffffu, mine, nu_row);
+    const int tid = threadIdx.x;
+    const bool wr = tid < nu && (tid % (2 * nu_row)) == 0;
+    if (wr) ll_store(dst + ((r0 + tid / nu_row) >> 1), mine | (other << 16), flag);
+    if (hint) {
+        const unsigned n = __popc(__ballot_sync(0xffffffffu, wr));
+        if ((tid & 31) == 0 && n) hint_add(hint, n);
+    }
+}
+
 // ---- optional phase timeline (profiles/): one CTA, thread 0 stamps %globaltimer ------------------------------------------------
 // slot map: [0] token start; per layer l, base = 1 + 16*l: +0 residual+LN2 done, +1 qkv gemv done, +2 P1 epilogue done, +3 B1,
 // +4 attention done, +5 B2, +6 attn16 loaded, +7 out_proj done, +8 B3, +9 LN1 done, +10 fc1 done, +11 B4, +12 h1 loaded,
@@ -153,29 +281,47 @@ __device__ __forceinline__ void prof_stamp(const DecodeParams& p, int slot, bool
         p.prof[slot] = t;
     }
 }
+// the same 15 per-layer stamps for EVERY CTA, for one layer (5) of the profiled token: prof[4096 + 16 * cta + k]
+__device__ __forceinline__ void prof_all(const DecodeParams& p, int k, bool on) {
+    if (on && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.prof[4096 + 16 * blockIdx.x + k] = t;
+    }
+}
 
 // ---- work partition (identical on the producer and the consumer side) ------------------------------------------------------------
 struct RowRange { int r0, r1; };
-__device__ __forceinline__ RowRange cta_rows(int R) {
+__device__ __forceinline__ RowRange cta_rows(int R) {     // R * gridDim.x < 2^31 (checked by the host): 32-bit arithmetic, no division call
     RowRange rr;
-    rr.r0 = (int)(((long long)R * blockIdx.x) / gridDim.x);
-    rr.r1 = (int)(((long long)R * (blockIdx.x + 1)) / gridDim.x);
+    const unsigned b = blockIdx.x, g = gridDim.x;
+#ifdef ER_ODD_ROWS
+    if (true) {
+#else
+    if (R & 1) {
+#endif
+        rr.r0 = (int)(((unsigned)R * b) / g);
+        rr.r1 = (int)(((unsigned)R * (b + 1)) / g);
+    } else {   // whole fp16 PAIRS of rows per CTA: one 8-byte exchange word never has two writers
+        rr.r0 = 2 * (int)(((unsigned)(R >> 1) * b) / g);
+        rr.r1 = 2 * (int)(((unsigned)(R >> 1) * (b + 1)) / g);
+    }
     return rr;
 }
 struct AttnRange { int h, b0, b1, k0, k1, is_new; };   // old keys [k0,k1) in K blocks [b0,b1); is_new: this CTA also owns key L
-__device__ __forceinline__ bool attn_range(const DecodeParams& p, int L, AttnRange& a) {
-    if ((int)blockIdx.x >= p.H * p.S) return false;
-    a.h = blockIdx.x / p.S;
-    const int s = blockIdx.x % p.S;
+__device__ __forceinline__ bool attn_range(int H, int S, int split_handicap, int L, AttnRange& a) {
+    if ((int)blockIdx.x >= H * S) return false;
+    a.h = blockIdx.x / S;
+    const int s = blockIdx.x % S;
     const int nblk = (L + 31) >> 5;                  // blocks holding old keys 0..L-1
     // the last split also owns the new key and (being the last to finish) usually merges the head: that fixed work is worth
-    // about p.split_handicap (<= kLastSplitHandicap) blocks of streaming, so it gets that many fewer blocks
-    const int bps = (nblk + p.split_handicap + p.S - 1) / p.S;
+    // about split_handicap (<= kLastSplitHandicap) blocks of streaming, so it gets that many fewer blocks
+    const int bps = (nblk + split_handicap + S - 1) / S;
     a.b0 = min(s * bps, nblk);
     a.b1 = min(a.b0 + bps, nblk);
     a.k0 = a.b0 * 32;
     a.k1 = max(a.k0, min(a.b1 * 32, L));             // empty splits: b0 == b1 == nblk, k0 may exceed L
-    a.is_new = (s == p.S - 1);
+    a.is_new = (s == S - 1);
     return true;
 }
 
@@ -210,8 +356,14 @@ __device__ __forceinline__ bool produce(const Ring r, Cursor& cur, const void* b
     return true;
 }
 
+// The kernel parameters are copied into registers up front: the consumers' acquire loads at the grid barrier invalidate the L1, and a
+// parameter fetched through a reference (local / generic memory) right after that costs the producer an L2 round trip per field.
 __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, volatile int* stop, volatile uint32_t* cons_it) {
-    const int C = p.C, F = p.F, H = p.H;
+    const int C = p.C, F = p.F, H = p.H, S = p.S, V = p.V, layers = p.layers, ustride = p.ustride, handicap = p.split_handicap;
+    const int nkb = p.nkb, Lmax = p.Lmax;
+    const __half* const wdec = p.wdec;
+    const __half* const kc = p.kc;
+    const __half* const vc = p.vc;
     int t = p.st->t, L = p.st->L;
     if (p.st->done) return;
     // forward passes of this launch: token tt is followed by a pass iff tt + 1 < max_new (EOS is handled through `stop`)
@@ -220,30 +372,28 @@ __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, 
     bool ok = true;
     // decode weights live in `wdec` as units of C fp16 padded to `ustride` (bank-conflict-free ldmatrix rows); per layer:
     // [3C qkv rows][C out_proj rows][F fc1 rows][C fc2 rows x F/C units]; after the layers: V lm_head rows.
-    const size_t ub = (size_t)p.ustride * 2;
+    const size_t ub = (size_t)ustride * 2;
     const uint32_t wchunk = (uint32_t)(p.upstage * ub);
     const int nuf = F / C;
     const size_t UL = (size_t)4 * C + 2 * (size_t)F;
+    const RowRange rq = cta_rows(3 * C), rc = cta_rows(C), rf = cta_rows(F), rv = cta_rows(V);
     for (int pass = 0; pass < n_fwd && ok; ++pass, ++L) {
-        for (int layer = 0; layer < p.layers && ok; ++layer) {
-            const __half* wl = p.wdec + (size_t)layer * UL * p.ustride;
-            RowRange rr = cta_rows(3 * C);
-            ok = produce(r, cur, wl + (size_t)rr.r0 * p.ustride, (size_t)(rr.r1 - rr.r0) * ub, wchunk, stop);
-            AttnRange a;
-            if (ok && attn_range(p, L, a)) {
-                const __half* kbase = p.kc + (((size_t)layer * H + a.h) * p.nkb + a.b0) * (size_t)(HV * 256);
+        AttnRange a;
+        const bool has_attn = attn_range(H, S, handicap, L, a);
+        for (int layer = 0; layer < layers && ok; ++layer) {
+            const __half* wl = wdec + (size_t)layer * UL * ustride;
+            ok = produce(r, cur, wl + (size_t)rq.r0 * ustride, (size_t)(rq.r1 - rq.r0) * ub, wchunk, stop);
+            if (ok && has_attn) {
+                const __half* kbase = kc + (((size_t)layer * H + a.h) * nkb + a.b0) * (size_t)(HV * 256);
                 ok = produce(r, cur, kbase, (size_t)(a.b1 - a.b0) * kKBlockBytes, kKVChunk, stop);
-                const __half* vbase = p.vc + (((size_t)layer * H + a.h) * p.Lmax + a.k0) * HD;
+                const __half* vbase = vc + (((size_t)layer * H + a.h) * Lmax + a.k0) * HD;
                 if (ok) ok = produce(r, cur, vbase, (size_t)(a.k1 - a.k0) * HD * 2, kKVChunk, stop);
             }
-            rr = cta_rows(C);
-            if (ok) ok = produce(r, cur, wl + ((size_t)3 * C + rr.r0) * p.ustride, (size_t)(rr.r1 - rr.r0) * ub, wchunk, stop);
-            RowRange rf = cta_rows(F);
-            if (ok) ok = produce(r, cur, wl + ((size_t)4 * C + rf.r0) * p.ustride, (size_t)(rf.r1 - rf.r0) * ub, wchunk, stop);
-            if (ok) ok = produce(r, cur, wl + ((size_t)4 * C + F + (size_t)rr.r0 * nuf) * p.ustride, (size_t)(rr.r1 - rr.r0) * nuf * ub, wchunk, stop);
+            if (ok) ok = produce(r, cur, wl + ((size_t)3 * C + rc.r0) * ustride, (size_t)(rc.r1 - rc.r0) * ub, wchunk, stop);
+            if (ok) ok = produce(r, cur, wl + ((size_t)4 * C + rf.r0) * ustride, (size_t)(rf.r1 - rf.r0) * ub, wchunk, stop);
+            if (ok) ok = produce(r, cur, wl + ((size_t)4 * C + F + (size_t)rc.r0 * nuf) * ustride, (size_t)(rc.r1 - rc.r0) * nuf * ub, wchunk, stop);
         }
-        RowRange rv = cta_rows(p.V);
-        if (ok) ok = produce(r, cur, p.wdec + ((size_t)p.layers * UL + rv.r0) * p.ustride, (size_t)(rv.r1 - rv.r0) * ub, wchunk, stop);
+        if (ok) ok = produce(r, cur, wdec + ((size_t)layers * UL + rv.r0) * ustride, (size_t)(rv.r1 - rv.r0) * ub, wchunk, stop);
     }
     if (!ok) {
         // EOS: the consumers stopped at stage *cons_it; every copy we issued beyond it must land before the CTA may exit
@@ -437,15 +587,22 @@ __device__ __forceinline__ void unpack8(const uint4 u, float* f) {
     t = h2f2(u.z); f[4] = t.x; f[5] = t.y;
     t = h2f2(u.w); f[6] = t.x; f[7] = t.y;
 }
-__device__ __noinline__ void residual_layer_norm(uint32_t xres_s, uint32_t x16_s, const __half* y, bool round_first, const LnParams lp,
-                                                 int C, float inv_c, float* red) {
+__device__ __forceinline__ void residual_layer_norm(uint32_t xres_s, uint32_t x16_s, const __half* y, const unsigned long long* yll, uint32_t flag,
+                                                 int rounds, const unsigned* hint, unsigned target, bool round_first, const LnParams lp, int C, float inv_c, float* red) {
     const int t = threadIdx.x;
     const bool act = t < (C >> 3);
     float v[8];
     float s = 0.f, q = 0.f;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (yll && hint) hint_wait(hint, target);
+    if (yll) ll_poll2<2>(w, act ? 3u : 0u, flag, rounds, [&](int j) { return yll + 4 * t + 2 * j; });
     if (act) {
         float yv[8];
-        unpack8(ldg_cg(reinterpret_cast<const uint4*>(y) + t), yv);
+        if (yll) {
+            unpack8(make_uint4(w[0], w[1], w[2], w[3]), yv);
+        } else {
+            unpack8(ldg_cg(reinterpret_cast<const uint4*>(y) + t), yv);
+        }
         const float4 a = lds_f4(xres_s + t * 32), b = lds_f4(xres_s + t * 32 + 16);
         v[0] = a.x + yv[0]; v[1] = a.y + yv[1]; v[2] = a.z + yv[2]; v[3] = a.w + yv[3];
         v[4] = b.x + yv[4]; v[5] = b.y + yv[5]; v[6] = b.z + yv[6]; v[7] = b.w + yv[7];
@@ -588,11 +745,17 @@ __device__ __forceinline__ float dot_k8(const uint4 kv, const float4 qa, const f
     f = h2f2(kv.w); acc = fmaf(f.x, qb.z, acc); acc = fmaf(f.y, qb.w, acc);
     return acc;
 }
-__device__ __noinline__ Cursor attention_phase(const DecodeParams& p, const Ring r, Cursor cur, int layer, int L, float* qs,
-                                               float* sc, float* vred, float* red, int* s_flag) {
+#ifdef ER_ATTN_NOINLINE
+#define ER_ATTN_INLINE __noinline__
+#else
+#define ER_ATTN_INLINE __forceinline__
+#endif
+template <bool LL>
+__device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ring r, Cursor cur, int layer, int L, float* qs,
+                                               float* sc, float* vred, float* red, int* s_flag, float* mg, uint32_t flag) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     AttnRange a;
-    if (!attn_range(p, L, a)) return cur;
+    if (!attn_range(p.H, p.S, p.split_handicap, L, a)) return cur;
     const int H = p.H;
     const float cl2 = rsqrtf((float)HD) * 1.4426950408889634f;   // softmax scale in log2 units
     float* outp = p.part + ((size_t)a.h * p.S + (blockIdx.x % p.S)) * 100;
@@ -606,13 +769,31 @@ __device__ __noinline__ Cursor attention_phase(const DecodeParams& p, const Ring
     // the K pass / at publish time, so their L2 round trips hide behind the streamed passes
     uint4 knew = make_uint4(0, 0, 0, 0);
     unsigned short vnew = 0;
-    if (a.is_new) {
+    if (LL) {
+        // q / new k / new v of this head arrive as flagged words from the CTAs that own those qkv rows: threads 128..175 take the 48 q
+        // words, (last split only) lanes 0..11 of warp 0 the new key (4 words each) and threads 0..95 the new value (word tid / 2)
+        if (nk > 0) {
+            const bool qrole = tid >= 128 && tid < 128 + HD / 2;
+            const unsigned long long* kq = p.ll_q + ((p.C + a.h * HD) >> 1) + tid * 4;
+            const unsigned long long* vq = p.ll_q + ((2 * p.C + a.h * HD) >> 1) + (tid >> 1);
+            const unsigned long long* qq = p.ll_q + ((a.h * HD) >> 1) + (tid - 128);
+            uint32_t w[5];
+            const uint32_t mask = ((a.is_new && tid < HV) ? 0xFu : 0u) | (((a.is_new && tid < HD) || qrole) ? 0x10u : 0u);
+            ll_poll<5>(w, mask, flag, p.poll_rounds, [&](int j) { return j < 4 ? kq + j : (qrole ? qq : vq); });
+            if (a.is_new && tid < HV) knew = make_uint4(w[0], w[1], w[2], w[3]);
+            if (a.is_new && tid < HD) vnew = (unsigned short)((tid & 1) ? (w[4] >> 16) : (w[4] & 0xffffu));
+            if (qrole) {
+                const float2 f = h2f2(w[4]);
+                qs[2 * (tid - 128)] = f.x; qs[2 * (tid - 128) + 1] = f.y;
+            }
+        }
+    } else if (a.is_new) {
         if (warp == 0 && lane < HV)
             knew = ldg_cg(reinterpret_cast<const uint4*>(p.kc + ((((size_t)layer * H + a.h) * p.nkb + (L >> 5)) * HV + lane) * 256 + (size_t)(L & 31) * 8));
         if (tid < HD) vnew = ldg_cg_u16(p.vc + (((size_t)layer * H + a.h) * p.Lmax + L) * HD + tid);
     }
     if (nk > 0) {
-        if (tid < HD) qs[tid] = __half2float(__ushort_as_half(ldg_cg_u16(p.q16 + a.h * HD + tid)));
+        if (!LL && tid < HD) qs[tid] = __half2float(__ushort_as_half(ldg_cg_u16(p.q16 + a.h * HD + tid)));
         cbar();
 
         // ---- K pass ----
@@ -703,8 +884,9 @@ __device__ __noinline__ Cursor attention_phase(const DecodeParams& p, const Ring
         }
         cbar();
     }
-    if (warp >= 4) return cur;                                 // warps 0..3 publish; the others go on to the grid barrier
+    if (warp >= 4 && !LL) return cur;                    // warps 0..3 publish; the others go on to the grid barrier
     // ---- publish the split partial ----
+    unsigned long long* outl = p.ll_part + ((size_t)a.h * p.S + (blockIdx.x % p.S)) * 100;
     if (tid < HD) {
         float acc = 0.f;
         if (nk > 0) {
@@ -712,15 +894,58 @@ __device__ __noinline__ Cursor attention_phase(const DecodeParams& p, const Ring
             for (int g = 0; g < 2 * kConsumerWarps; g++) acc += vred[g * HD + tid];
             if (a.is_new) acc = fmaf(sc[new_slot] * red[32], __half2float(__ushort_as_half(vnew)), acc);   // new key: normalised by warp 0
         }
-        outp[tid] = acc;
+        if (LL) ll_store(outl + tid, __float_as_uint(acc), flag); else outp[tid] = acc;
     } else if (tid == HD) {
         float l = 0.f;
         if (nk > 0) {
             for (int g = 0; g < 2 * kConsumerWarps; g++) l += red[64 + g];
             if (a.is_new) l += sc[new_slot] * red[32];
         }
-        outp[HD] = (nk > 0) ? M * rsqrtf((float)HD) : -INFINITY;        // max in softmax (scaled) units
-        outp[HD + 1] = l;
+        const float mval = (nk > 0) ? M * rsqrtf((float)HD) : -INFINITY;        // max in softmax (scaled) units
+        if (LL) { ll_store(outl + HD, __float_as_uint(mval), flag); ll_store(outl + HD + 1, __float_as_uint(l), flag); }
+        else { outp[HD] = mval; outp[HD + 1] = l; }
+    }
+    if (LL) {
+        // ---- merge, spread over the S CTAs of the head: split s owns output pairs [48 s / S, 48 (s+1) / S).  Thread (d, s') polls
+        // partial s' for dimension d (16 splits x 16 dimensions per round), the sixteen values of a dimension meet in shared memory and
+        // one lane folds them in split order (same arithmetic as the single-merger path below) ----
+        const int S = p.S, s = blockIdx.x % S;
+        const int pr0 = (HD / 2 * s) / S, pr1 = (HD / 2 * (s + 1)) / S;
+        const int nd = 2 * (pr1 - pr0);
+        const int sp = tid & 15;
+        float* my = mg + (tid >> 4) * 48;
+        cbar();   // mg aliases the GEMV partials: warp 0 may still be summing P1's when this split had no keys to stream
+        for (int d0 = 0; d0 < nd; d0 += 16) {
+            const int d = d0 + (tid >> 4);
+            const bool act = d < nd && sp < S;
+            const unsigned long long* src = p.ll_part + ((size_t)a.h * S + sp) * 100;
+            uint32_t w[3];
+            ll_poll<3>(w, act ? 7u : 0u, flag, p.poll_rounds, [&](int j) { return src + (j == 0 ? 2 * pr0 + d : HD + j - 1); });
+            if (act) { my[sp * 3] = __uint_as_float(w[0]); my[sp * 3 + 1] = __uint_as_float(w[1]); my[sp * 3 + 2] = __uint_as_float(w[2]); }
+            __syncwarp();
+            float val = 0.f;
+            if (sp == 0 && d < nd) {
+                float Mx = -INFINITY;
+                for (int q = 0; q < S; q++) Mx = fmaxf(Mx, my[q * 3 + 1]);
+                float den = 0.f, num = 0.f;
+                for (int q = 0; q < S; q++) {
+                    const float ms = my[q * 3 + 1];
+                    const float w8 = (ms == -INFINITY) ? 0.f : __expf(ms - Mx);
+                    den = fmaf(w8, my[q * 3 + 2], den);
+                    num = fmaf(w8, my[q * 3], num);
+                }
+                val = num / den;
+            }
+            const uint32_t mine = __half_as_ushort(__float2half_rn(val));
+            const uint32_t other = __shfl_sync(0xffffffffu, mine, 16);
+            if (lane == 0 && d < nd) ll_store(p.ll_attn + ((a.h * HD) >> 1) + pr0 + (d >> 1), mine | (other << 16), flag);
+            __syncwarp();
+        }
+        if (p.use_hint) {   // one reduction per CTA (six per CTA on one address would serialise at the L2)
+            cbar();
+            if (tid == 0) hint_add(p.hint + 0 * p.layers + layer, (unsigned)(pr1 - pr0));
+        }
+        return cur;
     }
     // ---- last split of this head to finish merges the S partials (release/acquire ticket on a monotonic counter) ----
     pbar();
@@ -758,7 +983,9 @@ __device__ __noinline__ Cursor attention_phase(const DecodeParams& p, const Ring
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const DecodeParams p) {
+// PROF: the timeline instrumentation is a separate instantiation so that the production kernel carries neither its registers nor its branches
+template <bool PROF, bool LL>
+__global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __grid_constant__ DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C, F = p.F, H = p.H, V = p.V;
     // smem carve-up: ring first (128-byte aligned stages), then the small arrays
@@ -779,12 +1006,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
     __shared__ int s_stop;
     __shared__ uint32_t s_cons_it;
     __shared__ int s_flag;
+    __shared__ int s_rows[8];   // this CTA's row ranges of the 3C / C / F / V phases (computed once; registers are scarce)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int i = 0; i < p.nstage; i++) { mbar_init(ring.fullb(i), 1); mbar_init(ring.emptyb(i), kConsumerWarps); }
         s_stop = 0;
         s_cons_it = 0;
+        const RowRange r3 = cta_rows(3 * C), r1 = cta_rows(C), rf = cta_rows(F), rv = cta_rows(V);
+        s_rows[0] = r3.r0; s_rows[1] = r3.r1; s_rows[2] = r1.r0; s_rows[3] = r1.r1; s_rows[4] = rf.r0; s_rows[5] = rf.r1; s_rows[6] = rv.r0; s_rows[7] = rv.r1;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -802,13 +1032,12 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
         int t = p.st->t, L = p.st->L, counter = p.st->counter, last_tok = p.st->last_tok;
         const bool done0 = p.st->done != 0;
         bool state_written = done0;
-        const size_t nkb = (size_t)p.nkb;
         const int nu_fc2 = (F / C) * kUnitDiv;      // units per fc2 row
         const int nu1 = kUnitDiv;                   // units per row of the C-wide phases
         const int nparts = p.use_mma ? kConsumerWarps : 32;
         const GemvCfg gc{p.C, p.ustride, p.upstage, p.use_mma};
         for (int iter = 0; iter < p.steps && !done0; ++iter, ++t) {
-            const bool prof_on = p.prof != nullptr && t == p.prof_token && (int)blockIdx.x == p.prof_cta;
+            const bool prof_on = PROF && p.prof != nullptr && t == p.prof_token && (int)blockIdx.x == p.prof_cta;
             prof_stamp(p, 0, prof_on);
             // ================= sample token t from the current logits =============================================================
             if (p.use_fsm && t > 0) fsm_update(counter, last_tok);
@@ -843,26 +1072,30 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
 
             for (int layer = 0; layer < p.layers; ++layer) {
                 const int pb = 1 + 16 * layer;
+                const uint32_t flag = (uint32_t)(t * p.layers + layer + 1);   // exchange-word flag of this (token, layer)
+                const bool all_on = PROF && p.prof != nullptr && t == p.prof_token && layer == 5;
                 // ---------------- P1: q,k,v = x16 @ Wqkv^T + b ; KV append in place ----------------------------------------------
                 {
-                    const RowRange rr = cta_rows(3 * C);
+                    const RowRange rr{s_rows[0], s_rows[1]};
                     const int nr = rr.r1 - rr.r0;
-                    prof_stamp(p, pb + 0, prof_on);
+                    prof_stamp(p, pb + 0, prof_on); prof_all(p, 0, all_on);
                     const int nu = nr * nu1;
                     const bool own = tid < nu && (tid % nu1) == 0;
                     const float bias = own ? __half2float(p.bqkv[(size_t)layer * 3 * C + rr.r0 + tid / nu1]) : 0.f;   // in flight during the GEMV
                     cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
-                    prof_stamp(p, pb + 1, prof_on);
+                    prof_stamp(p, pb + 1, prof_on); prof_all(p, 1, all_on);
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu1, nparts);
+                        const __half hv = __float2half_rn(sum + bias);
+                        // publish first: the attention CTAs of this head wait for these words; the cache rows are for later tokens
+                        if (LL) ll_publish_rows(p.ll_q, rr.r0, nu, nu1, hv, flag, nullptr);
                         if (own) {
                             const int r = rr.r0 + tid / nu1;
-                            const __half hv = __float2half_rn(sum + bias);
                             if (r < C) {
-                                p.q16[r] = hv;
+                                if (!LL) p.q16[r] = hv;
                             } else if (r < 2 * C) {
                                 const int c = r - C, h = c / HD, d = c % HD;
-                                const size_t idx = ((((size_t)layer * H + h) * nkb + (L >> 5)) * HV + (d >> 3)) * 256 + (size_t)(L & 31) * 8 + (d & 7);
+                                const size_t idx = ((((size_t)layer * H + h) * (size_t)p.nkb + (L >> 5)) * HV + (d >> 3)) * 256 + (size_t)(L & 31) * 8 + (d & 7);
                                 p.kc[idx] = hv;
                             } else {
                                 const int c = r - 2 * C, h = c / HD, d = c % HD;
@@ -871,86 +1104,90 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const De
                         }
                     }
                 }
-                prof_stamp(p, pb + 2, prof_on);
-                grid_barrier(p.bar, epoch);
-                prof_stamp(p, pb + 3, prof_on);
+                prof_stamp(p, pb + 2, prof_on); prof_all(p, 2, all_on);
+                if (!LL) grid_barrier(p.bar, epoch);
+                prof_stamp(p, pb + 3, prof_on); prof_all(p, 3, all_on);
                 // ---------------- P2: attention -----------------------------------------------------------------------------------------
-                unsigned long long ta0 = 0;
-                if (p.prof != nullptr && t == p.prof_token && layer == 5 && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ta0));
-                cur = attention_phase(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag);
-                if (p.prof != nullptr && t == p.prof_token && layer == 5 && tid == 0) {   // per-CTA attention duration (all CTAs)
-                    unsigned long long ta1;
-                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ta1));
-                    p.prof[2048 + blockIdx.x] = ta1 - ta0;
-                    p.prof[2048 + 256 + blockIdx.x] = s_flag;
-                }
-                prof_stamp(p, pb + 4, prof_on);
-                grid_barrier(p.bar, epoch);
-                prof_stamp(p, pb + 5, prof_on);
+                cur = attention_phase<LL>(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag, part, flag);
+                prof_stamp(p, pb + 4, prof_on); prof_all(p, 4, all_on);
+                if (!LL) grid_barrier(p.bar, epoch);
+                prof_stamp(p, pb + 5, prof_on); prof_all(p, 5, all_on);
                 // ---------------- P3: out_proj on the merged attention output -----------------------------------------------------------
                 {
-                    for (int i = tid; i < C / 8; i += kConsumers)
-                        reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.attn16) + i);
+                    if (LL) {
+                        ll_fetch(p.ll_attn, xin_s, C / 4, flag, p.poll_rounds, p.use_hint ? p.hint + 0 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2));
+                    } else {
+                        for (int i = tid; i < C / 8; i += kConsumers)
+                            reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.attn16) + i);
+                    }
                     cbar();
-                    const RowRange rr = cta_rows(C);
+                    const RowRange rr{s_rows[2], s_rows[3]};
                     const int nr = rr.r1 - rr.r0;
-                    prof_stamp(p, pb + 6, prof_on);
+                    prof_stamp(p, pb + 6, prof_on); prof_all(p, 6, all_on);
                     const int nu = nr * nu1;
                     const bool own = tid < nu && (tid % nu1) == 0;
                     const float bias = own ? __half2float(p.bo[(size_t)layer * C + rr.r0 + tid / nu1]) : 0.f;
                     cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu1, nparts);
-                        if (own) p.y1[rr.r0 + tid / nu1] = __float2half_rn(sum + bias);
+                        if (LL) ll_publish_rows(p.ll_y1, rr.r0, nu, nu1, __float2half_rn(sum + bias), flag, p.use_hint ? p.hint + 1 * p.layers + layer : nullptr);
+                        else if (own) p.y1[rr.r0 + tid / nu1] = __float2half_rn(sum + bias);
                     }
                 }
                 const LnParams lp1 = ln_load(p.ln1_w + (size_t)layer * C, p.ln1_b + (size_t)layer * C, C);   // lands while we wait at the barrier
-                prof_stamp(p, pb + 7, prof_on);
-                grid_barrier(p.bar, epoch);
-                prof_stamp(p, pb + 8, prof_on);
+                prof_stamp(p, pb + 7, prof_on); prof_all(p, 7, all_on);
+                if (!LL) grid_barrier(p.bar, epoch);
+                prof_stamp(p, pb + 8, prof_on); prof_all(p, 8, all_on);
                 // ---------------- P4: x = LN1(x + y1) ; h1 = relu(fc1(x)) -----------------------------------------------------------
                 {
-                    residual_layer_norm(xres_s, xin_s, p.y1, layer == 0, lp1, C, inv_c, red);
-                    const RowRange rr = cta_rows(F);
+                    residual_layer_norm(xres_s, xin_s, p.y1, LL ? p.ll_y1 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 1 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), layer == 0, lp1, C, inv_c, red);
+                    const RowRange rr{s_rows[4], s_rows[5]};
                     const int nr = rr.r1 - rr.r0;
-                    prof_stamp(p, pb + 9, prof_on);
+                    prof_stamp(p, pb + 9, prof_on); prof_all(p, 9, all_on);
                     const int nu = nr * nu1;
                     const bool own = tid < nu && (tid % nu1) == 0;
                     const float bias = own ? __half2float(p.b1[(size_t)layer * F + rr.r0 + tid / nu1]) : 0.f;
                     cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu1, nparts);
-                        if (own) p.h1[rr.r0 + tid / nu1] = __float2half_rn(fmaxf(round_f16(sum + bias), 0.f));
+                        const __half hv = __float2half_rn(fmaxf(round_f16(sum + bias), 0.f));
+                        if (LL) ll_publish_rows(p.ll_h1, rr.r0, nu, nu1, hv, flag, p.use_hint ? p.hint + 2 * p.layers + layer : nullptr);
+                        else if (own) p.h1[rr.r0 + tid / nu1] = hv;
                     }
                 }
-                prof_stamp(p, pb + 10, prof_on);
-                grid_barrier(p.bar, epoch);
-                prof_stamp(p, pb + 11, prof_on);
+                prof_stamp(p, pb + 10, prof_on); prof_all(p, 10, all_on);
+                if (!LL) grid_barrier(p.bar, epoch);
+                prof_stamp(p, pb + 11, prof_on); prof_all(p, 11, all_on);
                 // ---------------- P5: y2 = fc2(h1) -----------------------------------------------------------------------------------------
                 {
-                    for (int i = tid; i < F / 8; i += kConsumers)
-                        reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.h1) + i);
+                    if (LL) {
+                        ll_fetch(p.ll_h1, xin_s, F / 4, flag, p.poll_rounds, p.use_hint ? p.hint + 2 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(F / 2));
+                    } else {
+                        for (int i = tid; i < F / 8; i += kConsumers)
+                            reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.h1) + i);
+                    }
                     cbar();
-                    const RowRange rr = cta_rows(C);
+                    const RowRange rr{s_rows[2], s_rows[3]};
                     const int nr = rr.r1 - rr.r0, nu = nr * nu_fc2;
-                    prof_stamp(p, pb + 12, prof_on);
+                    prof_stamp(p, pb + 12, prof_on); prof_all(p, 12, all_on);
                     const float bias = (tid < nu && (tid % nu_fc2) == 0) ? __half2float(p.b2[(size_t)layer * C + rr.r0 + tid / nu_fc2]) : 0.f;
                     cur = gemv_job(ring, cur, nu, nu_fc2, gc, xin_s, part_s);
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu_fc2, nparts);
-                        if (tid < nu && (tid % nu_fc2) == 0) p.y2[rr.r0 + tid / nu_fc2] = __float2half_rn(sum + bias);
+                        if (LL) ll_publish_rows(p.ll_y2, rr.r0, nu, nu_fc2, __float2half_rn(sum + bias), flag, p.use_hint ? p.hint + 3 * p.layers + layer : nullptr);
+                        else if (tid < nu && (tid % nu_fc2) == 0) p.y2[rr.r0 + tid / nu_fc2] = __float2half_rn(sum + bias);
                     }
                 }
                 const LnParams lp2 = ln_load(p.ln2_w + (size_t)layer * C, p.ln2_b + (size_t)layer * C, C);
-                prof_stamp(p, pb + 13, prof_on);
-                grid_barrier(p.bar, epoch);
-                prof_stamp(p, pb + 14, prof_on);
+                prof_stamp(p, pb + 13, prof_on); prof_all(p, 13, all_on);
+                if (!LL) grid_barrier(p.bar, epoch);
+                prof_stamp(p, pb + 14, prof_on); prof_all(p, 14, all_on);
                 // ---------------- x = LN2(x + y2) ------------------------------------------------------------------------------------------
-                residual_layer_norm(xres_s, xin_s, p.y2, false, lp2, C, inv_c, red);
+                residual_layer_norm(xres_s, xin_s, p.y2, LL ? p.ll_y2 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 3 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), false, lp2, C, inv_c, red);
             }
             // ================= lm_head: logits_pre = fp16(x) @ W^T (fp32 value before the fp16 store) ================
             {
-                const RowRange rr = cta_rows(V);
+                const RowRange rr{s_rows[6], s_rows[7]};
                 const int nr = rr.r1 - rr.r0;
                 const int nu = nr * nu1;
                 cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
@@ -987,18 +1224,27 @@ int er_decode_pick_stages(const er::DecodeParams& p, size_t smem_limit) {
 int er_decode_max_units() { return er::kMaxUnits; }
 int er_decode_stage_bytes() { return er::kStageBytes; }
 
+static const void* er_decode_kernel_fn(bool prof, bool ll) {
+    if (prof) return ll ? (const void*)er::decode_persistent_kernel<true, true> : (const void*)er::decode_persistent_kernel<true, false>;
+    return ll ? (const void*)er::decode_persistent_kernel<false, true> : (const void*)er::decode_persistent_kernel<false, false>;
+}
 cudaError_t er_decode_launch(const er::DecodeParams& p, int grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(er::decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const void* fn = er_decode_kernel_fn(p.prof != nullptr, p.use_ll != 0);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&p};
-    return cudaLaunchCooperativeKernel((const void*)er::decode_persistent_kernel, dim3(grid), dim3(er::kThreads), args, smem, stream);
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(er::kThreads), args, smem, stream);
 }
 
 int er_decode_max_grid(size_t smem) {
     int dev = 0, sms = 0, per = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(er::decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, er::decode_persistent_kernel, er::kThreads, smem);
-    return per > 0 ? sms : 0;
+    int ok = 1;
+    for (int v = 0; v < 4; ++v) {
+        const void* fn = er_decode_kernel_fn((v & 1) != 0, (v & 2) != 0);
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, er::kThreads, smem) != cudaSuccess || per < 1) ok = 0;
+    }
+    return ok ? sms : 0;
 }

@@ -36,6 +36,13 @@ struct DecodeParams {
     unsigned *head_cnt;   // [H] monotonic split-completion tickets (zeroed with the barrier counter)
     float *part;      // [H][S][100]: o[96], m, l
     float *logits;    // [V] fp32 lm_head output before the fp16 rounding
+    // flagged exchange (use_ll): the same vectors as 8-byte {payload, flag} words that readers poll instead of meeting at a grid
+    // barrier; payload = two fp16 (q|k|v, attn, y1, h1, y2) or one fp32 (split partials).  Zeroed by the host before each launch.
+    unsigned long long *ll_q, *ll_attn, *ll_y1, *ll_h1, *ll_y2, *ll_part;
+    int use_ll;
+    unsigned *hint;    // [4][layers] arrival-hint counters (attn, y1, h1, y2), zeroed before each launch
+    int use_hint;
+    int poll_rounds;   // all-thread polling rounds before a warp falls back to one spinning lane
     DecodeState *st;
     unsigned *bar;    // grid barrier counter (zeroed by the host before each launch)
     // io

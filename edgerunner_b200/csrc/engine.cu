@@ -86,6 +86,7 @@ struct er_engine {
     // cache + decode scratch
     __half *kc, *vc, *q16, *y1, *h1, *y2, *attn16;
     float *part, *logits, *cond32;
+    unsigned long long* ll = nullptr; size_t ll_words = 0; int use_ll = 0; unsigned* hint = nullptr;   // flagged exchange words of the decode kernel
     er::DecodeState* st;
     unsigned* bar;
     int32_t* ids_dev;
@@ -210,8 +211,8 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     ALLOC(e->logits, V); ALLOC(e->st, 1); ALLOC(e->bar, 64 + 64); ALLOC(e->cond32, (size_t)P * C);
     ALLOC(e->ids_dev, 65536); ALLOC(e->gen_ids_dev, cfg->max_seq_rows + 8); ALLOC(e->gen_len_dev, 4);
     ALLOC(e->conds_dev_buf, (size_t)(cfg->max_points > LQ * LD ? cfg->max_points * 3 : LQ * LD) + 16);
-    ALLOC(e->prof, 4096);
-    CK(cudaMemset(e->prof, 0, 4096 * 8));
+    ALLOC(e->prof, 8192);
+    CK(cudaMemset(e->prof, 0, 8192 * 8));
     CK(cudaMemset(e->st, 0, sizeof(er::DecodeState)));
     // decode launch geometry
     int sms = 0;
@@ -219,6 +220,12 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     e->grid = sms;
     e->S = sms / H; if (e->S > 16) e->S = 16; if (e->S < 1) { delete e; return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
     ALLOC(e->part, (size_t)H * e->S * 100);
+    e->ll_words = (size_t)3 * C / 2 + 3 * (size_t)(C / 2) + F / 2 + (size_t)H * e->S * 100;
+    ALLOC(e->ll, e->ll_words);
+    ALLOC(e->hint, 4 * (size_t)NL);
+    // experiment switch: 1 = flagged-word exchange instead of grid barriers inside a layer (measured slower: same number of
+    // dependent L2 round trips per exchange once polling is throttled, plus register pressure)
+    if (const char* v = getenv("ER_DECODE_LL")) e->use_ll = atoi(v) != 0;
     e->sc_len = std::max(((e->nkb + 7 + e->S - 1) / e->S) * 32 + 64, (V + 3) / 4 * 4);   // 7 = kLastSplitHandicap (decode_kernel.cu)
     {
         er::DecodeParams p{}; p.C = C; p.F = F; p.H = H; p.V = V; p.S = e->S; p.sc_len = e->sc_len;
@@ -438,6 +445,12 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.split_handicap = 4;
     if (const char* v = getenv("ER_SPLIT_HANDICAP")) p.split_handicap = std::max(0, std::min(7, atoi(v)));
     p.kc = e->kc; p.vc = e->vc; p.attn16 = e->attn16; p.head_cnt = e->bar + 64; p.q16 = e->q16; p.y1 = e->y1; p.h1 = e->h1; p.y2 = e->y2; p.part = e->part; p.logits = e->logits;
+    p.ll_q = e->ll; p.ll_attn = p.ll_q + 3 * C / 2; p.ll_y1 = p.ll_attn + C / 2; p.ll_y2 = p.ll_y1 + C / 2; p.ll_h1 = p.ll_y2 + C / 2;
+    p.ll_part = p.ll_h1 + F / 2; p.use_ll = e->use_ll && (C % 4 == 0) && (V % 2 == 0);
+    p.poll_rounds = 4;
+    p.hint = e->hint; p.use_hint = 1;
+    if (const char* v = getenv("ER_DECODE_HINT")) p.use_hint = atoi(v) != 0;
+    if (const char* v = getenv("ER_POLL_ROUNDS")) p.poll_rounds = std::max(0, atoi(v));
     p.st = e->st; p.bar = e->bar;
     p.out_ids = out_ids_dev; p.out_logits = out_logits_dev; p.forced = forced_ids_dev;
     p.max_new = max_new_tokens; p.mode = mode; p.top_k = top_k > 0 ? top_k : 10; p.use_fsm = use_tokenizer_fsm; p.eos = e->cfg.eos_token_id;
@@ -447,6 +460,7 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     for (int done = 0; done < max_new_tokens; done += chunk) {
         p.steps = std::min(chunk, max_new_tokens - done);
         CK(cudaMemsetAsync(e->bar, 0, (64 + 64) * 4, st));
+        if (p.use_ll) { CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st)); CK(cudaMemsetAsync(e->hint, 0, 4 * (size_t)e->NL * 4, st)); }
         CKL(e, er_decode_launch(p, G, e->dec_smem, st));
     }
     if (out_len_dev) {
@@ -547,7 +561,7 @@ extern "C" int er_debug_phase_timeline(er_engine* e, int32_t token, int32_t cta)
     return ER_OK;
 }
 extern "C" int er_debug_read_timeline(er_engine* e, uint64_t* out_host, int32_t n) {
-    if (!e || !out_host || n < 0 || n > 4096) return set_err(ER_ERR_INVALID, "bad argument");
+    if (!e || !out_host || n < 0 || n > 8192) return set_err(ER_ERR_INVALID, "bad argument");
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out_host, e->prof, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return ER_OK;

@@ -111,7 +111,8 @@ int32_t er_cache_rows(const er_engine* e);               /* rows currently in th
 int64_t er_kernel_launches(const er_engine* e);          /* kernels launched by this engine so far */
 
 /* Profiling aid (profiles/): phase timeline of one CTA for one generated token of the next er_decode call. Slots (ns):
- * [0] token start, then for each layer 5 x (phase end, barrier end), then (lm_head end, barrier end). */
+ * [0] token start, then for each layer 15 stamps (phase / exchange boundaries, see decode_kernel.cu), then (lm_head end,
+ * barrier end); slots [4096 + 16 * cta + k]: the same 15 stamps of layer 5 for every CTA.  n <= 8192. */
 int er_debug_phase_timeline(er_engine* e, int32_t token, int32_t cta);
 int er_debug_read_timeline(er_engine* e, uint64_t* out_host, int32_t n);
 
