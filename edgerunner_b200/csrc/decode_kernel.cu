@@ -270,6 +270,25 @@ __device__ __forceinline__ void ll_publish_rows(unsigned long long* dst, int r0,
     }
 }
 
+// the same barrier in two halves: work placed between them overlaps the counter round trip
+__device__ __forceinline__ void grid_arrive(unsigned* counter, unsigned& epoch) {
+    cbar();
+    if (threadIdx.x == 0) {
+        epoch += 1;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    }
+}
+__device__ __forceinline__ void grid_wait(unsigned* counter, unsigned epoch) {
+    if (threadIdx.x == 0) {
+        const unsigned target = epoch * gridDim.x;
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    cbar();
+}
+
 // ---- optional phase timeline (profiles/): one CTA, thread 0 stamps %globaltimer ------------------------------------------------
 // slot map: [0] token start; per layer l, base = 1 + 16*l: +0 residual+LN2 done, +1 qkv gemv done, +2 P1 epilogue done, +3 B1,
 // +4 attention done, +5 B2, +6 attn16 loaded, +7 out_proj done, +8 B3, +9 LN1 done, +10 fc1 done, +11 B4, +12 h1 loaded,
@@ -358,7 +377,10 @@ __device__ __forceinline__ bool produce(const Ring r, Cursor& cur, const void* b
 
 // The kernel parameters are copied into registers up front: the consumers' acquire loads at the grid barrier invalidate the L1, and a
 // parameter fetched through a reference (local / generic memory) right after that costs the producer an L2 round trip per field.
-__device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, volatile int* stop, volatile uint32_t* cons_it) {
+// Run-ahead bound: weights never change, but the K block / V rows that hold key L-1 were written by the PREVIOUS token's P1.  The ring
+// alone does not bound the producer by tokens (a CTA that owns few rows of a small model needs fewer stages per token than the ring has
+// slots), so K/V copies of pass j are only issued once the consumers have left the token-end grid barrier of pass j-1 (`tok_done`).
+__device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, volatile int* stop, volatile uint32_t* cons_it, volatile int* tok_done) {
     const int C = p.C, F = p.F, H = p.H, S = p.S, V = p.V, layers = p.layers, ustride = p.ustride, handicap = p.split_handicap;
     const int nkb = p.nkb, Lmax = p.Lmax;
     const __half* const wdec = p.wdec;
@@ -383,6 +405,10 @@ __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, 
         for (int layer = 0; layer < layers && ok; ++layer) {
             const __half* wl = wdec + (size_t)layer * UL * ustride;
             ok = produce(r, cur, wl + (size_t)rq.r0 * ustride, (size_t)(rq.r1 - rq.r0) * ub, wchunk, stop);
+            if (ok && has_attn && layer == 0 && pass > 0) {
+                while (*tok_done < pass) { if (*stop) { ok = false; break; } }
+                asm volatile("fence.proxy.async.global;" ::: "memory");   // rows written through the generic proxy, read by the bulk copy below
+            }
             if (ok && has_attn) {
                 const __half* kbase = kc + (((size_t)layer * H + a.h) * nkb + a.b0) * (size_t)(HV * 256);
                 ok = produce(r, cur, kbase, (size_t)(a.b1 - a.b0) * kKBlockBytes, kKVChunk, stop);
@@ -788,9 +814,8 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
             }
         }
     } else if (a.is_new) {
-        if (warp == 0 && lane < HV)
-            knew = ldg_cg(reinterpret_cast<const uint4*>(p.kc + ((((size_t)layer * H + a.h) * p.nkb + (L >> 5)) * HV + lane) * 256 + (size_t)(L & 31) * 8));
-        if (tid < HD) vnew = ldg_cg_u16(p.vc + (((size_t)layer * H + a.h) * p.Lmax + L) * HD + tid);
+        if (warp == 0 && lane < HV) knew = ldg_cg(reinterpret_cast<const uint4*>(p.q16 + p.C + a.h * HD) + lane);
+        if (tid < HD) vnew = ldg_cg_u16(p.q16 + 2 * p.C + a.h * HD + tid);
     }
     if (nk > 0) {
         if (!LL && tid < HD) qs[tid] = __half2float(__ushort_as_half(ldg_cg_u16(p.q16 + a.h * HD + tid)));
@@ -1006,6 +1031,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
     __shared__ int s_stop;
     __shared__ uint32_t s_cons_it;
     __shared__ int s_flag;
+    __shared__ int s_tok_done;   // tokens of this launch whose token-end grid barrier the consumers have passed
     __shared__ int s_rows[8];   // this CTA's row ranges of the 3C / C / F / V phases (computed once; registers are scarce)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1013,6 +1039,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
         for (int i = 0; i < p.nstage; i++) { mbar_init(ring.fullb(i), 1); mbar_init(ring.emptyb(i), kConsumerWarps); }
         s_stop = 0;
         s_cons_it = 0;
+        s_tok_done = 0;
         const RowRange r3 = cta_rows(3 * C), r1 = cta_rows(C), rf = cta_rows(F), rv = cta_rows(V);
         s_rows[0] = r3.r0; s_rows[1] = r3.r1; s_rows[2] = r1.r0; s_rows[3] = r1.r1; s_rows[4] = rf.r0; s_rows[5] = rf.r1; s_rows[6] = rv.r0; s_rows[7] = rv.r1;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1022,7 +1049,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
 
     if (warp == kConsumerWarps) {
         // ===== producer warp: one elected lane streams this CTA's byte ranges through the ring =====
-        if (lane == 0) producer_loop(p, ring, &s_stop, &s_cons_it);
+        if (lane == 0) producer_loop(p, ring, &s_stop, &s_cons_it, &s_tok_done);
     } else {
         // ===== consumers =====
         unsigned epoch = 0;
@@ -1084,28 +1111,31 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     const float bias = own ? __half2float(p.bqkv[(size_t)layer * 3 * C + rr.r0 + tid / nu1]) : 0.f;   // in flight during the GEMV
                     cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
                     prof_stamp(p, pb + 1, prof_on); prof_all(p, 1, all_on);
+                    // q, new k, new v go to a small dense vector the attention CTAs read (q16[3C]) — or to flagged words; the K/V CACHE rows
+                    // (scattered 2-byte stores into pages only this token touches: TLB misses that hold the storing warp for ~1 us)
+                    // are only needed by later tokens and are written after this CTA has arrived at the barrier
+                    __half hv = __float2half_rn(0.f);
+                    const int r = rr.r0 + tid / nu1;
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu1, nparts);
-                        const __half hv = __float2half_rn(sum + bias);
-                        // publish first: the attention CTAs of this head wait for these words; the cache rows are for later tokens
+                        hv = __float2half_rn(sum + bias);
                         if (LL) ll_publish_rows(p.ll_q, rr.r0, nu, nu1, hv, flag, nullptr);
-                        if (own) {
-                            const int r = rr.r0 + tid / nu1;
-                            if (r < C) {
-                                if (!LL) p.q16[r] = hv;
-                            } else if (r < 2 * C) {
-                                const int c = r - C, h = c / HD, d = c % HD;
-                                const size_t idx = ((((size_t)layer * H + h) * (size_t)p.nkb + (L >> 5)) * HV + (d >> 3)) * 256 + (size_t)(L & 31) * 8 + (d & 7);
-                                p.kc[idx] = hv;
-                            } else {
-                                const int c = r - 2 * C, h = c / HD, d = c % HD;
-                                p.vc[(((size_t)layer * H + h) * p.Lmax + L) * HD + d] = hv;
-                            }
+                        else if (own) p.q16[r] = hv;
+                    }
+                    prof_stamp(p, pb + 2, prof_on); prof_all(p, 2, all_on);
+                    if (!LL) grid_arrive(p.bar, epoch);
+                    if (own && r >= C) {
+                        if (r < 2 * C) {
+                            const int c = r - C, h = c / HD, d = c % HD;
+                            const size_t idx = ((((size_t)layer * H + h) * (size_t)p.nkb + (L >> 5)) * HV + (d >> 3)) * 256 + (size_t)(L & 31) * 8 + (d & 7);
+                            p.kc[idx] = hv;
+                        } else {
+                            const int c = r - 2 * C, h = c / HD, d = c % HD;
+                            p.vc[(((size_t)layer * H + h) * p.Lmax + L) * HD + d] = hv;
                         }
                     }
+                    if (!LL) grid_wait(p.bar, epoch);
                 }
-                prof_stamp(p, pb + 2, prof_on); prof_all(p, 2, all_on);
-                if (!LL) grid_barrier(p.bar, epoch);
                 prof_stamp(p, pb + 3, prof_on); prof_all(p, 3, all_on);
                 // ---------------- P2: attention -----------------------------------------------------------------------------------------
                 cur = attention_phase<LL>(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag, part, flag);
@@ -1199,6 +1229,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
             L += 1;
             prof_stamp(p, 1 + 16 * p.layers, prof_on);
             grid_barrier(p.bar, epoch);
+            if (tid == 0) { __threadfence_block(); *(volatile int*)&s_tok_done = iter + 1; }
             prof_stamp(p, 2 + 16 * p.layers, prof_on);
         }
         if (!state_written && blockIdx.x == 0 && tid == 0) { p.st->t = t; p.st->L = L; p.st->counter = counter; p.st->last_tok = last_tok; }

@@ -32,7 +32,7 @@ struct DecodeParams {
     // KV cache: K blocked [layer][head][key/32][d/8][key%32][8], V natural [layer][head][key][96]
     __half *kc, *vc;
     // cross-CTA scratch (global, read back with ld.cg)
-    __half *q16, *y1, *h1, *y2, *attn16;
+    __half *q16, *y1, *h1, *y2, *attn16;   // q16: [3C] = q | new k | new v of the current token
     unsigned *head_cnt;   // [H] monotonic split-completion tickets (zeroed with the barrier counter)
     float *part;      // [H][S][100]: o[96], m, l
     float *logits;    // [V] fp32 lm_head output before the fp16 rounding

@@ -108,6 +108,17 @@ template <typename T>
 static int dev_alloc(er_engine* e, T** p, size_t n) {
     void* q = nullptr;
     CK(cudaMalloc(&q, n * sizeof(T) + 256));
+    // debugging aid (tests/test_gpu_parity.py::test_poisoned_memory): fill every allocation with 0xFF bytes (fp16 / fp32 NaN) so that
+    // any read of memory the engine did not write first shows up as NaN instead of passing by luck on zeroed pages
+    static const char* poison = getenv("ER_POISON_ALLOC");   // "1" = everything; "kc" / "vc" / "rest" narrow it down (the two big caches are
+    static int seq = 0;                                        // the 1st and 2nd allocation of the "KV cache + decode scratch" block)
+    if (poison) {
+        const bool is_kc = (void*)p == (void*)&e->kc, is_vc = (void*)p == (void*)&e->vc;
+        const bool want = !strcmp(poison, "1") || (!strcmp(poison, "kc") && is_kc) || (!strcmp(poison, "vc") && is_vc) ||
+                          (!strcmp(poison, "rest") && !is_kc && !is_vc);
+        if (want) CK(cudaMemset(q, 0xFF, n * sizeof(T) + 256));
+    }
+    (void)seq;
     e->allocs.push_back(q);
     *p = (T*)q;
     return ER_OK;
@@ -207,7 +218,7 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     }
     // ---- KV cache + decode scratch ---------------------------------------------------------------------------------------------
     ALLOC(e->kc, (size_t)NL * H * e->nkb * 32 * 96); ALLOC(e->vc, (size_t)NL * H * Lmax * 96);
-    ALLOC(e->q16, C); ALLOC(e->y1, C); ALLOC(e->h1, F); ALLOC(e->y2, C); ALLOC(e->attn16, C);
+    ALLOC(e->q16, 3 * (size_t)C); ALLOC(e->y1, C); ALLOC(e->h1, F); ALLOC(e->y2, C); ALLOC(e->attn16, C);
     ALLOC(e->logits, V); ALLOC(e->st, 1); ALLOC(e->bar, 64 + 64); ALLOC(e->cond32, (size_t)P * C);
     ALLOC(e->ids_dev, 65536); ALLOC(e->gen_ids_dev, cfg->max_seq_rows + 8); ALLOC(e->gen_len_dev, 4);
     ALLOC(e->conds_dev_buf, (size_t)(cfg->max_points > LQ * LD ? cfg->max_points * 3 : LQ * LD) + 16);

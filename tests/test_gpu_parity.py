@@ -126,6 +126,19 @@ def test_chunked_launches_equal_single_launch(tiny_setup):
         assert torch.equal(r['logits_pre'], res[0]['logits_pre'])      # bit-exact: same kernel, same order
 
 
+@pytest.mark.parametrize('which', ['tiny', 'arae'])
+def test_poisoned_memory_and_repeatability(which):
+    """Fresh process, every device allocation pre-filled with NaN bytes (ER_POISON_ALLOC): no NaN may reach the logits (nothing is read
+    before the engine wrote it) and the FIRST decode of a new engine equals the following ones bit for bit."""
+    import json, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, 'poison_check.py'), which], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res['nan'] == [0, 0, 0], res
+    assert res['identical_to_first'] == [True, True], res
+
+
 def test_generate_host_equals_device_path(tiny_setup):
     opt, sd, eng, orc, cond = tiny_setup
     eng.encode_cond(cond[0].cuda(), 2500)
