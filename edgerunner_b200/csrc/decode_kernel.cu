@@ -1002,7 +1002,8 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
             den = fmaf(w, ls[s], den);
             num = fmaf(w, ov[s], num);
         }
-        p.attn16[a.h * HD + tid] = __float2half_rn(num / den);
+        const __half av = __float2half_rn(num / den);
+        for (int c = 0; c < p.xrep; c++) p.attn16[(size_t)c * p.C + a.h * HD + tid] = av;
     }
     return cur;
 }
@@ -1063,6 +1064,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
         const int nu1 = kUnitDiv;                   // units per row of the C-wide phases
         const int nparts = p.use_mma ? kConsumerWarps : 32;
         const GemvCfg gc{p.C, p.ustride, p.upstage, p.use_mma};
+        const int xcopy = (int)(blockIdx.x % (unsigned)p.xrep);   // which replica of the exchanged vectors this CTA reads
         for (int iter = 0; iter < p.steps && !done0; ++iter, ++t) {
             const bool prof_on = PROF && p.prof != nullptr && t == p.prof_token && (int)blockIdx.x == p.prof_cta;
             prof_stamp(p, 0, prof_on);
@@ -1148,7 +1150,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                         ll_fetch(p.ll_attn, xin_s, C / 4, flag, p.poll_rounds, p.use_hint ? p.hint + 0 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2));
                     } else {
                         for (int i = tid; i < C / 8; i += kConsumers)
-                            reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.attn16) + i);
+                            reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.attn16 + (size_t)xcopy * C) + i);
                     }
                     cbar();
                     const RowRange rr{s_rows[2], s_rows[3]};
@@ -1161,7 +1163,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu1, nparts);
                         if (LL) ll_publish_rows(p.ll_y1, rr.r0, nu, nu1, __float2half_rn(sum + bias), flag, p.use_hint ? p.hint + 1 * p.layers + layer : nullptr);
-                        else if (own) p.y1[rr.r0 + tid / nu1] = __float2half_rn(sum + bias);
+                        else if (own) { const __half yv = __float2half_rn(sum + bias); for (int c = 0; c < p.xrep; c++) p.y1[(size_t)c * C + rr.r0 + tid / nu1] = yv; }
                     }
                 }
                 const LnParams lp1 = ln_load(p.ln1_w + (size_t)layer * C, p.ln1_b + (size_t)layer * C, C);   // lands while we wait at the barrier
@@ -1170,7 +1172,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 prof_stamp(p, pb + 8, prof_on); prof_all(p, 8, all_on);
                 // ---------------- P4: x = LN1(x + y1) ; h1 = relu(fc1(x)) -----------------------------------------------------------
                 {
-                    residual_layer_norm(xres_s, xin_s, p.y1, LL ? p.ll_y1 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 1 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), layer == 0, lp1, C, inv_c, red);
+                    residual_layer_norm(xres_s, xin_s, p.y1 + (size_t)xcopy * C, LL ? p.ll_y1 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 1 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), layer == 0, lp1, C, inv_c, red);
                     const RowRange rr{s_rows[4], s_rows[5]};
                     const int nr = rr.r1 - rr.r0;
                     prof_stamp(p, pb + 9, prof_on); prof_all(p, 9, all_on);
@@ -1182,7 +1184,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                         const float sum = reduce_rows(part_s, nu, nu1, nparts);
                         const __half hv = __float2half_rn(fmaxf(round_f16(sum + bias), 0.f));
                         if (LL) ll_publish_rows(p.ll_h1, rr.r0, nu, nu1, hv, flag, p.use_hint ? p.hint + 2 * p.layers + layer : nullptr);
-                        else if (own) p.h1[rr.r0 + tid / nu1] = hv;
+                        else if (own) for (int c = 0; c < p.xrep; c++) p.h1[(size_t)c * F + rr.r0 + tid / nu1] = hv;
                     }
                 }
                 prof_stamp(p, pb + 10, prof_on); prof_all(p, 10, all_on);
@@ -1194,7 +1196,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                         ll_fetch(p.ll_h1, xin_s, F / 4, flag, p.poll_rounds, p.use_hint ? p.hint + 2 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(F / 2));
                     } else {
                         for (int i = tid; i < F / 8; i += kConsumers)
-                            reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.h1) + i);
+                            reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.h1 + (size_t)xcopy * F) + i);
                     }
                     cbar();
                     const RowRange rr{s_rows[2], s_rows[3]};
@@ -1205,7 +1207,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu_fc2, nparts);
                         if (LL) ll_publish_rows(p.ll_y2, rr.r0, nu, nu_fc2, __float2half_rn(sum + bias), flag, p.use_hint ? p.hint + 3 * p.layers + layer : nullptr);
-                        else if (tid < nu && (tid % nu_fc2) == 0) p.y2[rr.r0 + tid / nu_fc2] = __float2half_rn(sum + bias);
+                        else if (tid < nu && (tid % nu_fc2) == 0) { const __half yv = __float2half_rn(sum + bias); for (int c = 0; c < p.xrep; c++) p.y2[(size_t)c * C + rr.r0 + tid / nu_fc2] = yv; }
                     }
                 }
                 const LnParams lp2 = ln_load(p.ln2_w + (size_t)layer * C, p.ln2_b + (size_t)layer * C, C);
@@ -1213,7 +1215,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 if (!LL) grid_barrier(p.bar, epoch);
                 prof_stamp(p, pb + 14, prof_on); prof_all(p, 14, all_on);
                 // ---------------- x = LN2(x + y2) ------------------------------------------------------------------------------------------
-                residual_layer_norm(xres_s, xin_s, p.y2, LL ? p.ll_y2 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 3 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), false, lp2, C, inv_c, red);
+                residual_layer_norm(xres_s, xin_s, p.y2 + (size_t)xcopy * C, LL ? p.ll_y2 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 3 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), false, lp2, C, inv_c, red);
             }
             // ================= lm_head: logits_pre = fp16(x) @ W^T (fp32 value before the fp16 store) ================
             {

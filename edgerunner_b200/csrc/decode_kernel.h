@@ -32,6 +32,7 @@ struct DecodeParams {
     // KV cache: K blocked [layer][head][key/32][d/8][key%32][8], V natural [layer][head][key][96]
     __half *kc, *vc;
     // cross-CTA scratch (global, read back with ld.cg)
+    int xrep;   // replicas of attn16 / y1 / h1 / y2 (writers store all, CTA b reads replica b % xrep): spreads 148 readers over L2 slices
     __half *q16, *y1, *h1, *y2, *attn16;   // q16: [3C] = q | new k | new v of the current token
     unsigned *head_cnt;   // [H] monotonic split-completion tickets (zeroed with the barrier counter)
     float *part;      // [H][S][100]: o[96], m, l

@@ -218,7 +218,7 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     }
     // ---- KV cache + decode scratch ---------------------------------------------------------------------------------------------
     ALLOC(e->kc, (size_t)NL * H * e->nkb * 32 * 96); ALLOC(e->vc, (size_t)NL * H * Lmax * 96);
-    ALLOC(e->q16, 3 * (size_t)C); ALLOC(e->y1, C); ALLOC(e->h1, F); ALLOC(e->y2, C); ALLOC(e->attn16, C);
+    ALLOC(e->q16, 3 * (size_t)C); ALLOC(e->y1, 8 * (size_t)C); ALLOC(e->h1, 8 * (size_t)F); ALLOC(e->y2, 8 * (size_t)C); ALLOC(e->attn16, 8 * (size_t)C);
     ALLOC(e->logits, V); ALLOC(e->st, 1); ALLOC(e->bar, 64 + 64); ALLOC(e->cond32, (size_t)P * C);
     ALLOC(e->ids_dev, 65536); ALLOC(e->gen_ids_dev, cfg->max_seq_rows + 8); ALLOC(e->gen_len_dev, 4);
     ALLOC(e->conds_dev_buf, (size_t)(cfg->max_points > LQ * LD ? cfg->max_points * 3 : LQ * LD) + 16);
@@ -459,6 +459,8 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.ll_q = e->ll; p.ll_attn = p.ll_q + 3 * C / 2; p.ll_y1 = p.ll_attn + C / 2; p.ll_y2 = p.ll_y1 + C / 2; p.ll_h1 = p.ll_y2 + C / 2;
     p.ll_part = p.ll_h1 + F / 2; p.use_ll = e->use_ll && (C % 4 == 0) && (V % 2 == 0);
     p.poll_rounds = 4;
+    p.xrep = 1;
+    if (const char* v = getenv("ER_XREP")) p.xrep = std::max(1, std::min(8, atoi(v)));
     p.hint = e->hint; p.use_hint = 1;
     if (const char* v = getenv("ER_DECODE_HINT")) p.use_hint = atoi(v) != 0;
     if (const char* v = getenv("ER_POLL_ROUNDS")) p.poll_rounds = std::max(0, atoi(v));
