@@ -48,7 +48,6 @@ constexpr int kStageBytes = 24704;                // 8 padded weight units of (1
 constexpr int kKVChunk = 24576;                   // bytes per stage of the K / V jobs (4 K blocks = 128 V rows)
 constexpr int kMaxStages = 8;
 constexpr int kKBlockBytes = HV * 32 * 16;        // 6144: one 32-key block of the blocked K cache
-constexpr int kLastSplitHandicap = 7;             // see attn_range()
 constexpr int kMaxUnits = 64 * kUnitDiv;          // weight units a CTA owns in one phase
 constexpr int kPartStride = kMaxUnits + 1;        // lane-partial matrix [32][kPartStride] (odd stride: conflict-free both ways)
 
@@ -334,7 +333,7 @@ __device__ __forceinline__ bool attn_range(int H, int S, int split_handicap, int
     const int s = blockIdx.x % S;
     const int nblk = (L + 31) >> 5;                  // blocks holding old keys 0..L-1
     // the last split also owns the new key and (being the last to finish) usually merges the head: that fixed work is worth
-    // about split_handicap (<= kLastSplitHandicap) blocks of streaming, so it gets that many fewer blocks
+    // about split_handicap (<= 7, see engine.cu sc_len) blocks of streaming, so it gets that many fewer blocks
     const int bps = (nblk + split_handicap + S - 1) / S;
     a.b0 = min(s * bps, nblk);
     a.b1 = min(a.b0 + bps, nblk);
@@ -782,7 +781,6 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     AttnRange a;
     if (!attn_range(p.H, p.S, p.split_handicap, L, a)) return cur;
-    const int H = p.H;
     const float cl2 = rsqrtf((float)HD) * 1.4426950408889634f;   // softmax scale in log2 units
     float* outp = p.part + ((size_t)a.h * p.S + (blockIdx.x % p.S)) * 100;
     const int nold = a.k1 - a.k0;

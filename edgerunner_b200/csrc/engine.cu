@@ -110,15 +110,13 @@ static int dev_alloc(er_engine* e, T** p, size_t n) {
     CK(cudaMalloc(&q, n * sizeof(T) + 256));
     // debugging aid (tests/test_gpu_parity.py::test_poisoned_memory): fill every allocation with 0xFF bytes (fp16 / fp32 NaN) so that
     // any read of memory the engine did not write first shows up as NaN instead of passing by luck on zeroed pages
-    static const char* poison = getenv("ER_POISON_ALLOC");   // "1" = everything; "kc" / "vc" / "rest" narrow it down (the two big caches are
-    static int seq = 0;                                        // the 1st and 2nd allocation of the "KV cache + decode scratch" block)
+    static const char* poison = getenv("ER_POISON_ALLOC");   // "1" = everything; "kc" / "vc" / "rest" narrow a finding down
     if (poison) {
         const bool is_kc = (void*)p == (void*)&e->kc, is_vc = (void*)p == (void*)&e->vc;
         const bool want = !strcmp(poison, "1") || (!strcmp(poison, "kc") && is_kc) || (!strcmp(poison, "vc") && is_vc) ||
                           (!strcmp(poison, "rest") && !is_kc && !is_vc);
         if (want) CK(cudaMemset(q, 0xFF, n * sizeof(T) + 256));
     }
-    (void)seq;
     e->allocs.push_back(q);
     *p = (T*)q;
     return ER_OK;
@@ -237,7 +235,7 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     // experiment switch: 1 = flagged-word exchange instead of grid barriers inside a layer (measured slower: same number of
     // dependent L2 round trips per exchange once polling is throttled, plus register pressure)
     if (const char* v = getenv("ER_DECODE_LL")) e->use_ll = atoi(v) != 0;
-    e->sc_len = std::max(((e->nkb + 7 + e->S - 1) / e->S) * 32 + 64, (V + 3) / 4 * 4);   // 7 = kLastSplitHandicap (decode_kernel.cu)
+    e->sc_len = std::max(((e->nkb + 7 + e->S - 1) / e->S) * 32 + 64, (V + 3) / 4 * 4);   // 7 = largest split handicap er_decode accepts
     {
         er::DecodeParams p{}; p.C = C; p.F = F; p.H = H; p.V = V; p.S = e->S; p.sc_len = e->sc_len;
         int smem_max = 0;

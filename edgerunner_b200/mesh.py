@@ -1,7 +1,8 @@
 """Minimal triangle-mesh holder used when ``trimesh`` is not installed (it is absent from the target image).
 
 Covers what ``save_mesh`` / ``infer.py`` touch: ``vertices`` / ``faces``, ``merge_vertices``, ``unique_faces`` +
-``update_faces``, ``fix_normals`` (orientation propagation per connected component) and ``export`` to .ply/.obj.
+``update_faces``, ``fix_normals`` (winding propagated over shared edges inside each connected component, then every component
+with negative signed volume is inverted — the two steps of trimesh's ``repair.fix_normals``) and ``export`` to .ply/.obj.
 Host-side post-processing only; the reference delegates this to third-party trimesh (parity unpinned).
 """
 
@@ -39,10 +40,13 @@ class SimpleMesh:
             for u, v in ((a, b), (b, c), (c, a)):
                 edges.setdefault((min(u, v), max(u, v)), []).append((i, u, v))
         seen = np.zeros(len(f), dtype=bool)
+        comp = np.zeros(len(f), dtype=np.int64)
+        ncomp = 0
         for start in range(len(f)):
             if seen[start]:
                 continue
             seen[start] = True
+            comp[start] = ncomp
             stack = [start]
             while stack:
                 i = stack.pop()
@@ -57,7 +61,20 @@ class SimpleMesh:
                         if (u, v) in dir_j:
                             self.faces[j] = self.faces[j][::-1]
                         seen[j] = True
+                        comp[j] = comp[i]
                         stack.append(j)
+            ncomp += 1
+        # outward orientation: signed volume of each component (sum of v0 . (v1 x v2) / 6); negative -> invert that component
+        tri = self.vertices[self.faces]
+        vol6 = np.einsum('ij,ij->i', tri[:, 0], np.cross(tri[:, 1], tri[:, 2]))
+        flip = np.bincount(comp, weights=vol6, minlength=ncomp) < 0
+        sel = flip[comp]
+        self.faces[sel] = self.faces[sel][:, ::-1]
+
+    @property
+    def volume(self):
+        tri = self.vertices[self.faces]
+        return float(np.einsum('ij,ij->i', tri[:, 0], np.cross(tri[:, 1], tri[:, 2])).sum() / 6.0)
 
     def export(self, path):
         ext = str(path).rsplit('.', 1)[-1].lower()

@@ -184,3 +184,24 @@ def test_encode_rejects_bad_indices():
         Engine(512).encode(v, np.array([[0, 1, 3]]))
     tok, order, ftype = Engine(512).encode(v, np.zeros((0, 3), np.int32))
     assert len(tok) == 0 and len(order) == 0 and len(ftype) == 0
+
+
+def test_simple_mesh_clean_up():
+    """edgerunner_b200.mesh.SimpleMesh (used by save_mesh when trimesh is absent): merge, de-duplicate, consistent outward winding."""
+    import meshes
+    from edgerunner_b200.mesh import SimpleMesh
+    v, f = meshes.cube()
+    soup_v = v[f].reshape(-1, 3)                                   # un-indexed triangle soup, like the detokenizer's output
+    soup_f = np.arange(len(soup_v)).reshape(-1, 3)
+    soup_f[[1, 4, 7]] = soup_f[[1, 4, 7]][:, ::-1]                 # three faces with the wrong winding
+    soup_f = np.concatenate([soup_f, soup_f[:2][:, [1, 2, 0]]])    # two duplicated faces (rotated index order)
+    m = SimpleMesh(vertices=soup_v, faces=soup_f)
+    m.merge_vertices()
+    assert m.vertices.shape == (8, 3)
+    m.update_faces(m.unique_faces())
+    assert m.faces.shape == (12, 3)
+    m.fix_normals()
+    assert m.volume == pytest.approx(1.9 ** 3, rel=1e-6)           # closed, consistently wound, outward: +volume of the 1.9 cube
+    two = SimpleMesh(vertices=np.concatenate([v, v + 3.0]), faces=np.concatenate([f[:, ::-1], f + len(v)]))
+    two.fix_normals()                                              # first component inverted as a whole, second one fine
+    assert two.volume == pytest.approx(2 * 1.9 ** 3, rel=1e-6)
