@@ -76,10 +76,12 @@ def collate_fn(batch, opt: Options):
     Item keys as in the reference datasets: ``cond`` [N,3], ``coords`` (mesh tokens, +3 offset), ``len``, ``num_faces``,
     ``azimuth``, ``path``.  Output: tokens [B,1+M+1] (BOS, body, EOS, pad), labels [B,C+1+M+1] (-100 on cond / BOS / pad),
     masks [B,C+1+M+1] bool, num_tokens = C+1+len+1.  A sequence longer than ``max_seq_length`` is truncated and gets no EOS
-    (reference :516-531); it is right-padded to the batch width (the reference's np.stack would fail on the ragged row).
+    (reference :516-531): a batch of only such rows is one column narrower (no EOS column), exactly as in the reference; in a
+    mixed batch the truncated rows are right-padded to the common width (the reference's np.stack would fail on the ragged rows).
     """
     max_len = min(max(item['len'] for item in batch), opt.max_seq_length)
-    B, Cn, W = len(batch), opt.num_cond_tokens, max_len + 2
+    any_full = any(item['len'] <= max_len for item in batch)
+    B, Cn, W = len(batch), opt.num_cond_tokens, max_len + 1 + int(any_full)
     tokens = np.full((B, W), opt.pad_token_id, dtype=np.int64)
     labels = np.full((B, Cn + W), -100, dtype=np.int64)
     masks = np.zeros((B, Cn + W), dtype=bool)

@@ -1,6 +1,6 @@
 """Generate golden vectors by EXECUTING THE REFERENCE (build container only; needs /root/reference).
 
-TEST INFRASTRUCTURE.  Run as a standalone process:  ``python oracle/gen_golden.py [--only tiny|arae|meto|meta]``
+TEST INFRASTRUCTURE.  Run as a standalone process:  ``python oracle/gen_golden.py [--only tiny|arae|meto|meta|provider]``
 
 The reference modules (``core.models.LMM``, ``core.transformer.*``) are imported from /root/reference
 with ``flash_attn`` masked (so ``core/transformer/attention.py:19-25`` picks its naive bmm path on CPU)
@@ -292,6 +292,52 @@ def gen_meta(synth):
     print('[gen] wrote options.json / quantize_num_faces.json', flush=True)
 
 
+def provider_items(rng, opt, lens):
+    """Synthetic dataset items with the reference's keys (provider.py:437-466): deterministic per call order."""
+    items = []
+    for i, n in enumerate(lens):
+        items.append(dict(cond=rng.uniform(-0.95, 0.95, (opt.point_num, 3)).astype(np.float32),
+                          coords=rng.randint(3, opt.discrete_bins + 3, size=n).astype(np.int64), len=int(n),
+                          num_faces=int(rng.randint(10, 9000)), azimuth=int(rng.randint(0, 360)), path=f'item{i}'))
+    return items
+
+
+def gen_provider_goldens(synth):
+    """The reference's own provider functions executed here: tokenize_mesh (naive and meto paths), detokenize_mesh (naive path),
+    collate_fn on un-truncated and on all-truncated batches (a mixed batch makes the reference's np.stack raise)."""
+    from core.provider import tokenize_mesh, detokenize_mesh, collate_fn
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    import meshes
+    opt = synth.tiny_options()
+    out = {}
+
+    class RefEnc:   # meto.Engine.encode surface over the compiled reference tokenizer (meto/meto/__init__.py:40-45)
+        def __init__(self, bins):
+            import _meto
+            self.impl = _meto.Engine_LR_ABSCO(bins, False)
+
+        def encode(self, vertices, faces):
+            t, o, f = self.impl.encode(vertices, faces)
+            return np.asarray(t), np.asarray(o), np.asarray(f)
+
+    for name in ('cube', 'torus', 'icosphere', 'random_soup'):
+        v, f = meshes.all_meshes()[name]
+        v = v.astype(np.float64)
+        out[f'tok_naive_{name}'] = np.asarray(tokenize_mesh(v, f, 512, tokenizer=None))
+        out[f'tok_meto_{name}'] = np.asarray(tokenize_mesh(v, f, 512, tokenizer=RefEnc(512)))
+        dv, df = detokenize_mesh(out[f'tok_naive_{name}'], 512, tokenizer=None)
+        out[f'detok_naive_v_{name}'] = np.asarray(dv, dtype=np.float64)
+        out[f'detok_naive_f_{name}'] = np.asarray(df, dtype=np.int64)
+    for tag, lens in (('plain', [40, 13, 27, 40]), ('trunc', [opt.max_seq_length + 5, opt.max_seq_length + 90])):
+        batch = provider_items(np.random.RandomState(5), opt, lens)
+        res = collate_fn(batch, opt)
+        for k in ('conds', 'num_faces', 'num_tokens', 'azimuths', 'tokens', 'labels', 'masks'):
+            out[f'collate_{tag}_{k}'] = res[k].numpy()
+        out[f'collate_{tag}_lens'] = np.asarray(lens)
+    np.savez_compressed(os.path.join(GOLD, 'provider.npz'), **out)
+    print('[gen] wrote provider.npz', flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--only', default='all')
@@ -303,6 +349,8 @@ def main():
         gen_meta(synth)
     if args.only in ('all', 'meto'):
         gen_meto_goldens()
+    if args.only in ('all', 'provider'):
+        gen_provider_goldens(synth)
     if args.only in ('all', 'tiny'):
         opt = synth.tiny_options()
         gen_model_goldens(synth, 'tiny', opt, steps=160, num_faces=1000, sample_steps=64, tf_len=40)
