@@ -37,10 +37,10 @@ SIGNATURES = {
     'er_kernel_launches': (c_i64, [c_vp]),
     'er_debug_phase_timeline': (C.c_int, [c_vp, c_i32, c_i32]),
     'er_debug_read_timeline': (C.c_int, [c_vp, C.POINTER(c_u64), c_i32]),
-    'er_meto_decode': (C.c_int, [c_i32, C.POINTER(c_i32), c_i64, C.POINTER(c_f32), C.POINTER(c_i32), C.POINTER(c_i32),
+    'er_meto_decode': (C.c_int, [c_i32, c_i32, C.POINTER(c_i32), c_i64, C.POINTER(c_f32), C.POINTER(c_i32), C.POINTER(c_i32),
                                  C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]),
-    'er_meto_encode': (C.c_int, [c_i32, C.POINTER(c_f32), c_i64, C.POINTER(c_i32), c_i64, C.POINTER(c_i32), C.POINTER(c_i32),
-                                 C.POINTER(c_i32), C.POINTER(c_i64)]),
+    'er_meto_encode': (C.c_int, [c_i32, c_i32, C.POINTER(c_f32), c_i64, C.POINTER(c_i32), c_i64, C.POINTER(c_i32), c_i64,
+                                 C.POINTER(c_i32), C.POINTER(c_i32), c_i64, C.POINTER(c_i64), C.POINTER(c_i64)]),
 }
 
 _lib = None

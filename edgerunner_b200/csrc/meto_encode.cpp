@@ -1,8 +1,11 @@
-// Native meto tokenizer, LR_ABSCO backend, ENCODE side (mesh -> token stream) behind the C ABI.
+// Native meto tokenizer, LR_ABSCO and LR backends, ENCODE side (mesh -> token stream) behind the C ABI.
 //
 // Stands in for the pybind module `_meto` of the reference on the training-data side:
 //   Mesh::Mesh                 meto/include/meto/mesh.h:172-278     (quantise, half-edges, twins, boundary marks, ordering heuristics)
 //   Engine_LR_ABSCO::encode    meto/include/meto/engine_lr_absco.h:66-220 (EdgeBreaker-style traversal, L / R / BOM ops + absolute coords)
+//   Engine_LR::encode          meto/include/meto/engine_lr.h:54-169 (same traversal; coordinates as residuals of the parallelogram
+//                              prediction, out-of-range residual -> token -1; a split always goes right first; a pending sub-mesh is
+//                              opened even if its gate face was reached another way in the meantime, so faces can repeat)
 // Same token stream, face order and face types as the reference, bit for bit (tests/test_meto_cpu.py against goldens produced by the
 // compiled reference).  Differences by design: index-based flat arrays instead of a pointer graph (no per-element new/delete), the
 // traversal is ITERATIVE with an explicit stack of pending sub-meshes (the reference recurses once per face: stack depth = faces per
@@ -140,22 +143,32 @@ struct Builder {
 };
 
 struct Emitter {
-    int32_t *tok, *ord, *typ;
-    int64_t nt = 0, no = 0, ny = 0;
-    void coord(const QVert& v) { tok[nt++] = v.x + kNumOps; tok[nt++] = v.y + kNumOps; tok[nt++] = v.z + kNumOps; }
+    std::vector<int32_t> tok, ord, typ;
+    int bins; bool lr;
+    void abs3(const QVert& v) {                     // a vertex written as such: +3 (LR_ABSCO) or + bins + 3 (LR)
+        const int off = lr ? bins + kNumOps : kNumOps;
+        tok.push_back(v.x + off); tok.push_back(v.y + off); tok.push_back(v.z + off);
+    }
+    int32_t rel(int d) const { return (d < -bins || d >= bins) ? -1 : d + bins + kNumOps; }   // LR residual / delta token
+    void rel3(int dx, int dy, int dz) { tok.push_back(rel(dx)); tok.push_back(rel(dy)); tok.push_back(rel(dz)); }
 };
 
 }  // namespace
 
-extern "C" int er_meto_encode(int32_t discrete_bins, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces,
-                              int32_t* tokens, int32_t* face_order, int32_t* face_type, int64_t* n_tokens) {
-    if (discrete_bins <= 0 || n_verts < 0 || n_faces < 0 || (n_faces > 0 && (!verts || !faces)) || !tokens || !face_order || !face_type || !n_tokens)
+extern "C" int er_meto_encode(int32_t backend, int32_t discrete_bins, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces,
+                              int32_t* tokens, int64_t tokens_cap, int32_t* face_order, int32_t* face_type, int64_t faces_cap,
+                              int64_t* n_tokens, int64_t* n_faces_out) {
+    if ((backend != ER_METO_LR_ABSCO && backend != ER_METO_LR) || discrete_bins <= 0 || n_verts < 0 || n_faces < 0 ||
+        (n_faces > 0 && (!verts || !faces)) || !tokens || !face_order || !face_type || !n_tokens || !n_faces_out)
         return ER_ERR_INVALID;
     for (int64_t i = 0; i < 3 * n_faces; ++i)
         if (faces[i] < 0 || faces[i] >= n_verts) return ER_ERR_INVALID;   // the reference would read out of bounds
+    const bool lr = backend == ER_METO_LR;
     Builder m;
     m.build(verts, n_verts, faces, n_faces, discrete_bins);
-    Emitter out{tokens, face_order, face_type};
+    Emitter out;
+    out.bins = discrete_bins; out.lr = lr;
+    out.tok.reserve(10 * n_faces + 16); out.ord.reserve(n_faces + 16); out.typ.reserve(n_faces + 16);
     std::vector<int> pending;   // sub-meshes still to be opened (LIFO == the reference's recursion order)
     auto visited_face = [&](int h) { return m.F[m.H[h].face].mark != 0; };
     for (int64_t i = 0; i < n_faces; ++i) {
@@ -164,20 +177,32 @@ extern "C" int er_meto_encode(int32_t discrete_bins, const float* verts, int64_t
         while (!pending.empty()) {
             int c = pending.back();
             pending.pop_back();
-            if (visited_face(c)) continue;                    // hole / handle: the face was reached another way
-            // ---- open a sub-mesh at gate c: BOM + three absolute vertices ----
-            out.tok[out.nt++] = kBegin;
-            out.coord(m.V[m.H[c].v]); out.coord(m.V[m.H[c].s]); out.coord(m.V[m.H[c].e]);
+            if (!lr && visited_face(c)) continue;             // hole / handle: the face was reached another way (LR opens it regardless)
+            // ---- open a sub-mesh at gate c: BOM + three vertices (absolute; LR: first absolute, then two deltas) ----
+            out.tok.push_back(kBegin);
+            {
+                const QVert &qv = m.V[m.H[c].v], &qs = m.V[m.H[c].s], &qe = m.V[m.H[c].e];
+                out.abs3(qv);
+                if (lr) { out.rel3(qs.x - qv.x, qs.y - qv.y, qs.z - qv.z); out.rel3(qe.x - qs.x, qe.y - qs.y, qe.z - qs.z); }
+                else { out.abs3(qs); out.abs3(qe); }
+            }
             m.V[m.H[c].s].mark = 1; m.V[m.H[c].e].mark = 1;
             bool first = true;
             for (;;) {                                        // one iteration per face (the reference recurses here)
                 HalfEdge& hc = m.H[c];
                 m.F[hc.face].mark = 1;
-                out.ord[out.no++] = m.F[hc.face].index;
+                out.ord.push_back(m.F[hc.face].index);
                 if (!first) {
                     const HalfEdge& tw = m.H[hc.twin];       // the gate we came through
                     if (!(hc.s == tw.e && hc.e == tw.s)) m.flip(hc.face);   // inconsistent orientation: repair it
-                    out.coord(m.V[m.H[c].v]);
+                    const HalfEdge& hf = m.H[c];             // (after the flip)
+                    const QVert& qv = m.V[hf.v];
+                    if (lr) {                                // residual of the parallelogram prediction  twin.v' = next.v + prev.v - twin.v
+                        const QVert &qo = m.V[m.H[hf.twin].v], &qn = m.V[m.H[hf.next].v], &qp = m.V[m.H[hf.prev].v];
+                        out.rel3(qv.x + qo.x - qn.x - qp.x, qv.y + qo.y - qn.y - qp.y, qv.z + qo.z - qn.z - qp.z);
+                    } else {
+                        out.abs3(qv);
+                    }
                 }
                 first = false;
                 const HalfEdge& h = m.H[c];                   // (re-read: flip may have changed next / prev)
@@ -187,17 +212,21 @@ extern "C" int er_meto_encode(int32_t discrete_bins, const float* verts, int64_t
                 const bool right_seen = right_gate < 0 || visited_face(right_gate);
                 if (!tip_seen) {                              // "C": new vertex, continue to the right
                     m.V[h.v].mark = 1;
-                    out.tok[out.nt++] = kLeft; out.typ[out.ny++] = kLeft;
+                    out.tok.push_back(kLeft); out.typ.push_back(kLeft);
                     c = right_gate;
                 } else if (left_seen && right_seen) {         // "E": this strip ends
-                    out.typ[out.ny++] = kBegin;
+                    out.typ.push_back(kBegin);
                     break;
                 } else if (left_seen) {
-                    out.tok[out.nt++] = kLeft; out.typ[out.ny++] = kLeft;
+                    out.tok.push_back(kLeft); out.typ.push_back(kLeft);
                     c = right_gate;
                 } else if (right_seen) {
-                    out.tok[out.nt++] = kRight; out.typ[out.ny++] = kRight;
+                    out.tok.push_back(kRight); out.typ.push_back(kRight);
                     c = left_gate;
+                } else if (lr) {                              // "S" (LR): always to the right; the left side becomes a new sub-mesh later
+                    out.tok.push_back(kLeft); out.typ.push_back(kLeft);
+                    pending.push_back(left_gate);
+                    c = right_gate;
                 } else {                                      // "S": split — walk the shorter boundary loop first
                     int len_left = 0, len_right = 0;
                     for (int cur = right_gate;;) {
@@ -213,11 +242,11 @@ extern "C" int er_meto_encode(int32_t discrete_bins, const float* verts, int64_t
                         if (cur == left_gate) break;
                     }
                     if (len_left < len_right) {
-                        out.tok[out.nt++] = kLeft; out.typ[out.ny++] = kLeft;
+                        out.tok.push_back(kLeft); out.typ.push_back(kLeft);
                         pending.push_back(left_gate);
                         c = right_gate;
                     } else {
-                        out.tok[out.nt++] = kRight; out.typ[out.ny++] = kRight;
+                        out.tok.push_back(kRight); out.typ.push_back(kRight);
                         pending.push_back(right_gate);
                         c = left_gate;
                     }
@@ -225,6 +254,11 @@ extern "C" int er_meto_encode(int32_t discrete_bins, const float* verts, int64_t
             }
         }
     }
-    *n_tokens = out.nt;
+    *n_tokens = (int64_t)out.tok.size();
+    *n_faces_out = (int64_t)out.ord.size();
+    if ((int64_t)out.tok.size() > tokens_cap || (int64_t)out.ord.size() > faces_cap) return ER_ERR_CAPACITY;   // counts are valid: retry
+    std::copy(out.tok.begin(), out.tok.end(), tokens);
+    std::copy(out.ord.begin(), out.ord.end(), face_order);
+    std::copy(out.typ.begin(), out.typ.end(), face_type);
     return ER_OK;
 }

@@ -116,21 +116,29 @@ int64_t er_kernel_launches(const er_engine* e);          /* kernels launched by 
 int er_debug_phase_timeline(er_engine* e, int32_t token, int32_t cta);
 int er_debug_read_timeline(er_engine* e, uint64_t* out_host, int32_t n);
 
-/* meto tokenizer, LR_ABSCO backend (CPU, native): replaces the pybind module `_meto`
- * (meto/src/bindings.cpp:25-28 -> Engine_LR_ABSCO::decode, meto/include/meto/engine_lr_absco.h:223-295).
- * tokens are already -3 shifted (provider.py:115).  Capacities: verts >= 3*(n/4+3) floats*3, faces >= (n/4+3)*3,
- * face_type >= n/4+3.  Counts are returned through n_verts/n_faces/n_types. */
-int er_meto_decode(int32_t discrete_bins, const int32_t* tokens, int64_t n, float* verts, int32_t* faces, int32_t* face_type,
-                   int64_t* n_verts, int64_t* n_faces, int64_t* n_types);
+/* meto tokenizer backends of the reference's pybind module `_meto` (meto/src/bindings.cpp:11-28; CLERS is not reachable from
+ * core.options.Options and is not provided) */
+#define ER_METO_LR_ABSCO 0   /* Engine_LR_ABSCO: absolute coordinates, vocabulary bins + 3 (the ArAE / DiT presets) */
+#define ER_METO_LR 1         /* Engine_LR: parallelogram residuals, vocabulary 2 * bins + 3 (Options.meto_backend = 'LR') */
 
-/* meto tokenizer, LR_ABSCO backend, ENCODE side (CPU, native): replaces `_meto.Engine_LR_ABSCO.encode`
- * (meto/src/bindings.cpp:25-28 -> Mesh::Mesh, meto/include/meto/mesh.h:172-278, and Engine_LR_ABSCO::encode,
- * meto/include/meto/engine_lr_absco.h:66-220), the tokenizer call of the training-data path (core/provider.py:69-106).
- * verts [n_verts][3] float32 in [-1, 1], faces [n_faces][3] vertex indices.  Outputs (caller-allocated): tokens, capacity
- * >= 10*n_faces, in the _meto alphabet (0 L, 1 R, 2 BOM, coords +3); face_order [n_faces] = input index of each face in
- * emission order; face_type [n_faces] (0 L, 1 R, 2 end-of-strip).  Returns ER_ERR_INVALID for out-of-range vertex indices. */
-int er_meto_encode(int32_t discrete_bins, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces,
-                   int32_t* tokens, int32_t* face_order, int32_t* face_type, int64_t* n_tokens);
+/* Detokenizer (CPU, native): replaces `_meto.Engine_{LR_ABSCO,LR}.decode`
+ * (meto/include/meto/engine_lr_absco.h:223-295, engine_lr.h:171-254).  tokens are already -3 shifted (provider.py:115).
+ * Capacities: verts >= 3*(n/4+3) floats*3, faces >= (n/4+3)*3, face_type >= n/4+3.  Counts are returned through
+ * n_verts/n_faces/n_types. */
+int er_meto_decode(int32_t backend, int32_t discrete_bins, const int32_t* tokens, int64_t n, float* verts, int32_t* faces,
+                   int32_t* face_type, int64_t* n_verts, int64_t* n_faces, int64_t* n_types);
+
+/* Tokenizer, ENCODE side (CPU, native): replaces `_meto.Engine_{LR_ABSCO,LR}.encode` (Mesh::Mesh, meto/include/meto/mesh.h:172-278;
+ * Engine_LR_ABSCO::encode, engine_lr_absco.h:66-220; Engine_LR::encode, engine_lr.h:54-169), the tokenizer call of the
+ * training-data path (core/provider.py:69-106).  verts [n_verts][3] float32 in [-1, 1], faces [n_faces][3] vertex indices.
+ * Outputs (caller-allocated): tokens [tokens_cap] in the _meto alphabet (0 L, 1 R, 2 BOM, coordinates from 3; LR marks an
+ * out-of-range residual with -1); face_order / face_type [faces_cap]: input index and type (0 L, 1 R, 2 end-of-strip) of each
+ * emitted face.  LR_ABSCO emits every face once (10 * n_faces tokens and n_faces entries always suffice); LR may emit faces more
+ * than once.  *n_tokens / *n_faces_out always receive the needed sizes; ER_ERR_CAPACITY if a capacity is too small (nothing is
+ * written then), ER_ERR_INVALID for out-of-range vertex indices. */
+int er_meto_encode(int32_t backend, int32_t discrete_bins, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces,
+                   int32_t* tokens, int64_t tokens_cap, int32_t* face_order, int32_t* face_type, int64_t faces_cap,
+                   int64_t* n_tokens, int64_t* n_faces_out);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,6 @@
 """``meto`` — mesh tokenizer package, drop-in for ``/root/reference/meto/meto/__init__.py``.
 
-``Engine(discrete_bins, verbose=False, backend='LR_ABSCO')`` keeps the reference's surface (:21-50):
+``Engine(discrete_bins, verbose=False, backend='LR_ABSCO' | 'LR')`` keeps the reference's surface (:21-50):
 ``encode(vertices [V,3], faces [F,3]) -> (tokens, face_order, face_type)``,
 ``decode(tokens[N] int) -> (vertices float64 [V,3], faces int [F,3], face_type)`` and the ``num_tokens`` /
 ``num_base_tokens`` / ``num_special_tokens`` attributes.  The implementation is the pair of native C-ABI functions
@@ -17,12 +17,13 @@ from edgerunner_b200 import _lib
 
 class Engine:
     def __init__(self, discrete_bins, verbose=False, backend: Literal['CLERS', 'LR', 'LR_ABSCO'] = 'LR_ABSCO'):
-        if backend != 'LR_ABSCO':
-            raise NotImplementedError(f"meto backend '{backend}': only LR_ABSCO (the ArAE/DiT preset backend) is on the B200 path")
+        if backend not in ('LR_ABSCO', 'LR'):
+            raise NotImplementedError(f"meto backend '{backend}': LR_ABSCO and LR (the two values of Options.meto_backend) are provided")
         self.discrete_bins = int(discrete_bins)
         self.verbose = verbose
         self.backend = backend
-        self.num_base_tokens = self.discrete_bins
+        self._backend_id = 0 if backend == 'LR_ABSCO' else 1          # ER_METO_LR_ABSCO / ER_METO_LR
+        self.num_base_tokens = self.discrete_bins * (1 if backend == 'LR_ABSCO' else 2)
         self.num_special_tokens = 3
         self.num_tokens = self.num_base_tokens + self.num_special_tokens
         self._lib = _lib.load()
@@ -36,7 +37,7 @@ class Engine:
         ftype = np.empty(cap, dtype=np.int32)
         nv, nf, nt = C.c_int64(), C.c_int64(), C.c_int64()
         p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-        _lib.check(self._lib.er_meto_decode(self.discrete_bins, p(tok, C.c_int32), n, p(verts, C.c_float), p(faces, C.c_int32),
+        _lib.check(self._lib.er_meto_decode(self._backend_id, self.discrete_bins, p(tok, C.c_int32), n, p(verts, C.c_float), p(faces, C.c_int32),
                                             p(ftype, C.c_int32), C.byref(nv), C.byref(nf), C.byref(nt)))
         # the reference returns np.asarray of Python floats: float64 holding float32-valued numbers
         return verts[:nv.value].astype(np.float64), faces[:nf.value].astype(np.int64), ftype[:nt.value].astype(np.int64)
@@ -49,14 +50,20 @@ class Engine:
         nv, nf = v.shape[0], f.shape[0]
         if nf and (f.min() < 0 or f.max() >= nv):
             raise ValueError('meto.encode: face index out of range')
-        tok = np.empty(max(10 * nf, 1), dtype=np.int32)
-        order = np.empty(max(nf, 1), dtype=np.int32)
-        ftype = np.empty(max(nf, 1), dtype=np.int32)
-        nt = C.c_int64()
         p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-        _lib.check(self._lib.er_meto_encode(self.discrete_bins, p(v, C.c_float), nv, p(f, C.c_int32), nf, p(tok, C.c_int32),
-                                            p(order, C.c_int32), p(ftype, C.c_int32), C.byref(nt)))
-        return tok[:nt.value].astype(np.int64), order[:nf].astype(np.int64), ftype[:nf].astype(np.int64)
+        tcap, fcap = max(10 * nf, 1), max(nf, 1)                       # always enough for LR_ABSCO; LR may repeat faces: retry once
+        for _ in range(2):
+            tok = np.empty(tcap, dtype=np.int32)
+            order = np.empty(fcap, dtype=np.int32)
+            ftype = np.empty(fcap, dtype=np.int32)
+            nt, ne = C.c_int64(), C.c_int64()
+            rc = self._lib.er_meto_encode(self._backend_id, self.discrete_bins, p(v, C.c_float), nv, p(f, C.c_int32), nf, p(tok, C.c_int32), tcap,
+                                          p(order, C.c_int32), p(ftype, C.c_int32), fcap, C.byref(nt), C.byref(ne))
+            if rc != -4:                                                # ER_ERR_CAPACITY: the needed sizes are in nt / ne
+                break
+            tcap, fcap = nt.value, ne.value
+        _lib.check(rc)
+        return tok[:nt.value].astype(np.int64), order[:ne.value].astype(np.int64), ftype[:ne.value].astype(np.int64)
 
 
 def normalize_mesh(vertices, bound=0.95):

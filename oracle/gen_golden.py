@@ -273,6 +273,43 @@ def gen_meto_goldens():
         out[f'stream{i}_dv'] = np.asarray(dv, dtype=np.float64).reshape(-1, 3)
         out[f'stream{i}_df'] = np.asarray(df, dtype=np.int32).reshape(-1, 3)
         out[f'stream{i}_dt'] = np.asarray(dt, dtype=np.int32)
+    # ---- LR backend (Options.meto_backend = 'LR'): encode + decode of the fixtures, encode of the stress meshes, malformed streams ----
+    lr_names, lr_enc_names = [], []
+    for name, (v, f) in fixture_meshes().items():
+        eng = _meto.Engine_LR(512, False)
+        tok, order, ftype = eng.encode(v.astype(np.float32).tolist(), f.astype(np.int32).tolist())
+        dv, df, dt = eng.decode(tok)
+        key = f'lr_{name}_512'
+        lr_names.append(key)
+        out[key + '_tokens'] = np.asarray(tok, dtype=np.int32)
+        out[key + '_order'] = np.asarray(order, dtype=np.int32)
+        out[key + '_ftype'] = np.asarray(ftype, dtype=np.int32)
+        out[key + '_dv'] = np.asarray(dv, dtype=np.float64).reshape(-1, 3)
+        out[key + '_df'] = np.asarray(df, dtype=np.int32).reshape(-1, 3)
+        out[key + '_dt'] = np.asarray(dt, dtype=np.int32)
+    for name, (v, f) in meshes.stress_meshes().items():
+        for bins in (8, 512):
+            tok, order, ftype = _meto.Engine_LR(bins, False).encode(v.astype(np.float32).tolist(), f.astype(np.int32).tolist())
+            key = f'lr_{name}_{bins}'
+            lr_enc_names.append(key)
+            out[key + '_tokens'] = np.asarray(tok, dtype=np.int16)
+            out[key + '_order'] = np.asarray(order, dtype=np.int16)
+            out[key + '_ftype'] = np.asarray(ftype, dtype=np.int8)
+    rng = np.random.RandomState(12)
+    lr_streams = [np.zeros(0, np.int64), grammar_tokens(rng, 2001, 1024) - 3, grammar_tokens(rng, 10, 1024) - 3, grammar_tokens(rng, 11, 1024) - 3]
+    bad = grammar_tokens(rng, 120, 1024) - 3
+    bad[40] = 900; bad[77] = -1
+    lr_streams.append(bad)
+    eng = _meto.Engine_LR(512, False)
+    for i, s in enumerate(lr_streams):
+        dv, df, dt = eng.decode([int(x) for x in s])
+        out[f'lr_stream{i}_tokens'] = s.astype(np.int32)
+        out[f'lr_stream{i}_dv'] = np.asarray(dv, dtype=np.float64).reshape(-1, 3)
+        out[f'lr_stream{i}_df'] = np.asarray(df, dtype=np.int32).reshape(-1, 3)
+        out[f'lr_stream{i}_dt'] = np.asarray(dt, dtype=np.int32)
+    out['lr_names'] = np.asarray(lr_names)
+    out['lr_enc_names'] = np.asarray(lr_enc_names)
+    out['n_lr_streams'] = np.asarray(len(lr_streams))
     out['names'] = np.asarray(names)
     out['n_streams'] = np.asarray(len(streams))
     np.savez_compressed(os.path.join(GOLD, 'meto.npz'), **out)

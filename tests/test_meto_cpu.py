@@ -132,11 +132,19 @@ def test_encode_live_against_compiled_reference():
             f = np.concatenate([f, rng.randint(0, len(v), (7, 3)).astype(np.int32)])
         v = np.clip(v, -1, 1)
         bins = int(rng.choice([4, 32, 256, 512, 1024]))
-        rt, ro, rf = _meto.Engine_LR_ABSCO(bins, False).encode(v.tolist(), f.tolist())
-        tok, order, ftype = Engine(bins).encode(v, f)
-        np.testing.assert_array_equal(tok, rt, err_msg=f'iter {it}')
-        np.testing.assert_array_equal(order, ro, err_msg=f'iter {it}')
-        np.testing.assert_array_equal(ftype, rf, err_msg=f'iter {it}')
+        for backend, ref_cls in (('LR_ABSCO', _meto.Engine_LR_ABSCO), ('LR', _meto.Engine_LR)):
+            ref = ref_cls(bins, False)
+            rt, ro, rf = ref.encode(v.tolist(), f.tolist())
+            eng = Engine(bins, backend=backend)
+            tok, order, ftype = eng.encode(v, f)
+            np.testing.assert_array_equal(tok, rt, err_msg=f'{backend} iter {it}')
+            np.testing.assert_array_equal(order, ro, err_msg=f'{backend} iter {it}')
+            np.testing.assert_array_equal(ftype, rf, err_msg=f'{backend} iter {it}')
+            dv, df, dt = ref.decode(rt)
+            mv, mf, mt = eng.decode(tok)
+            np.testing.assert_array_equal(mv, np.asarray(dv, dtype=np.float64).reshape(-1, 3), err_msg=f'{backend} iter {it}')
+            np.testing.assert_array_equal(mf, np.asarray(df).reshape(-1, 3), err_msg=f'{backend} iter {it}')
+            np.testing.assert_array_equal(mt, dt, err_msg=f'{backend} iter {it}')
 
 
 def test_encode_decode_round_trip():
@@ -205,3 +213,44 @@ def test_simple_mesh_clean_up():
     two = SimpleMesh(vertices=np.concatenate([v, v + 3.0]), faces=np.concatenate([f[:, ::-1], f + len(v)]))
     two.fix_normals()                                              # first component inverted as a whole, second one fine
     assert two.volume == pytest.approx(2 * 1.9 ** 3, rel=1e-6)
+
+
+# ------------------------------------------------------------------ LR backend (Options.meto_backend = 'LR') ------------------------------------------------------------------
+
+def test_lr_backend_matches_reference_goldens(golden_dir):
+    """Engine(backend='LR'): encode + decode against the compiled reference's Engine_LR (residual coordinates, repeated faces, -1 markers)."""
+    import meshes
+    from meto import Engine
+    g = np.load(os.path.join(golden_dir, 'meto.npz'))
+    fixtures = dict(meshes.all_meshes())
+    fixtures.update(meshes.stress_meshes())
+    n = repeated = 0
+    for key in list(g['lr_names']) + list(g['lr_enc_names']):
+        key = str(key)
+        name, bins = key[3:].rsplit('_', 1)
+        v, f = fixtures[name]
+        eng = Engine(int(bins), backend='LR')
+        assert eng.num_tokens == 2 * int(bins) + 3
+        tok, order, ftype = eng.encode(v, f)
+        np.testing.assert_array_equal(tok, g[key + '_tokens'], err_msg=key)
+        np.testing.assert_array_equal(order, g[key + '_order'], err_msg=key)
+        np.testing.assert_array_equal(ftype, g[key + '_ftype'], err_msg=key)
+        repeated += len(order) != len(f)
+        if key + '_dv' in g:
+            dv, df, dt = eng.decode(tok)
+            np.testing.assert_array_equal(dv, g[key + '_dv'].reshape(-1, 3), err_msg=key)
+            np.testing.assert_array_equal(df, g[key + '_df'].reshape(-1, 3), err_msg=key)
+            np.testing.assert_array_equal(dt, g[key + '_dt'], err_msg=key)
+        n += 1
+    assert n >= 60 and repeated > 0          # the capacity-retry path of er_meto_encode is exercised
+    for i in range(int(g['n_lr_streams'])):
+        dv, df, dt = Engine(512, backend='LR').decode(g[f'lr_stream{i}_tokens'])
+        np.testing.assert_array_equal(dv, g[f'lr_stream{i}_dv'].reshape(-1, 3), err_msg=f'stream {i}')
+        np.testing.assert_array_equal(df, g[f'lr_stream{i}_df'].reshape(-1, 3), err_msg=f'stream {i}')
+        np.testing.assert_array_equal(dt, g[f'lr_stream{i}_dt'], err_msg=f'stream {i}')
+
+
+def test_unknown_backend_is_refused():
+    from meto import Engine
+    with pytest.raises(NotImplementedError):
+        Engine(512, backend='CLERS')
