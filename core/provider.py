@@ -45,9 +45,12 @@ def save_mesh(tokens, opt: Options, path=None, tokenizer=None, clean=True, verbo
         print(f'[INFO] vertices: {vertices.shape[0]}, faces: {faces.shape[0]}')
     mesh = _Mesh(vertices=vertices, faces=faces)
     if clean:
-        mesh.merge_vertices()
-        mesh.update_faces(mesh.unique_faces())
-        mesh.fix_normals()
+        if hasattr(mesh, 'clean_up'):       # SimpleMesh: the same three steps in one native call (er_mesh_clean)
+            mesh.clean_up()
+        else:
+            mesh.merge_vertices()
+            mesh.update_faces(mesh.unique_faces())
+            mesh.fix_normals()
         if verbose:
             print(f'[INFO] cleaned vertices: {mesh.vertices.shape[0]}, faces: {mesh.faces.shape[0]}')
     if path is None:

@@ -41,6 +41,8 @@ SIGNATURES = {
                                  C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]),
     'er_meto_encode': (C.c_int, [c_i32, c_i32, C.POINTER(c_f32), c_i64, C.POINTER(c_i32), c_i64, C.POINTER(c_i32), c_i64,
                                  C.POINTER(c_i32), C.POINTER(c_i32), c_i64, C.POINTER(c_i64), C.POINTER(c_i64)]),
+    'er_mesh_clean': (C.c_int, [C.POINTER(C.c_double), c_i64, C.POINTER(c_i32), c_i64, c_i32, C.POINTER(C.c_double), C.POINTER(c_i32),
+                                C.POINTER(c_i64), C.POINTER(c_i64)]),
 }
 
 _lib = None

@@ -15,12 +15,30 @@ class SimpleMesh:
         self.faces = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
 
     def merge_vertices(self):
+        """Vertices equal to 8 decimals become one; the survivors keep the order of their first occurrence (as in trimesh)."""
         if len(self.vertices) == 0:
             return
-        uniq, inv = np.unique(np.round(self.vertices, 8), axis=0, return_inverse=True)
-        self.vertices, self.faces = uniq, inv.reshape(-1)[self.faces]
+        _, first, inv = np.unique(np.round(self.vertices, 8), axis=0, return_index=True, return_inverse=True)
+        rank = np.argsort(np.argsort(first))                 # unique id (sorted order) -> position by first occurrence
+        self.vertices = self.vertices[np.sort(first)]
+        self.faces = rank[inv.reshape(-1)][self.faces]
+
+    def clean_up(self):
+        """merge_vertices + update_faces(unique_faces()) + fix_normals in one native call (``er_mesh_clean``)."""
+        import ctypes as C
+        from edgerunner_b200 import _lib
+        lib = _lib.load()
+        v = np.ascontiguousarray(self.vertices, dtype=np.float64)
+        f = np.ascontiguousarray(self.faces, dtype=np.int32)
+        vo, fo = np.empty_like(v), np.empty_like(f)
+        nv, nf = C.c_int64(), C.c_int64()
+        P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        _lib.check(lib.er_mesh_clean(P(v, C.c_double), len(v), P(f, C.c_int32), len(f), 8, P(vo, C.c_double), P(fo, C.c_int32), C.byref(nv), C.byref(nf)))
+        self.vertices, self.faces = vo[:nv.value].copy(), fo[:nf.value].astype(np.int64)
 
     def unique_faces(self):
+        if len(self.faces) == 0:
+            return np.zeros(0, dtype=bool)
         key = np.sort(self.faces, axis=1)
         _, first = np.unique(key, axis=0, return_index=True)
         mask = np.zeros(len(self.faces), dtype=bool)

@@ -140,6 +140,14 @@ int er_meto_encode(int32_t backend, int32_t discrete_bins, const float* verts, i
                    int32_t* tokens, int64_t tokens_cap, int32_t* face_order, int32_t* face_type, int64_t faces_cap,
                    int64_t* n_tokens, int64_t* n_faces_out);
 
+/* Mesh clean-up at the tail of save_mesh (core/provider.py:55-58; the reference calls third-party trimesh: merge_vertices,
+ * update_faces(unique_faces()), fix_normals).  CPU, native: merge vertices equal after rounding to `digits` decimals (first
+ * occurrence order), drop faces whose vertex set already occurred, make the winding consistent per edge-connected component and
+ * outward (non-negative signed volume).  verts [n_verts][3] float64, faces [n_faces][3]; outputs caller-allocated with the input
+ * sizes; the new counts are returned through n_verts_out / n_faces_out. */
+int er_mesh_clean(const double* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces, int32_t digits,
+                  double* verts_out, int32_t* faces_out, int64_t* n_verts_out, int64_t* n_faces_out);
+
 #ifdef __cplusplus
 }
 #endif

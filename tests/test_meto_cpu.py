@@ -254,3 +254,33 @@ def test_unknown_backend_is_refused():
     from meto import Engine
     with pytest.raises(NotImplementedError):
         Engine(512, backend='CLERS')
+
+
+def test_native_mesh_clean_matches_python_steps():
+    """er_mesh_clean (one native call) == SimpleMesh.merge_vertices + update_faces(unique_faces()) + fix_normals, on triangle soups with
+    duplicated vertices / faces and random flips; outward orientation gives the positive volume of the closed fixtures."""
+    import meshes
+    from edgerunner_b200.mesh import SimpleMesh
+    rng = np.random.RandomState(4)
+    for name in ('cube', 'tetrahedron', 'torus', 'icosphere', 'icosphere2', 'two_components', 'grid', 'annulus'):
+        v, f = meshes.all_meshes()[name]
+        soup_v = v[f].reshape(-1, 3).astype(np.float64)          # like the detokenizer's output: three fresh vertices per face
+        soup_f = np.arange(len(soup_v)).reshape(-1, 3)
+        flip = rng.rand(len(soup_f)) < 0.4
+        soup_f[flip] = soup_f[flip][:, ::-1]
+        soup_f = np.concatenate([soup_f, soup_f[:3][:, [2, 0, 1]]])
+        a = SimpleMesh(vertices=soup_v, faces=soup_f)
+        a.merge_vertices(); a.update_faces(a.unique_faces()); a.fix_normals()
+        b = SimpleMesh(vertices=soup_v, faces=soup_f)
+        b.clean_up()
+        np.testing.assert_array_equal(a.vertices, b.vertices, err_msg=name)
+        assert len(b.faces) == len(f), name
+        if name in ('cube', 'tetrahedron', 'torus', 'icosphere', 'icosphere2', 'two_components'):   # closed: orientation is unique
+            np.testing.assert_array_equal(a.faces, b.faces, err_msg=name)
+            assert b.volume > 0
+        else:                                                                       # open patch: consistent up to a global flip
+            same = (a.faces == b.faces).all(axis=1)
+            assert same.all() or (a.faces[:, ::-1] == b.faces).all(), name
+    e = SimpleMesh(vertices=np.zeros((0, 3)), faces=np.zeros((0, 3), dtype=np.int64))
+    e.clean_up()
+    assert e.vertices.shape == (0, 3) and e.faces.shape == (0, 3)
