@@ -29,6 +29,7 @@
 // dtype ledger (mirrored by oracle/er_oracle.py mode='ledger'): fp16 weights and KV,
 // fp32 accumulation everywhere, activations rounded to fp16 exactly where model.half()+autocast(fp16) does.
 #include "decode_kernel.h"
+#include "decode_partition.h"
 
 #include "common.cuh"
 
@@ -309,38 +310,9 @@ __device__ __forceinline__ void prof_all(const DecodeParams& p, int k, bool on) 
 }
 
 // ---- work partition (identical on the producer and the consumer side) ------------------------------------------------------------
-struct RowRange { int r0, r1; };
-__device__ __forceinline__ RowRange cta_rows(int R) {     // R * gridDim.x < 2^31 (checked by the host): 32-bit arithmetic, no division call
-    RowRange rr;
-    const unsigned b = blockIdx.x, g = gridDim.x;
-#ifdef ER_ODD_ROWS
-    if (true) {
-#else
-    if (R & 1) {
-#endif
-        rr.r0 = (int)(((unsigned)R * b) / g);
-        rr.r1 = (int)(((unsigned)R * (b + 1)) / g);
-    } else {   // whole fp16 PAIRS of rows per CTA: one 8-byte exchange word never has two writers
-        rr.r0 = 2 * (int)(((unsigned)(R >> 1) * b) / g);
-        rr.r1 = 2 * (int)(((unsigned)(R >> 1) * (b + 1)) / g);
-    }
-    return rr;
-}
-struct AttnRange { int h, b0, b1, k0, k1, is_new; };   // old keys [k0,k1) in K blocks [b0,b1); is_new: this CTA also owns key L
+__device__ __forceinline__ RowRange cta_rows(int R) { return cta_rows_of(R, blockIdx.x, gridDim.x); }
 __device__ __forceinline__ bool attn_range(int H, int S, int split_handicap, int L, AttnRange& a) {
-    if ((int)blockIdx.x >= H * S) return false;
-    a.h = blockIdx.x / S;
-    const int s = blockIdx.x % S;
-    const int nblk = (L + 31) >> 5;                  // blocks holding old keys 0..L-1
-    // the last split also owns the new key and (being the last to finish) usually merges the head: that fixed work is worth
-    // about split_handicap (<= 7, see engine.cu sc_len) blocks of streaming, so it gets that many fewer blocks
-    const int bps = (nblk + split_handicap + S - 1) / S;
-    a.b0 = min(s * bps, nblk);
-    a.b1 = min(a.b0 + bps, nblk);
-    a.k0 = a.b0 * 32;
-    a.k1 = max(a.k0, min(a.b1 * 32, L));             // empty splits: b0 == b1 == nblk, k0 may exceed L
-    a.is_new = (s == S - 1);
-    return true;
+    return attn_range_of(H, S, split_handicap, L, blockIdx.x, a);
 }
 
 struct Ring {          // passed by value (registers): shared-space addresses of the stage data and the mbarrier arrays

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "decode_kernel.h"
+#include "decode_partition.h"
 #include "kernels.h"
 
 static thread_local char g_err[512] = "";
@@ -235,7 +236,7 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     // experiment switch: 1 = flagged-word exchange instead of grid barriers inside a layer (measured slower: same number of
     // dependent L2 round trips per exchange once polling is throttled, plus register pressure)
     if (const char* v = getenv("ER_DECODE_LL")) e->use_ll = atoi(v) != 0;
-    e->sc_len = std::max(((e->nkb + 7 + e->S - 1) / e->S) * 32 + 64, (V + 3) / 4 * 4);   // 7 = largest split handicap er_decode accepts
+    e->sc_len = er::score_scratch_len(e->nkb, e->S, V);
     {
         er::DecodeParams p{}; p.C = C; p.F = F; p.H = H; p.V = V; p.S = e->S; p.sc_len = e->sc_len;
         int smem_max = 0;

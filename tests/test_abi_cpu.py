@@ -65,3 +65,14 @@ def test_no_product_import_of_oracle():
                     if re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M) or re.search(r'#include.*oracle', txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_decode_partition_invariants(tmp_path):
+    """The decode kernel's work partition (csrc/decode_partition.h, shared by producer, consumers and the host) checked natively:
+    row ranges tile [0, R) on pair boundaries; the KV splits of a head tile its keys / blocks exactly once for every cache length;
+    one split owns the new key; the score scratch is large enough for every split handicap er_decode accepts."""
+    import subprocess
+    exe = str(tmp_path / 'partition_check')
+    subprocess.check_call(['g++', '-std=c++17', '-O2', '-o', exe, os.path.join(REPO, 'tests', 'partition_check.cpp')])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith('ok '), out.stdout[-500:]
