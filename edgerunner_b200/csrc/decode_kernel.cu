@@ -49,6 +49,8 @@ constexpr int kStageBytes = 24704;                // 8 padded weight units of (1
 constexpr int kKVChunk = 24576;                   // bytes per stage of the K / V jobs (4 K blocks = 128 V rows)
 constexpr int kMaxStages = 8;
 constexpr int kKBlockBytes = HV * 32 * 16;        // 6144: one 32-key block of the blocked K cache
+constexpr int kHoStride = HD + 8;                 // fused phases: fp16 per (head, row) unit of the per-head out_proj copy (208 B)
+constexpr int kHoUnitsPerStage = kStageBytes / (kHoStride * 2);   // 118
 constexpr int kMaxUnits = 64 * kUnitDiv;          // weight units a CTA owns in one phase
 constexpr int kPartStride = kMaxUnits + 1;        // lane-partial matrix [32][kPartStride] (odd stride: conflict-free both ways)
 
@@ -351,10 +353,13 @@ __device__ __forceinline__ bool produce(const Ring r, Cursor& cur, const void* b
 // Run-ahead bound: weights never change, but the K block / V rows that hold key L-1 were written by the PREVIOUS token's P1.  The ring
 // alone does not bound the producer by tokens (a CTA that owns few rows of a small model needs fewer stages per token than the ring has
 // slots), so K/V copies of pass j are only issued once the consumers have left the token-end grid barrier of pass j-1 (`tok_done`).
+template <bool FUSE>
 __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, volatile int* stop, volatile uint32_t* cons_it, volatile int* tok_done) {
     const int C = p.C, F = p.F, H = p.H, S = p.S, V = p.V, layers = p.layers, ustride = p.ustride, handicap = p.split_handicap;
     const int nkb = p.nkb, Lmax = p.Lmax;
     const __half* const wdec = p.wdec;
+    const __half* const wfuse = FUSE ? p.wfuse : nullptr;
+    const size_t fuse_layer = FUSE ? (size_t)H * C * kHoStride + (size_t)F * ustride : 0;   // fp16 per layer of the fused-phase weight copies
     const __half* const kc = p.kc;
     const __half* const vc = p.vc;
     int t = p.st->t, L = p.st->L;
@@ -385,10 +390,17 @@ __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, 
                 ok = produce(r, cur, kbase, (size_t)(a.b1 - a.b0) * kKBlockBytes, kKVChunk, stop);
                 const __half* vbase = vc + (((size_t)layer * H + a.h) * Lmax + a.k0) * HD;
                 if (ok) ok = produce(r, cur, vbase, (size_t)(a.k1 - a.k0) * HD * 2, kKVChunk, stop);
+                if (FUSE && ok) {   // this split's rows of the head's out_proj columns
+                    const RowRange rs = cta_rows_of(C, blockIdx.x % (unsigned)S, (unsigned)S);
+                    ok = produce(r, cur, wfuse + (size_t)layer * fuse_layer + ((size_t)a.h * C + rs.r0) * kHoStride, (size_t)(rs.r1 - rs.r0) * kHoStride * 2,
+                                 (uint32_t)(kHoUnitsPerStage * kHoStride * 2), stop);
+                }
             }
-            if (ok) ok = produce(r, cur, wl + ((size_t)3 * C + rc.r0) * ustride, (size_t)(rc.r1 - rc.r0) * ub, wchunk, stop);
+            if (!FUSE && ok) ok = produce(r, cur, wl + ((size_t)3 * C + rc.r0) * ustride, (size_t)(rc.r1 - rc.r0) * ub, wchunk, stop);
             if (ok) ok = produce(r, cur, wl + ((size_t)4 * C + rf.r0) * ustride, (size_t)(rf.r1 - rf.r0) * ub, wchunk, stop);
-            if (ok) ok = produce(r, cur, wl + ((size_t)4 * C + F + (size_t)rc.r0 * nuf) * ustride, (size_t)(rc.r1 - rc.r0) * nuf * ub, wchunk, stop);
+            if (!FUSE && ok) ok = produce(r, cur, wl + ((size_t)4 * C + F + (size_t)rc.r0 * nuf) * ustride, (size_t)(rc.r1 - rc.r0) * nuf * ub, wchunk, stop);
+            if (FUSE && ok)     // the fc2 columns matching this CTA's fc1 rows (one transposed unit per column)
+                ok = produce(r, cur, wfuse + (size_t)layer * fuse_layer + (size_t)H * C * kHoStride + (size_t)rf.r0 * ustride, (size_t)(rf.r1 - rf.r0) * ub, wchunk, stop);
         }
         if (ok) ok = produce(r, cur, wdec + ((size_t)layers * UL + rv.r0) * ustride, (size_t)(rv.r1 - rv.r0) * ub, wchunk, stop);
     }
@@ -562,6 +574,29 @@ __device__ __forceinline__ float reduce_rows(uint32_t part_s, int n_units, int n
     return s;
 }
 
+// ---- fused phases (experimental, FUSE = true): K-split GEMVs reduced in L2 instead of exchanged -------------------------------------------
+// Two of the five exchanges of a layer exist only because a GEMV's input is spread over all CTAs:
+//   * out_proj needs the whole attention vector.  Its K dimension is the concatenation of the heads, so the S CTAs of head h (which
+//     hold that head's output after a 9-CTA flagged-word merge) multiply it by the matching 96 columns of Wo, each for ~C/S output
+//     rows, and add the fp32 partial rows into a fixed-point accumulator (16 addends per row);
+//   * fc2 needs the whole fc1 output.  A CTA multiplies ITS OWN 40-42 fc1 outputs by the matching columns of W2 (stored transposed,
+//     one unit per column) and adds the 1536 partial sums into a second accumulator (148 addends per element).
+// The accumulators are u64 fixed point (2^-40): integer addition is associative, so the result does not depend on arrival order
+// and runs stay bit-reproducible.  Measured beforehand (scripts/microbench/atomic_reduce.cu): +1.5 us on the barrier that follows
+// instead of a 3 us exchange.  Each accumulator has two copies used by alternating layers; the copy a layer has finished with is
+// zeroed, slice by slice, after the next layer's first barrier.
+constexpr float kFixScale = 1099511627776.0f;      // 2^40
+constexpr float kFixInv = 1.0f / 1099511627776.0f;
+__device__ __forceinline__ void fix_add(unsigned long long* acc, float v) {
+    const long long q = __float2ll_rn(v * kFixScale);            // exact: power-of-two scaling of a 24-bit significand
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc), "l"(q) : "memory");
+}
+__device__ __forceinline__ float fix_get(const unsigned long long* acc) {
+    long long q;
+    asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(q) : "l"(acc));
+    return __ll2float_rn(q) * kFixInv;
+}
+
 // ---- fused residual + LayerNorm --------------------------------------------------------------------------------------------------------------
 // x = LayerNorm(xres + y) in place (fp32 statistics, eps 1e-5, fp16 affine params), plus the fp16 copy used as the next GEMV
 // input.  y is the fp16 phase output other CTAs just published (read at L2).  Thread t < C/8 owns elements 8t..8t+7;
@@ -585,7 +620,8 @@ __device__ __forceinline__ void unpack8(const uint4 u, float* f) {
     t = h2f2(u.w); f[6] = t.x; f[7] = t.y;
 }
 __device__ __forceinline__ void residual_layer_norm(uint32_t xres_s, uint32_t x16_s, const __half* y, const unsigned long long* yll, uint32_t flag,
-                                                 int rounds, const unsigned* hint, unsigned target, bool round_first, const LnParams lp, int C, float inv_c, float* red) {
+                                                 int rounds, const unsigned* hint, unsigned target, bool round_first, const LnParams lp, int C, float inv_c, float* red,
+                                                 const unsigned long long* yacc = nullptr, const __half* ybias = nullptr) {
     const int t = threadIdx.x;
     const bool act = t < (C >> 3);
     float v[8];
@@ -595,7 +631,12 @@ __device__ __forceinline__ void residual_layer_norm(uint32_t xres_s, uint32_t x1
     if (yll) ll_poll2<2>(w, act ? 3u : 0u, flag, rounds, [&](int j) { return yll + 4 * t + 2 * j; });
     if (act) {
         float yv[8];
-        if (yll) {
+        if (yacc) {                       // fused phases: y = fp16(sum of the K-split partials + bias), read from the fixed-point accumulator
+            float bv[8];
+            unpack8(*reinterpret_cast<const uint4*>(ybias + 8 * t), bv);
+#pragma unroll
+            for (int e = 0; e < 8; e++) yv[e] = round_f16(fix_get(yacc + 8 * t + e) + bv[e]);
+        } else if (yll) {
             unpack8(make_uint4(w[0], w[1], w[2], w[3]), yv);
         } else {
             unpack8(ldg_cg(reinterpret_cast<const uint4*>(y) + t), yv);
@@ -747,9 +788,10 @@ __device__ __forceinline__ float dot_k8(const uint4 kv, const float4 qa, const f
 #else
 #define ER_ATTN_INLINE __forceinline__
 #endif
-template <bool LL>
+template <bool LL, bool FUSE>
 __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ring r, Cursor cur, int layer, int L, float* qs,
-                                               float* sc, float* vred, float* red, int* s_flag, float* mg, uint32_t flag) {
+                                               float* sc, float* vred, float* red, int* s_flag, float* mg, uint32_t flag,
+                                               unsigned long long* acc_y1) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     AttnRange a;
     if (!attn_range(p.H, p.S, p.split_handicap, L, a)) return cur;
@@ -879,7 +921,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
         }
         cbar();
     }
-    if (warp >= 4 && !LL) return cur;                    // warps 0..3 publish; the others go on to the grid barrier
+    if (warp >= 4 && !LL && !FUSE) return cur;           // warps 0..3 publish; the others go on to the grid barrier
     // ---- publish the split partial ----
     unsigned long long* outl = p.ll_part + ((size_t)a.h * p.S + (blockIdx.x % p.S)) * 100;
     if (tid < HD) {
@@ -889,7 +931,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
             for (int g = 0; g < 2 * kConsumerWarps; g++) acc += vred[g * HD + tid];
             if (a.is_new) acc = fmaf(sc[new_slot] * red[32], __half2float(__ushort_as_half(vnew)), acc);   // new key: normalised by warp 0
         }
-        if (LL) ll_store(outl + tid, __float_as_uint(acc), flag); else outp[tid] = acc;
+        if (LL || FUSE) ll_store(outl + tid, __float_as_uint(acc), flag); else outp[tid] = acc;
     } else if (tid == HD) {
         float l = 0.f;
         if (nk > 0) {
@@ -897,8 +939,71 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
             if (a.is_new) l += sc[new_slot] * red[32];
         }
         const float mval = (nk > 0) ? M * rsqrtf((float)HD) : -INFINITY;        // max in softmax (scaled) units
-        if (LL) { ll_store(outl + HD, __float_as_uint(mval), flag); ll_store(outl + HD + 1, __float_as_uint(l), flag); }
+        if (LL || FUSE) { ll_store(outl + HD, __float_as_uint(mval), flag); ll_store(outl + HD + 1, __float_as_uint(l), flag); }
         else { outp[HD] = mval; outp[HD + 1] = l; }
+    }
+    if (FUSE) {
+        // ---- fused tail: every CTA of the head merges the S partials itself (flagged words, 9 pollers per head: no storm), then
+        // multiplies the head's output by ITS rows of the per-head out_proj copy and adds the partial rows to the y1 accumulator ----
+        const int S = p.S, s = blockIdx.x % S;
+        float* pm = mg;                                   // [S][100] merged-partial staging (aliases the GEMV partials)
+        cbar();
+        {
+            const unsigned long long* src = p.ll_part + (size_t)a.h * S * 100;
+            const int nw = S * (HD + 2);
+            uint32_t w[7];
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 7; j++) mask |= (tid + kConsumers * j < nw) ? (1u << j) : 0u;
+            const uint32_t want = mask;
+            ll_poll<7>(w, mask, flag, p.poll_rounds, [&](int j) { const int i = tid + kConsumers * j; return src + (i / (HD + 2)) * 100 + i % (HD + 2); });
+#pragma unroll
+            for (int j = 0; j < 7; j++)
+                if ((want >> j) & 1u) { const int i = tid + kConsumers * j; pm[(i / (HD + 2)) * 100 + i % (HD + 2)] = __uint_as_float(w[j]); }
+        }
+        cbar();
+        if (tid < HD) {                                   // same fold as the single-merger path, split order
+            float Mx = -INFINITY;
+            for (int q = 0; q < S; q++) Mx = fmaxf(Mx, pm[q * 100 + HD]);
+            float den = 0.f, num = 0.f;
+            for (int q = 0; q < S; q++) {
+                const float ms = pm[q * 100 + HD];
+                const float w8 = (ms == -INFINITY) ? 0.f : __expf(ms - Mx);
+                den = fmaf(w8, pm[q * 100 + HD + 1], den);
+                num = fmaf(w8, pm[q * 100 + tid], num);
+            }
+            qs[tid] = round_f16(num / den);               // the attention output is an fp16 tensor in the reference; q is no longer needed
+        }
+        cbar();
+        const RowRange rs = cta_rows_of(p.C, (unsigned)s, (unsigned)S);
+        const int n = rs.r1 - rs.r0;
+        const int u = tid >> 1, hf = tid & 1;             // two threads per output row, 48 of the head's 96 columns each
+        float xa[HD / 2];
+#pragma unroll
+        for (int e = 0; e < HD / 2; e++) xa[e] = qs[hf * (HD / 2) + e];
+        const int nch = (n + kHoUnitsPerStage - 1) / kHoUnitsPerStage;
+        for (int c = 0; c < nch; ++c, cur.advance(r.nstage)) {
+            mbar_wait(r.fullb(cur.stage), cur.parity);
+            const int here = min(kHoUnitsPerStage, n - c * kHoUnitsPerStage);
+            float part = 0.f;
+            if (u < here) {
+                const uint32_t wb = r.stage(cur.stage) + (uint32_t)u * (kHoStride * 2) + (uint32_t)hf * HD;
+#pragma unroll
+                for (int v = 0; v < HD / 16; v++) {
+                    const uint4 wv = lds128(wb + v * 16);
+                    float2 f;
+                    f = h2f2(wv.x); part = fmaf(f.x, xa[8 * v + 0], part); part = fmaf(f.y, xa[8 * v + 1], part);
+                    f = h2f2(wv.y); part = fmaf(f.x, xa[8 * v + 2], part); part = fmaf(f.y, xa[8 * v + 3], part);
+                    f = h2f2(wv.z); part = fmaf(f.x, xa[8 * v + 4], part); part = fmaf(f.y, xa[8 * v + 5], part);
+                    f = h2f2(wv.w); part = fmaf(f.x, xa[8 * v + 6], part); part = fmaf(f.y, xa[8 * v + 7], part);
+                }
+            }
+            const float tot = part + __shfl_xor_sync(0xffffffffu, part, 1);
+            if (hf == 0 && u < here) fix_add(acc_y1 + rs.r0 + c * kHoUnitsPerStage + u, tot);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
+        }
+        return cur;
     }
     if (LL) {
         // ---- merge, spread over the S CTAs of the head: split s owns output pairs [48 s / S, 48 (s+1) / S).  Thread (d, s') polls
@@ -980,7 +1085,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------------------
 // PROF: the timeline instrumentation is a separate instantiation so that the production kernel carries neither its registers nor its branches
-template <bool PROF, bool LL>
+template <bool PROF, bool LL, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __grid_constant__ DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C, F = p.F, H = p.H, V = p.V;
@@ -1020,7 +1125,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
 
     if (warp == kConsumerWarps) {
         // ===== producer warp: one elected lane streams this CTA's byte ranges through the ring =====
-        if (lane == 0) producer_loop(p, ring, &s_stop, &s_cons_it, &s_tok_done);
+        if (lane == 0) producer_loop<FUSE>(p, ring, &s_stop, &s_cons_it, &s_tok_done);
     } else {
         // ===== consumers =====
         unsigned epoch = 0;
@@ -1073,6 +1178,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 const int pb = 1 + 16 * layer;
                 const uint32_t flag = (uint32_t)(t * p.layers + layer + 1);   // exchange-word flag of this (token, layer)
                 const bool all_on = PROF && p.prof != nullptr && t == p.prof_token && layer == 5;
+                const int gl = iter * p.layers + layer;                          // layers run by this launch so far: parity picks the accumulator copy
+                unsigned long long* const acc_y1 = FUSE ? p.acc + (size_t)(gl & 1) * 2 * C : nullptr;
+                unsigned long long* const acc_y2 = FUSE ? acc_y1 + C : nullptr;
                 // ---------------- P1: q,k,v = x16 @ Wqkv^T + b ; KV append in place ----------------------------------------------
                 {
                     const RowRange rr{s_rows[0], s_rows[1]};
@@ -1107,15 +1215,20 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                         }
                     }
                     if (!LL) grid_wait(p.bar, epoch);
+                    if (FUSE) {   // everybody has finished with the other copy of the accumulators (previous layer): zero this CTA's slice of it
+                        unsigned long long* const other = p.acc + (size_t)((gl + 1) & 1) * 2 * C;
+                        const int z0 = s_rows[2], zn = s_rows[3] - s_rows[2];
+                        if (tid < zn) { other[z0 + tid] = 0ull; other[C + z0 + tid] = 0ull; }
+                    }
                 }
                 prof_stamp(p, pb + 3, prof_on); prof_all(p, 3, all_on);
                 // ---------------- P2: attention -----------------------------------------------------------------------------------------
-                cur = attention_phase<LL>(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag, part, flag);
+                cur = attention_phase<LL, FUSE>(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag, part, flag, acc_y1);
                 prof_stamp(p, pb + 4, prof_on); prof_all(p, 4, all_on);
-                if (!LL) grid_barrier(p.bar, epoch);
+                if (!LL && !FUSE) grid_barrier(p.bar, epoch);
                 prof_stamp(p, pb + 5, prof_on); prof_all(p, 5, all_on);
                 // ---------------- P3: out_proj on the merged attention output -----------------------------------------------------------
-                {
+                if (!FUSE) {
                     if (LL) {
                         ll_fetch(p.ll_attn, xin_s, C / 4, flag, p.poll_rounds, p.use_hint ? p.hint + 0 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2));
                     } else {
@@ -1142,7 +1255,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 prof_stamp(p, pb + 8, prof_on); prof_all(p, 8, all_on);
                 // ---------------- P4: x = LN1(x + y1) ; h1 = relu(fc1(x)) -----------------------------------------------------------
                 {
-                    residual_layer_norm(xres_s, xin_s, p.y1 + (size_t)xcopy * C, LL ? p.ll_y1 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 1 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), layer == 0, lp1, C, inv_c, red);
+                    residual_layer_norm(xres_s, xin_s, p.y1 + (size_t)xcopy * C, LL ? p.ll_y1 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 1 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), layer == 0, lp1, C, inv_c, red, acc_y1, FUSE ? p.bo + (size_t)layer * C : nullptr);
                     const RowRange rr{s_rows[4], s_rows[5]};
                     const int nr = rr.r1 - rr.r0;
                     prof_stamp(p, pb + 9, prof_on); prof_all(p, 9, all_on);
@@ -1153,15 +1266,46 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu1, nparts);
                         const __half hv = __float2half_rn(fmaxf(round_f16(sum + bias), 0.f));
-                        if (LL) ll_publish_rows(p.ll_h1, rr.r0, nu, nu1, hv, flag, p.use_hint ? p.hint + 2 * p.layers + layer : nullptr);
+                        if (FUSE) { if (own) vred[tid] = __half2float(hv); }                  // this CTA's slice of h1 stays on chip
+                        else if (LL) ll_publish_rows(p.ll_h1, rr.r0, nu, nu1, hv, flag, p.use_hint ? p.hint + 2 * p.layers + layer : nullptr);
                         else if (own) for (int c = 0; c < p.xrep; c++) p.h1[(size_t)c * F + rr.r0 + tid / nu1] = hv;
+                    }
+                    if (FUSE) {
+                        // fc2, K-split: y2 += W2[:, j] * h1[j] over this CTA's columns j (one transposed unit per column, `upstage` per stage);
+                        // thread t < C/8 owns output elements 8t .. 8t+7, then adds them to the fixed-point accumulator
+                        cbar();
+                        float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        const int ups = p.upstage, ubytes = p.ustride * 2;
+                        const int nch = (nr + ups - 1) / ups;
+                        for (int c = 0; c < nch; ++c, cur.advance(ring.nstage)) {
+                            mbar_wait(ring.fullb(cur.stage), cur.parity);
+                            const int here = min(ups, nr - c * ups);
+                            if (tid < C / 8) {
+                                const uint32_t wb = ring.stage(cur.stage) + (uint32_t)tid * 16;
+                                for (int u = 0; u < here; ++u) {
+                                    const uint4 wv = lds128(wb + (uint32_t)u * ubytes);
+                                    const float hj = vred[c * ups + u];
+                                    float2 f;
+                                    f = h2f2(wv.x); a8[0] = fmaf(hj, f.x, a8[0]); a8[1] = fmaf(hj, f.y, a8[1]);
+                                    f = h2f2(wv.y); a8[2] = fmaf(hj, f.x, a8[2]); a8[3] = fmaf(hj, f.y, a8[3]);
+                                    f = h2f2(wv.z); a8[4] = fmaf(hj, f.x, a8[4]); a8[5] = fmaf(hj, f.y, a8[5]);
+                                    f = h2f2(wv.w); a8[6] = fmaf(hj, f.x, a8[6]); a8[7] = fmaf(hj, f.y, a8[7]);
+                                }
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(ring.emptyb(cur.stage));
+                        }
+                        if (tid < C / 8) {
+#pragma unroll
+                            for (int e = 0; e < 8; e++) fix_add(acc_y2 + 8 * tid + e, a8[e]);
+                        }
                     }
                 }
                 prof_stamp(p, pb + 10, prof_on); prof_all(p, 10, all_on);
-                if (!LL) grid_barrier(p.bar, epoch);
+                if (!LL && !FUSE) grid_barrier(p.bar, epoch);
                 prof_stamp(p, pb + 11, prof_on); prof_all(p, 11, all_on);
                 // ---------------- P5: y2 = fc2(h1) -----------------------------------------------------------------------------------------
-                {
+                if (!FUSE) {
                     if (LL) {
                         ll_fetch(p.ll_h1, xin_s, F / 4, flag, p.poll_rounds, p.use_hint ? p.hint + 2 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(F / 2));
                     } else {
@@ -1185,7 +1329,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 if (!LL) grid_barrier(p.bar, epoch);
                 prof_stamp(p, pb + 14, prof_on); prof_all(p, 14, all_on);
                 // ---------------- x = LN2(x + y2) ------------------------------------------------------------------------------------------
-                residual_layer_norm(xres_s, xin_s, p.y2 + (size_t)xcopy * C, LL ? p.ll_y2 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 3 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), false, lp2, C, inv_c, red);
+                residual_layer_norm(xres_s, xin_s, p.y2 + (size_t)xcopy * C, LL ? p.ll_y2 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 3 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), false, lp2, C, inv_c, red, acc_y2, FUSE ? p.b2 + (size_t)layer * C : nullptr);
             }
             // ================= lm_head: logits_pre = fp16(x) @ W^T (fp32 value before the fp16 store) ================
             {
@@ -1227,12 +1371,13 @@ int er_decode_pick_stages(const er::DecodeParams& p, size_t smem_limit) {
 int er_decode_max_units() { return er::kMaxUnits; }
 int er_decode_stage_bytes() { return er::kStageBytes; }
 
-static const void* er_decode_kernel_fn(bool prof, bool ll) {
-    if (prof) return ll ? (const void*)er::decode_persistent_kernel<true, true> : (const void*)er::decode_persistent_kernel<true, false>;
-    return ll ? (const void*)er::decode_persistent_kernel<false, true> : (const void*)er::decode_persistent_kernel<false, false>;
+static const void* er_decode_kernel_fn(bool prof, bool ll, bool fuse) {
+    if (fuse) return prof ? (const void*)er::decode_persistent_kernel<true, false, true> : (const void*)er::decode_persistent_kernel<false, false, true>;
+    if (prof) return ll ? (const void*)er::decode_persistent_kernel<true, true, false> : (const void*)er::decode_persistent_kernel<true, false, false>;
+    return ll ? (const void*)er::decode_persistent_kernel<false, true, false> : (const void*)er::decode_persistent_kernel<false, false, false>;
 }
 cudaError_t er_decode_launch(const er::DecodeParams& p, int grid, size_t smem, cudaStream_t stream) {
-    const void* fn = er_decode_kernel_fn(p.prof != nullptr, p.use_ll != 0);
+    const void* fn = er_decode_kernel_fn(p.prof != nullptr, p.use_ll != 0, p.use_fuse != 0);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&p};
@@ -1244,8 +1389,8 @@ int er_decode_max_grid(size_t smem) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int ok = 1;
-    for (int v = 0; v < 4; ++v) {
-        const void* fn = er_decode_kernel_fn((v & 1) != 0, (v & 2) != 0);
+    for (int v = 0; v < 6; ++v) {
+        const void* fn = v < 4 ? er_decode_kernel_fn((v & 1) != 0, (v & 2) != 0, false) : er_decode_kernel_fn((v & 1) != 0, false, true);
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, er::kThreads, smem) != cudaSuccess || per < 1) ok = 0;
     }

@@ -54,6 +54,9 @@ struct DecodeParams {
     unsigned long long seed;
     // optional phase timeline: slot 0 = token start, then (end of phase, end of barrier) x 5 per layer, + lm_head pair
     unsigned long long *prof; int prof_token, prof_cta;
+    // fused phases (use_fuse, experimental): per layer [H][C][HD+8] per-head out_proj units, then [F][ustride] transposed fc2 units;
+    // acc: u64 fixed-point accumulators [2 copies][y1 | y2][C], zeroed by the host before each launch
+    const __half *wfuse; unsigned long long *acc; int use_fuse;
 };
 
 }  // namespace er

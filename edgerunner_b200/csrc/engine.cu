@@ -64,6 +64,24 @@ __global__ void pack_units_kernel(const __half* src, int rows, int K, int C, __h
     *reinterpret_cast<uint4*>(dst + unit * ustride + v * 8) = val;
 }
 
+// fused decode phases (experimental): out_proj re-cut per head, Wo[C][C] -> dst[h][row][0..HD) (+ pad to hs), one unit per (head, row)
+__global__ void pack_head_cols_kernel(const __half* wo, int C, int H, int HDim, __half* dst, int hs) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // one destination element each
+    const size_t total = (size_t)H * C * hs;
+    if (i >= total) return;
+    const int d = (int)(i % hs); const size_t hr = i / hs;
+    const int row = (int)(hr % C), h = (int)(hr / C);
+    dst[i] = d < HDim ? wo[(size_t)row * C + (size_t)h * HDim + d] : __float2half_rn(0.f);
+}
+// fc2 transposed: W2[C][F] -> dst[j][0..C) (+ pad to ustride), one unit per fc2 input column j
+__global__ void pack_transposed_kernel(const __half* w2, int C, int F, __half* dst, int ustride) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)F * ustride;
+    if (i >= total) return;
+    const int c = (int)(i % ustride); const size_t j = i / ustride;
+    dst[i] = c < C ? w2[(size_t)c * F + j] : __float2half_rn(0.f);
+}
+
 struct Slot { __half* dst; int rows, cols, dst_ld; };
 
 }  // namespace
@@ -87,7 +105,8 @@ struct er_engine {
     // cache + decode scratch
     __half *kc, *vc, *q16, *y1, *h1, *y2, *attn16;
     float *part, *logits, *cond32;
-    unsigned long long* ll = nullptr; size_t ll_words = 0; int use_ll = 0; unsigned* hint = nullptr;   // flagged exchange words of the decode kernel
+    unsigned long long* ll = nullptr; size_t ll_words = 0; int use_ll = 0; unsigned* hint = nullptr;
+    __half* wfuse = nullptr; unsigned long long* acc = nullptr; int use_fuse = 0;   // fused decode phases (experimental, ER_DECODE_FUSE=1)   // flagged exchange words of the decode kernel
     er::DecodeState* st;
     unsigned* bar;
     int32_t* ids_dev;
@@ -236,6 +255,13 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     // experiment switch: 1 = flagged-word exchange instead of grid barriers inside a layer (measured slower: same number of
     // dependent L2 round trips per exchange once polling is throttled, plus register pressure)
     if (const char* v = getenv("ER_DECODE_LL")) e->use_ll = atoi(v) != 0;
+    // experiment switch: 1 = out_proj fused into the attention CTAs and fc2 into the fc1 CTAs (K-split partial sums reduced in L2 with
+    // fixed-point atomics; 3 exchanges per layer instead of 5).  NOT yet validated on hardware: written after round 1 ran out of GPU time.
+    if (const char* v = getenv("ER_DECODE_FUSE")) e->use_fuse = atoi(v) != 0 && !e->use_ll;
+    if (e->use_fuse) {
+        ALLOC(e->wfuse, (size_t)NL * ((size_t)H * C * 104 + (size_t)F * (C + 8)));
+        ALLOC(e->acc, 4 * (size_t)C);
+    }
     e->sc_len = er::score_scratch_len(e->nkb, e->S, V);
     {
         er::DecodeParams p{}; p.C = C; p.F = F; p.H = H; p.V = V; p.S = e->S; p.sc_len = e->sc_len;
@@ -315,6 +341,18 @@ extern "C" int er_finalize_weights(er_engine* e, void* stream) {
             CK(pack(e->w2 + (size_t)l * C * F, C, F, l * UL + 4 * (size_t)C + F));
         }
         CK(pack(e->lm_head, e->V, C, (size_t)e->NL * UL));
+        if (e->use_fuse) {
+            const size_t per_layer = (size_t)e->H * C * 104 + (size_t)F * us;
+            for (int l = 0; l < e->NL; l++) {
+                __half* dst = e->wfuse + (size_t)l * per_layer;
+                const size_t n1 = (size_t)e->H * C * 104, n2 = (size_t)F * us;
+                e->launches += 2;
+                pack_head_cols_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(e->wo + (size_t)l * C * C, C, e->H, 96, dst, 104);
+                CK(cudaGetLastError());
+                pack_transposed_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(e->w2 + (size_t)l * C * F, C, F, dst + n1, us);
+                CK(cudaGetLastError());
+            }
+        }
     }
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     e->finalized = true;
@@ -458,6 +496,7 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.ll_q = e->ll; p.ll_attn = p.ll_q + 3 * C / 2; p.ll_y1 = p.ll_attn + C / 2; p.ll_y2 = p.ll_y1 + C / 2; p.ll_h1 = p.ll_y2 + C / 2;
     p.ll_part = p.ll_h1 + F / 2; p.use_ll = e->use_ll && (C % 4 == 0) && (V % 2 == 0);
     p.poll_rounds = 4;
+    p.use_fuse = e->use_fuse; p.wfuse = e->wfuse; p.acc = e->acc;
     p.xrep = 1;
     if (const char* v = getenv("ER_XREP")) p.xrep = std::max(1, std::min(8, atoi(v)));
     p.hint = e->hint; p.use_hint = 1;
@@ -472,7 +511,8 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     for (int done = 0; done < max_new_tokens; done += chunk) {
         p.steps = std::min(chunk, max_new_tokens - done);
         CK(cudaMemsetAsync(e->bar, 0, (64 + 64) * 4, st));
-        if (p.use_ll) { CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st)); CK(cudaMemsetAsync(e->hint, 0, 4 * (size_t)e->NL * 4, st)); }
+        if (p.use_ll || p.use_fuse) { CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st)); CK(cudaMemsetAsync(e->hint, 0, 4 * (size_t)e->NL * 4, st)); }
+        if (p.use_fuse) CK(cudaMemsetAsync(e->acc, 0, 4 * (size_t)C * 8, st));
         CKL(e, er_decode_launch(p, G, e->dec_smem, st));
     }
     if (out_len_dev) {
