@@ -50,6 +50,25 @@ def test_oracle_matches_reference(golden_dir, oracle_lib):
     assert n >= 30
 
 
+def test_oracle_lr_matches_reference(golden_dir, oracle_lib):
+    """The LR restatement (oracle/meto_oracle.c::meto_oracle_decode_lr) against the compiled reference's Engine_LR.decode."""
+    g = np.load(os.path.join(golden_dir, 'meto.npz'))
+    keys = [(str(k) + '_tokens', str(k) + '_dv', str(k) + '_df', str(k) + '_dt') for k in g['lr_names']]
+    keys += [(f'lr_stream{i}_tokens', f'lr_stream{i}_dv', f'lr_stream{i}_df', f'lr_stream{i}_dt') for i in range(int(g['n_lr_streams']))]
+    P = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+    for kt, kv, kf, ktt in keys:
+        tok = np.ascontiguousarray(g[kt], dtype=np.int32)
+        n = len(tok); cap = n // 4 + 3
+        v = np.empty((3 * cap, 3), np.float32); f = np.empty((cap, 3), np.int32); t = np.empty(cap, np.int32)
+        nv, nf, nt = C.c_int64(), C.c_int64(), C.c_int64()
+        oracle_lib.meto_oracle_decode_lr(C.c_int(512), P(tok, C.c_int32), C.c_int64(n), P(v, C.c_float), P(f, C.c_int32), P(t, C.c_int32),
+                                         C.byref(nv), C.byref(nf), C.byref(nt))
+        np.testing.assert_array_equal(v[:nv.value].astype(np.float64), g[kv].reshape(-1, 3), err_msg=kt)
+        np.testing.assert_array_equal(f[:nf.value], g[kf].reshape(-1, 3), err_msg=kt)
+        np.testing.assert_array_equal(t[:nt.value], g[ktt], err_msg=kt)
+    assert len(keys) >= 15
+
+
 def test_native_matches_reference(golden_dir):
     from meto import Engine
     for name, bins, tok, dv, df, dt in cases(golden_dir):
