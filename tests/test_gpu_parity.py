@@ -352,3 +352,43 @@ def test_arae_long_run_properties(arae_setup):
     n_ops = int(((runs[0] >= 3) & (runs[0] <= 5)).sum())
     assert abs(len(f) - n_ops) <= 1          # a trailing incomplete face is dropped by the detokenizer
     assert len(v) >= len(f)
+
+
+@pytest.mark.skipif(os.environ.get('ER_TEST_EXPERIMENTAL') != '1', reason='experimental kernel variants: opt in with ER_TEST_EXPERIMENTAL=1')
+@pytest.mark.parametrize('switch', ['ER_DECODE_LL', 'ER_DECODE_FUSE'])
+def test_experimental_variant_against_default(switch):
+    """The flagged-word exchange (bit-identical by construction) and the fused out_proj / fc2 phases (different summation order: within
+    the logit tolerance, ids equal outside the near-tie band) against the default kernel, each in its own process (the switch is read
+    when the engine is created)."""
+    import json, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import os, sys, json
+        import numpy as np, torch
+        sys.path.insert(0, %r)
+        from edgerunner_b200 import synth
+        from edgerunner_b200.engine import Engine
+        opt = synth.tiny_options()
+        sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0)
+        cond = synth.synth_point_cloud(0, opt.point_num)[0].cuda()
+        out = {}
+        for mode in (0, 1):
+            os.environ[%r] = str(mode)
+            eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=200, max_points=opt.point_num)
+            eng.load_state_dict(sd)
+            eng.encode_cond(cond, 1000); eng.prefill([1])
+            forced = out.get('tokens')
+            r = eng.decode(160, mode='greedy', want_logits=True, forced=forced)
+            if mode == 0:
+                out['tokens'] = [int(x) for x in r['tokens']]; base = r['logits_pre'].clone()
+            else:
+                d = (r['logits_pre'] - base).abs()
+                print(json.dumps(dict(max=float(d.max()), mean=float(d.mean()), nan=int(torch.isnan(r['logits_pre']).sum()))))
+    ''') % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), switch)
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    d = json.loads(res.stdout.strip().splitlines()[-1])
+    assert d['nan'] == 0
+    if switch == 'ER_DECODE_LL':
+        assert d['max'] == 0.0, d
+    else:
+        assert d['max'] <= LOGIT_TOL and d['mean'] <= MEAN_TOL, d
