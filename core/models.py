@@ -37,7 +37,6 @@ class LMM(nn.Module):
         if opt.cond_mode == 'point':
             if opt.point_encoder_mode != 'embed':
                 raise NotImplementedError("point_encoder_mode='downsample' needs torch_cluster FPS; no preset uses it")
-            assert not opt.freeze_encoder
             from core.transformer.point import PointEncoderEmbed
             self.point_encoder = PointEncoderEmbed(hidden_dim=opt.point_hidden_dim, num_heads=opt.point_num_heads,
                                                    latent_size=opt.point_latent_size, latent_dim=opt.point_latent_dim,
@@ -113,8 +112,9 @@ class LMM(nn.Module):
 
         Inference-mode numerics (no dropout, no num-face dropout, dense causal attention): the masks must be all-True.
         No autograd graph is produced (the backward pass is the next row of the scope table)."""
-        if self.training and self.opt.use_num_face_cond:
-            raise NotImplementedError('training-mode forward (num-face dropout + backward) is not on the B200 path yet')
+        if self.training:
+            raise NotImplementedError('training-mode forward (dropout, num-face dropout, autograd graph) is not on the B200 path: '
+                                      'call model.eval(); the returned loss carries no graph')
         masks = data.get('masks')
         if masks is not None and not bool(masks.all()):
             raise NotImplementedError('padded batches need the varlen attention path (not built yet)')
@@ -133,20 +133,24 @@ class LMM(nn.Module):
         """Reference :204-319.  Returns (list of meshes, list of np.int64 token arrays incl. EOS, +3 offset)."""
         B = conds.shape[0]
         assert B == 1, 'Batch size must be 1 for generation.'
+        use_fsm = tokenizer is not None
         if tokenizer is not None and self.opt.meto_backend not in ('LR', 'LR_ABSCO'):
             print('[WARN] prefix_allowed_tokens_fn is not defined for meto backend:', self.opt.meto_backend)
+            use_fsm = False                                   # reference :273-275: the constraint is disabled, not kept
         max_new_tokens = self.opt.max_seq_length if max_new_tokens is None else max_new_tokens
-        e = self.get_engine(max_new_tokens=max_new_tokens)
-
         prompt = [self.opt.bos_token_id]
         if resume_ids is not None:
             prompt += [int(x) for x in resume_ids[0].detach().cpu().tolist()]
+        # the position table has max_seq_length + num_cond_tokens + 10 rows (reference :84): a resumed request with the default
+        # max_new_tokens = max_seq_length simply runs until the table ends (the reference would index past it)
+        max_new_tokens = min(int(max_new_tokens), self.opt.max_seq_length + 10 - len(prompt))
+        e = self.get_engine(max_new_tokens=max_new_tokens + max(0, len(prompt) - 64))    # the engine keeps 64 rows of slack for the prompt
         e.encode_cond(conds[0], int(num_faces))
         e.prefill(prompt)
         mode = 'greedy' if self.opt.generate_mode == 'greedy' else 'sample'
         # sample mode draws its seed from torch's global generator, like HF's multinomial does
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if mode == 'sample' else 0
-        out = e.decode(max_new_tokens, mode=mode, top_k=10, seed=seed, use_fsm=tokenizer is not None)
+        out = e.decode(max_new_tokens, mode=mode, top_k=10, seed=seed, use_fsm=use_fsm)
 
         tokens = out['tokens']
         if resume_ids is not None:

@@ -35,6 +35,7 @@ SIGNATURES = {
     'er_kv_bytes_per_row': (c_i64, [c_vp]),
     'er_cache_rows': (c_i32, [c_vp]),
     'er_kernel_launches': (c_i64, [c_vp]),
+    'er_debug_set': (C.c_int, [c_vp, C.c_char_p, c_i64]),
     'er_debug_phase_timeline': (C.c_int, [c_vp, c_i32, c_i32]),
     'er_debug_read_timeline': (C.c_int, [c_vp, C.POINTER(c_u64), c_i32]),
     'er_meto_decode': (C.c_int, [c_i32, c_i32, C.POINTER(c_i32), c_i64, C.POINTER(c_f32), C.POINTER(c_i32), C.POINTER(c_i32),
@@ -55,7 +56,7 @@ def load():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f'edgerunner_b200: {LIB_PATH} is missing - run `python -m edgerunner_b200.build` '
                                '(there is no CPU / PyTorch fallback for this path)')
-        lib = C.CDLL(os.environ.get('ER_LIB', LIB_PATH))   # ER_LIB: A/B a differently built copy of the same library (scripts/)
+        lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args

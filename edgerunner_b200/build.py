@@ -1,4 +1,5 @@
-"""In-tree build of the sm_100a CUDA library (no JIT cache: the .so travels with the repository snapshot).
+"""In-tree build of the sm_100a CUDA library (no JIT cache).  The .so is git-ignored but NOT gpurun-ignored: it is built here
+(`__graft_entry__.build()` / this module) and travels to the GPU box with the working-tree snapshot; `_lib.load()` never builds.
 
     python -m edgerunner_b200.build [--force]      # or: from edgerunner_b200.build import build; build()
 """
@@ -11,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libedgerunner_b200.so')
 SOURCES = ['engine.cu', 'decode_kernel.cu', 'gemm.cu', 'attention.cu', 'elementwise.cu', 'meto.cpp', 'meto_encode.cpp', 'mesh_clean.cpp']
-HEADERS = ['common.cuh', 'decode_kernel.h', 'kernels.h', os.path.join('..', '..', 'include', 'edgerunner_b200.h')]
+HEADERS = ['common.cuh', 'decode_kernel.h', 'decode_partition.h', 'kernels.h', os.path.join('..', '..', 'include', 'edgerunner_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

@@ -42,7 +42,7 @@ constexpr int kConsumerWarps = ER_CONSUMER_WARPS;   // 8 or 16
 constexpr int kUnitDiv = 1;                       // a weight unit is one K-slice of C fp16
 static_assert(kConsumerWarps == 8, "the GEMV consumers assume 8 warps (one K-eighth / one unit per warp)");
 constexpr int kConsumers = kConsumerWarps * 32;   // 256 compute threads
-constexpr int kThreads = kConsumers + 32;         // + one producer warp
+constexpr int kThreads = kConsumers + 64;         // + one producer warp + one L2 run-ahead warp
 constexpr int HD = 96;                            // decoder head_dim (ArAE: 1536 / 16)
 constexpr int HV = HD / 8;                        // 16-byte vectors per head row (12)
 constexpr int kStageBytes = 24704;                // 8 padded weight units of (1536 + 8) fp16; also holds 4 K blocks / 128 V rows
@@ -130,8 +130,9 @@ __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kC
 __device__ __forceinline__ void pbar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
 // grid barrier over the consumers of all CTAs (release/acquire on one monotonically increasing counter)
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, const bool nosync) {
     cbar();
+    if (nosync) return;                 // diagnostics only (DecodeParams::dbg_nosync)
     if (threadIdx.x == 0) {
         epoch += 1;
         const unsigned target = epoch * gridDim.x;
@@ -273,15 +274,15 @@ __device__ __forceinline__ void ll_publish_rows(unsigned long long* dst, int r0,
 }
 
 // the same barrier in two halves: work placed between them overlaps the counter round trip
-__device__ __forceinline__ void grid_arrive(unsigned* counter, unsigned& epoch) {
+__device__ __forceinline__ void grid_arrive(unsigned* counter, unsigned& epoch, const bool nosync) {
     cbar();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !nosync) {
         epoch += 1;
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     }
 }
-__device__ __forceinline__ void grid_wait(unsigned* counter, unsigned epoch) {
-    if (threadIdx.x == 0) {
+__device__ __forceinline__ void grid_wait(unsigned* counter, unsigned epoch, const bool nosync) {
+    if (threadIdx.x == 0 && !nosync) {
         const unsigned target = epoch * gridDim.x;
         unsigned v;
         do {
@@ -348,13 +349,14 @@ __device__ __forceinline__ bool produce(const Ring r, Cursor& cur, const void* b
     return true;
 }
 
+// ---- the byte ranges a CTA streams, in consumption order (shared by the ring producer and the L2 run-ahead warp) --------------------
 // The kernel parameters are copied into registers up front: the consumers' acquire loads at the grid barrier invalidate the L1, and a
-// parameter fetched through a reference (local / generic memory) right after that costs the producer an L2 round trip per field.
-// Run-ahead bound: weights never change, but the K block / V rows that hold key L-1 were written by the PREVIOUS token's P1.  The ring
-// alone does not bound the producer by tokens (a CTA that owns few rows of a small model needs fewer stages per token than the ring has
-// slots), so K/V copies of pass j are only issued once the consumers have left the token-end grid barrier of pass j-1 (`tok_done`).
-template <bool FUSE>
-__device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, volatile int* stop, volatile uint32_t* cons_it, volatile int* tok_done) {
+// parameter fetched through a reference (local / generic memory) right after that costs an L2 round trip per field.
+// job(base, bytes, chunk, kv_pass): stream `bytes` from `base` in pieces of `chunk`; kv_pass > 0 marks the first K/V range of forward
+// pass kv_pass (the rows of the previous token must be complete before a bulk COPY may read them); returns false to stop the walk.
+struct SnapState { int t, L, counter, last_tok, done; };     // one snapshot of DecodeState per CTA (shared memory)
+template <bool FUSE, typename Job>
+__device__ __forceinline__ void walk_jobs(const DecodeParams& p, const int t0, int L, Job job) {
     const int C = p.C, F = p.F, H = p.H, S = p.S, V = p.V, layers = p.layers, ustride = p.ustride, handicap = p.split_handicap;
     const int nkb = p.nkb, Lmax = p.Lmax;
     const __half* const wdec = p.wdec;
@@ -362,11 +364,8 @@ __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, 
     const size_t fuse_layer = FUSE ? (size_t)H * C * kHoStride + (size_t)F * ustride : 0;   // fp16 per layer of the fused-phase weight copies
     const __half* const kc = p.kc;
     const __half* const vc = p.vc;
-    int t = p.st->t, L = p.st->L;
-    if (p.st->done) return;
     // forward passes of this launch: token tt is followed by a pass iff tt + 1 < max_new (EOS is handled through `stop`)
-    const int n_fwd = min(p.steps, p.max_new - 1 - t);
-    Cursor cur{0u, 0u, 0u};
+    const int n_fwd = min(p.steps, p.max_new - 1 - t0);
     bool ok = true;
     // decode weights live in `wdec` as units of C fp16 padded to `ustride` (bank-conflict-free ldmatrix rows); per layer:
     // [3C qkv rows][C out_proj rows][F fc1 rows][C fc2 rows x F/C units]; after the layers: V lm_head rows.
@@ -380,34 +379,88 @@ __device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, 
         const bool has_attn = attn_range(H, S, handicap, L, a);
         for (int layer = 0; layer < layers && ok; ++layer) {
             const __half* wl = wdec + (size_t)layer * UL * ustride;
-            ok = produce(r, cur, wl + (size_t)rq.r0 * ustride, (size_t)(rq.r1 - rq.r0) * ub, wchunk, stop);
-            if (ok && has_attn && layer == 0 && pass > 0) {
-                while (*tok_done < pass) { if (*stop) { ok = false; break; } }
-                asm volatile("fence.proxy.async.global;" ::: "memory");   // rows written through the generic proxy, read by the bulk copy below
-            }
+            ok = job(wl + (size_t)rq.r0 * ustride, (size_t)(rq.r1 - rq.r0) * ub, wchunk, 0);
             if (ok && has_attn) {
                 const __half* kbase = kc + (((size_t)layer * H + a.h) * nkb + a.b0) * (size_t)(HV * 256);
-                ok = produce(r, cur, kbase, (size_t)(a.b1 - a.b0) * kKBlockBytes, kKVChunk, stop);
+                ok = job(kbase, (size_t)(a.b1 - a.b0) * kKBlockBytes, kKVChunk, layer == 0 ? pass : 0);
                 const __half* vbase = vc + (((size_t)layer * H + a.h) * Lmax + a.k0) * HD;
-                if (ok) ok = produce(r, cur, vbase, (size_t)(a.k1 - a.k0) * HD * 2, kKVChunk, stop);
+                if (ok) ok = job(vbase, (size_t)(a.k1 - a.k0) * HD * 2, kKVChunk, 0);
                 if (FUSE && ok) {   // this split's rows of the head's out_proj columns
                     const RowRange rs = cta_rows_of(C, blockIdx.x % (unsigned)S, (unsigned)S);
-                    ok = produce(r, cur, wfuse + (size_t)layer * fuse_layer + ((size_t)a.h * C + rs.r0) * kHoStride, (size_t)(rs.r1 - rs.r0) * kHoStride * 2,
-                                 (uint32_t)(kHoUnitsPerStage * kHoStride * 2), stop);
+                    ok = job(wfuse + (size_t)layer * fuse_layer + ((size_t)a.h * C + rs.r0) * kHoStride, (size_t)(rs.r1 - rs.r0) * kHoStride * 2,
+                             (uint32_t)(kHoUnitsPerStage * kHoStride * 2), 0);
                 }
             }
-            if (!FUSE && ok) ok = produce(r, cur, wl + ((size_t)3 * C + rc.r0) * ustride, (size_t)(rc.r1 - rc.r0) * ub, wchunk, stop);
-            if (ok) ok = produce(r, cur, wl + ((size_t)4 * C + rf.r0) * ustride, (size_t)(rf.r1 - rf.r0) * ub, wchunk, stop);
-            if (!FUSE && ok) ok = produce(r, cur, wl + ((size_t)4 * C + F + (size_t)rc.r0 * nuf) * ustride, (size_t)(rc.r1 - rc.r0) * nuf * ub, wchunk, stop);
+            if (!FUSE && ok) ok = job(wl + ((size_t)3 * C + rc.r0) * ustride, (size_t)(rc.r1 - rc.r0) * ub, wchunk, 0);
+            if (ok) ok = job(wl + ((size_t)4 * C + rf.r0) * ustride, (size_t)(rf.r1 - rf.r0) * ub, wchunk, 0);
+            if (!FUSE && ok) ok = job(wl + ((size_t)4 * C + F + (size_t)rc.r0 * nuf) * ustride, (size_t)(rc.r1 - rc.r0) * nuf * ub, wchunk, 0);
             if (FUSE && ok)     // the fc2 columns matching this CTA's fc1 rows (one transposed unit per column)
-                ok = produce(r, cur, wfuse + (size_t)layer * fuse_layer + (size_t)H * C * kHoStride + (size_t)rf.r0 * ustride, (size_t)(rf.r1 - rf.r0) * ub, wchunk, stop);
+                ok = job(wfuse + (size_t)layer * fuse_layer + (size_t)H * C * kHoStride + (size_t)rf.r0 * ustride, (size_t)(rf.r1 - rf.r0) * ub, wchunk, 0);
         }
-        if (ok) ok = produce(r, cur, wdec + ((size_t)layers * UL + rv.r0) * ustride, (size_t)(rv.r1 - rv.r0) * ub, wchunk, stop);
+        if (ok) ok = job(wdec + ((size_t)layers * UL + rv.r0) * ustride, (size_t)(rv.r1 - rv.r0) * ub, wchunk, 0);
     }
+}
+
+// Ring producer.  Run-ahead bound: weights never change, but the K block / V rows that hold key L-1 were written by the PREVIOUS
+// token's P1.  The ring alone does not bound the producer by tokens (a CTA that owns few rows of a small model needs fewer stages per
+// token than the ring has slots), so K/V copies of pass j are only issued once the consumers have left the token-end grid barrier of
+// pass j-1 (`tok_done`).  `issued` publishes the running byte count to the L2 run-ahead warp.
+template <bool FUSE>
+__device__ __noinline__ void producer_loop(const DecodeParams& p, const Ring r, const SnapState* snap, volatile int* stop, volatile uint32_t* cons_it,
+                                           volatile int* tok_done, volatile unsigned long long* issued) {
+    if (snap->done) return;
+    Cursor cur{0u, 0u, 0u};
+    bool ok = true;
+    unsigned long long total = 0;
+    walk_jobs<FUSE>(p, snap->t, snap->L, [&](const void* base, size_t bytes, uint32_t chunk, int kv_pass) -> bool {
+        if (kv_pass > 0) {
+            while (*tok_done < kv_pass) { if (*stop) { ok = false; return false; } }
+            asm volatile("fence.proxy.async.global;" ::: "memory");   // rows written through the generic proxy, read by the bulk copy below
+        }
+        const char* src = reinterpret_cast<const char*>(base);
+        for (size_t off = 0; off < bytes; off += chunk, cur.advance(r.nstage)) {
+            while (!mbar_try_wait(r.emptyb(cur.stage), cur.parity ^ 1)) {
+                if (*stop) { ok = false; return false; }
+            }
+            if (*stop) { ok = false; return false; }
+            const uint32_t n = (uint32_t)(bytes - off < (size_t)chunk ? bytes - off : (size_t)chunk);
+            mbar_arrive_expect_tx(r.fullb(cur.stage), n);
+            bulk_g2s(r.stage(cur.stage), src + off, n, r.fullb(cur.stage));
+            total += n;
+            *issued = total;
+        }
+        return true;
+    });
     if (!ok) {
         // EOS: the consumers stopped at stage *cons_it; every copy we issued beyond it must land before the CTA may exit
         for (uint32_t j = *cons_it; j < cur.it; ++j) mbar_wait(r.fullb(j % r.nstage), (j / r.nstage) & 1);
     }
+}
+
+// L2 run-ahead warp (one lane): walks the same byte ranges and asks the TMA unit to pull them into L2 (cp.async.bulk.prefetch.L2,
+// fire and forget), staying at most pf_dist bytes ahead of what the ring producer has requested.  The ring (7 x 24 KB) covers ~4 us
+// of HBM streaming; a layer has ~15 us of exchanges.  With the run-ahead HBM keeps streaming through them and the ring refills from
+// L2 afterwards.  Pieces the producer has already requested are skipped (no duplicate DRAM traffic).  Prefetching a K/V line that
+// the previous token is still writing is harmless: L2 is the point of coherence for those stores.
+template <bool FUSE>
+__device__ __noinline__ void prefetch_loop(const DecodeParams& p, const SnapState* snap, volatile int* stop, volatile unsigned long long* issued) {
+    if (snap->done) return;
+    const unsigned long long dist = (unsigned long long)p.pf_dist;
+    unsigned long long total = 0;
+    walk_jobs<FUSE>(p, snap->t, snap->L, [&](const void* base, size_t bytes, uint32_t chunk, int) -> bool {
+        const char* src = reinterpret_cast<const char*>(base);
+        for (size_t off = 0; off < bytes; off += chunk) {
+            const uint32_t n = (uint32_t)(bytes - off < (size_t)chunk ? bytes - off : (size_t)chunk);
+            unsigned long long have;
+            while (total + n > (have = *issued) + dist) {
+                if (*stop) return false;
+                __nanosleep(100);
+            }
+            if (total >= have) prefetch_l2_bulk(src + off, n);
+            total += n;
+        }
+        return !*stop;
+    });
 }
 
 // ---- consumer: GEMV over one streamed weight slice ------------------------------------------------------------------------------------
@@ -1109,13 +1162,18 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
     __shared__ int s_flag;
     __shared__ int s_tok_done;   // tokens of this launch whose token-end grid barrier the consumers have passed
     __shared__ int s_rows[8];   // this CTA's row ranges of the 3C / C / F / V phases (computed once; registers are scarce)
+    __shared__ SnapState s_snap; // ONE snapshot of the device state per CTA: producer, run-ahead warp and consumers must agree on `done`
+    __shared__ unsigned long long s_issued;   // bytes the ring producer has requested so far (read by the L2 run-ahead warp)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool nosync = p.dbg_nosync != 0;
     if (tid == 0) {
         for (int i = 0; i < p.nstage; i++) { mbar_init(ring.fullb(i), 1); mbar_init(ring.emptyb(i), kConsumerWarps); }
         s_stop = 0;
         s_cons_it = 0;
         s_tok_done = 0;
+        s_issued = 0ull;
+        s_snap.t = p.st->t; s_snap.L = p.st->L; s_snap.counter = p.st->counter; s_snap.last_tok = p.st->last_tok; s_snap.done = p.st->done;
         const RowRange r3 = cta_rows(3 * C), r1 = cta_rows(C), rf = cta_rows(F), rv = cta_rows(V);
         s_rows[0] = r3.r0; s_rows[1] = r3.r1; s_rows[2] = r1.r0; s_rows[3] = r1.r1; s_rows[4] = rf.r0; s_rows[5] = rf.r1; s_rows[6] = rv.r0; s_rows[7] = rv.r1;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1125,15 +1183,18 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
 
     if (warp == kConsumerWarps) {
         // ===== producer warp: one elected lane streams this CTA's byte ranges through the ring =====
-        if (lane == 0) producer_loop<FUSE>(p, ring, &s_stop, &s_cons_it, &s_tok_done);
+        if (lane == 0) producer_loop<FUSE>(p, ring, &s_snap, &s_stop, &s_cons_it, &s_tok_done, &s_issued);
+    } else if (warp == kConsumerWarps + 1) {
+        // ===== L2 run-ahead warp =====
+        if (lane == 0 && p.pf_dist > 0) prefetch_loop<FUSE>(p, &s_snap, &s_stop, &s_issued);
     } else {
         // ===== consumers =====
         unsigned epoch = 0;
         Cursor cur{0u, 0u, 0u};
         const uint32_t xin_s = s_addr(xin), xres_s = s_addr(xres), part_s = s_addr(part);
         const float inv_c = 1.0f / (float)C;
-        int t = p.st->t, L = p.st->L, counter = p.st->counter, last_tok = p.st->last_tok;
-        const bool done0 = p.st->done != 0;
+        int t = s_snap.t, L = s_snap.L, counter = s_snap.counter, last_tok = s_snap.last_tok;
+        const bool done0 = s_snap.done != 0;
         bool state_written = done0;
         const int nu_fc2 = (F / C) * kUnitDiv;      // units per fc2 row
         const int nu1 = kUnitDiv;                   // units per row of the C-wide phases
@@ -1203,7 +1264,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                         else if (own) p.q16[r] = hv;
                     }
                     prof_stamp(p, pb + 2, prof_on); prof_all(p, 2, all_on);
-                    if (!LL) grid_arrive(p.bar, epoch);
+                    if (!LL) grid_arrive(p.bar, epoch, nosync);
                     if (own && r >= C) {
                         if (r < 2 * C) {
                             const int c = r - C, h = c / HD, d = c % HD;
@@ -1214,7 +1275,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                             p.vc[(((size_t)layer * H + h) * p.Lmax + L) * HD + d] = hv;
                         }
                     }
-                    if (!LL) grid_wait(p.bar, epoch);
+                    if (!LL) grid_wait(p.bar, epoch, nosync);
                     if (FUSE) {   // everybody has finished with the other copy of the accumulators (previous layer): zero this CTA's slice of it
                         unsigned long long* const other = p.acc + (size_t)((gl + 1) & 1) * 2 * C;
                         const int z0 = s_rows[2], zn = s_rows[3] - s_rows[2];
@@ -1225,7 +1286,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 // ---------------- P2: attention -----------------------------------------------------------------------------------------
                 cur = attention_phase<LL, FUSE>(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag, part, flag, acc_y1);
                 prof_stamp(p, pb + 4, prof_on); prof_all(p, 4, all_on);
-                if (!LL && !FUSE) grid_barrier(p.bar, epoch);
+                if (!LL && !FUSE) grid_barrier(p.bar, epoch, nosync);
                 prof_stamp(p, pb + 5, prof_on); prof_all(p, 5, all_on);
                 // ---------------- P3: out_proj on the merged attention output -----------------------------------------------------------
                 if (!FUSE) {
@@ -1251,7 +1312,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 }
                 const LnParams lp1 = ln_load(p.ln1_w + (size_t)layer * C, p.ln1_b + (size_t)layer * C, C);   // lands while we wait at the barrier
                 prof_stamp(p, pb + 7, prof_on); prof_all(p, 7, all_on);
-                if (!LL) grid_barrier(p.bar, epoch);
+                if (!LL) grid_barrier(p.bar, epoch, nosync);
                 prof_stamp(p, pb + 8, prof_on); prof_all(p, 8, all_on);
                 // ---------------- P4: x = LN1(x + y1) ; h1 = relu(fc1(x)) -----------------------------------------------------------
                 {
@@ -1302,7 +1363,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     }
                 }
                 prof_stamp(p, pb + 10, prof_on); prof_all(p, 10, all_on);
-                if (!LL && !FUSE) grid_barrier(p.bar, epoch);
+                if (!LL && !FUSE) grid_barrier(p.bar, epoch, nosync);
                 prof_stamp(p, pb + 11, prof_on); prof_all(p, 11, all_on);
                 // ---------------- P5: y2 = fc2(h1) -----------------------------------------------------------------------------------------
                 if (!FUSE) {
@@ -1326,7 +1387,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 }
                 const LnParams lp2 = ln_load(p.ln2_w + (size_t)layer * C, p.ln2_b + (size_t)layer * C, C);
                 prof_stamp(p, pb + 13, prof_on); prof_all(p, 13, all_on);
-                if (!LL) grid_barrier(p.bar, epoch);
+                if (!LL) grid_barrier(p.bar, epoch, nosync);
                 prof_stamp(p, pb + 14, prof_on); prof_all(p, 14, all_on);
                 // ---------------- x = LN2(x + y2) ------------------------------------------------------------------------------------------
                 residual_layer_norm(xres_s, xin_s, p.y2 + (size_t)xcopy * C, LL ? p.ll_y2 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 3 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), false, lp2, C, inv_c, red, acc_y2, FUSE ? p.b2 + (size_t)layer * C : nullptr);
@@ -1344,7 +1405,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
             }
             L += 1;
             prof_stamp(p, 1 + 16 * p.layers, prof_on);
-            grid_barrier(p.bar, epoch);
+            grid_barrier(p.bar, epoch, nosync);
             if (tid == 0) { __threadfence_block(); *(volatile int*)&s_tok_done = iter + 1; }
             prof_stamp(p, 2 + 16 * p.layers, prof_on);
         }
@@ -1389,8 +1450,8 @@ int er_decode_max_grid(size_t smem) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int ok = 1;
-    for (int v = 0; v < 4; ++v) {   // (the experimental fused instantiations are only checked when they are launched: er_decode_launch fails loudly)
-        const void* fn = er_decode_kernel_fn((v & 1) != 0, (v & 2) != 0, false);
+    for (int v = 0; v < 6; ++v) {
+        const void* fn = v < 4 ? er_decode_kernel_fn((v & 1) != 0, (v & 2) != 0, false) : er_decode_kernel_fn((v & 1) != 0, false, true);
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, er::kThreads, smem) != cudaSuccess || per < 1) ok = 0;
     }

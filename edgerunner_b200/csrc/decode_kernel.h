@@ -57,6 +57,11 @@ struct DecodeParams {
     // fused phases (use_fuse, experimental): per layer [H][C][HD+8] per-head out_proj units, then [F][ustride] transposed fc2 units;
     // acc: u64 fixed-point accumulators [2 copies][y1 | y2][C], zeroed by the host before each launch
     const __half *wfuse; unsigned long long *acc; int use_fuse;
+    // L2 run-ahead: a second streaming warp issues cp.async.bulk.prefetch.L2 for this CTA's future ring bytes, staying at most
+    // pf_dist bytes ahead of the ring producer, so that HBM keeps streaming while the consumers sit in an exchange (0 = off)
+    int pf_dist;
+    // diagnostics only (er_debug_set): skip the grid barriers (results are garbage; shows the streaming / consumption rate alone)
+    int dbg_nosync;
 };
 
 }  // namespace er

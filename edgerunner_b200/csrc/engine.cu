@@ -16,7 +16,12 @@
 #include "decode_partition.h"
 #include "kernels.h"
 
+#ifndef ER_DEFAULT_PF_DIST
+#define ER_DEFAULT_PF_DIST 0
+#endif
+
 static thread_local char g_err[512] = "";
+static int g_poison_alloc = 0;   // er_debug_set_global("poison_alloc", 1 everything | 2 K cache | 3 V cache | 4 the rest)
 static int set_err(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -120,7 +125,10 @@ struct er_engine {
     // encoder workspace
     __half *emb16, *pf16, *kvx16, *kvo16, *qln16, *qq16, *ea16, *ex1, *ex1ln, *eff, *egg, *ex2, *pc16;
     int cache_rows = 0;
+    bool cache_rows_stale = false;     // a decode ran since cache_rows was set: the exact row count lives in the device state
     unsigned long long* prof = nullptr; int prof_token = -1, prof_cta = 0;
+    // decode-kernel knobs (defaults = the production configuration; changed only through er_debug_set)
+    int split_handicap = 4, xrep = 1, use_hint = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
     int lat_batch_cap = 1;
 };
 
@@ -130,11 +138,10 @@ static int dev_alloc(er_engine* e, T** p, size_t n) {
     CK(cudaMalloc(&q, n * sizeof(T) + 256));
     // debugging aid (tests/test_gpu_parity.py::test_poisoned_memory): fill every allocation with 0xFF bytes (fp16 / fp32 NaN) so that
     // any read of memory the engine did not write first shows up as NaN instead of passing by luck on zeroed pages
-    static const char* poison = getenv("ER_POISON_ALLOC");   // "1" = everything; "kc" / "vc" / "rest" narrow a finding down
-    if (poison) {
+    if (g_poison_alloc) {
         const bool is_kc = (void*)p == (void*)&e->kc, is_vc = (void*)p == (void*)&e->vc;
-        const bool want = !strcmp(poison, "1") || (!strcmp(poison, "kc") && is_kc) || (!strcmp(poison, "vc") && is_vc) ||
-                          (!strcmp(poison, "rest") && !is_kc && !is_vc);
+        const bool want = g_poison_alloc == 1 || (g_poison_alloc == 2 && is_kc) || (g_poison_alloc == 3 && is_vc) ||
+                          (g_poison_alloc == 4 && !is_kc && !is_vc);
         if (want) CK(cudaMemset(q, 0xFF, n * sizeof(T) + 256));
     }
     e->allocs.push_back(q);
@@ -142,6 +149,44 @@ static int dev_alloc(er_engine* e, T** p, size_t n) {
     return ER_OK;
 }
 #define ALLOC(ptr, n) do { int _r = dev_alloc(e, &(ptr), (size_t)(n)); if (_r) return _r; } while (0)
+template <typename T>
+static void dev_free(er_engine* e, T** p) {
+    if (!*p) return;
+    for (auto it = e->allocs.begin(); it != e->allocs.end(); ++it)
+        if (*it == (void*)*p) { e->allocs.erase(it); break; }
+    cudaFree(*p);
+    *p = nullptr;
+}
+
+// Dense (N > 1 rows) workspace: sized for the 2050-row generate prefix at creation and grown on demand, so that a long resume prompt
+// (LMM.generate(resume_ids=...), infer.py --test_resume_tokens: up to max_seq_length rows in the reference) is not refused.
+static int ensure_dense_rows(er_engine* e, int rows) {
+    if (rows <= e->maxrows) return ER_OK;
+    CK(cudaDeviceSynchronize());
+    dev_free(e, &e->x32); dev_free(e, &e->x16); dev_free(e, &e->qkv16); dev_free(e, &e->a16); dev_free(e, &e->h16);
+    const bool had_logits = e->logits_all != nullptr;
+    dev_free(e, &e->logits_all);
+    const int maxrows = rows + 8;
+    const int C = e->C, F = e->F;
+    e->maxrows = 0;
+    ALLOC(e->x32, (size_t)maxrows * C); ALLOC(e->x16, (size_t)maxrows * C); ALLOC(e->qkv16, (size_t)maxrows * 3 * C);
+    ALLOC(e->a16, (size_t)maxrows * C); ALLOC(e->h16, (size_t)maxrows * F);
+    if (had_logits) ALLOC(e->logits_all, (size_t)maxrows * e->V);
+    e->maxrows = maxrows;
+    return ER_OK;
+}
+
+// rows in the KV cache: exact after a decode too (an early EOS leaves fewer rows than max_new_tokens would; read back from the device)
+static int sync_cache_rows(er_engine* e) {
+    if (e->cache_rows_stale) {
+        CK(cudaDeviceSynchronize());
+        int L = 0;
+        CK(cudaMemcpy(&L, &e->st->L, 4, cudaMemcpyDeviceToHost));
+        e->cache_rows = L;
+        e->cache_rows_stale = false;
+    }
+    return ER_OK;
+}
 
 extern "C" const char* er_last_error(void) { return g_err; }
 extern "C" int er_version(void) { return 100; }
@@ -150,20 +195,16 @@ static void add_slot(er_engine* e, const std::string& name, __half* dst, int row
     e->slots[name] = Slot{dst, rows, cols, dst_ld ? dst_ld : cols};
 }
 
-extern "C" int er_create(const er_config* cfg, er_engine** out) {
-    if (!cfg || !out) return set_err(ER_ERR_INVALID, "null argument");
-    CK(cudaSetDevice(cfg->device));
-    er_engine* e = new er_engine();
-    e->cfg = *cfg;
+static int create_impl(er_engine* e, const er_config* cfg) {
     const int C = e->C = cfg->hidden_dim, H = e->H = cfg->num_heads, F = e->F = cfg->ffn_dim, V = e->V = cfg->vocab_size;
     const int NL = e->NL = cfg->num_layers, P = e->P = cfg->num_cond_tokens;
     e->D = C / H;
-    if (e->D != 96 || C % 8 || F % 8) { delete e; return set_err(ER_ERR_INVALID, "decoder head_dim must be 96 (got %d), C,F multiples of 8", e->D); }
+    if (e->D != 96 || C % 8 || F % 8) { return set_err(ER_ERR_INVALID, "decoder head_dim must be 96 (got %d), C,F multiples of 8", e->D); }
     const int E = e->E = cfg->point_hidden_dim, LQ = e->LQ = cfg->point_latent_size, LD = e->LD = cfg->point_latent_dim;
     e->EH = cfg->point_num_heads;
     e->LDP = (LD + 7) / 8 * 8;
-    if (cfg->has_point_encoder && (E / e->EH != 64 || E % 8)) { delete e; return set_err(ER_ERR_INVALID, "encoder head_dim must be 64"); }
-    if (P != LQ + (cfg->use_num_face_cond ? 1 : 0)) { delete e; return set_err(ER_ERR_INVALID, "num_cond_tokens %d != latent_size %d + num_face token", P, LQ); }
+    if (cfg->has_point_encoder && (E / e->EH != 64 || E % 8)) { return set_err(ER_ERR_INVALID, "encoder head_dim must be 64"); }
+    if (P != LQ + (cfg->use_num_face_cond ? 1 : 0)) { return set_err(ER_ERR_INVALID, "num_cond_tokens %d != latent_size %d + num_face token", P, LQ); }
     const int Lmax = e->Lmax = (cfg->max_seq_rows + 31) / 32 * 32;
     e->nkb = Lmax / 32;
     if (Lmax > cfg->max_positions) {}  // positions are checked per call
@@ -177,7 +218,6 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     ALLOC(e->lm_head, (size_t)V * C); ALLOC(e->embd, (size_t)V * C); ALLOC(e->pos, (size_t)cfg->max_positions * C);
     e->ustride = C + 8;
     e->use_mma = (C % 256 == 0) ? 1 : 0;
-    if (const char* v = getenv("ER_DECODE_GEMV")) { if (!strcmp(v, "cuda")) e->use_mma = 0; }   // ablation switch: CUDA-core GEMV consumers
     e->upstage = e->use_mma ? 8 : er_decode_stage_bytes() / (e->ustride * 2) / 8 * 8;   // multiple of 8 (and so of F/C)
     ALLOC(e->wdec, ((size_t)NL * (4 * (size_t)C + 2 * (size_t)F) + V) * e->ustride + 64);
     char nm[256];
@@ -247,34 +287,25 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     e->grid = sms;
-    e->S = sms / H; if (e->S > 16) e->S = 16; if (e->S < 1) { delete e; return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
+    e->S = sms / H; if (e->S > 16) e->S = 16; if (e->S < 1) { return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
     ALLOC(e->part, (size_t)H * e->S * 100);
     e->ll_words = (size_t)3 * C / 2 + 3 * (size_t)(C / 2) + F / 2 + (size_t)H * e->S * 100;
     ALLOC(e->ll, e->ll_words);
     ALLOC(e->hint, 4 * (size_t)NL);
-    // experiment switch: 1 = flagged-word exchange instead of grid barriers inside a layer (measured slower: same number of
-    // dependent L2 round trips per exchange once polling is throttled, plus register pressure)
-    if (const char* v = getenv("ER_DECODE_LL")) e->use_ll = atoi(v) != 0;
-    // experiment switch: 1 = out_proj fused into the attention CTAs and fc2 into the fc1 CTAs (K-split partial sums reduced in L2 with
-    // fixed-point atomics; 3 exchanges per layer instead of 5).  NOT yet validated on hardware: written after round 1 ran out of GPU time.
-    if (const char* v = getenv("ER_DECODE_FUSE")) e->use_fuse = atoi(v) != 0 && !e->use_ll;
-    if (e->use_fuse) {
-        ALLOC(e->wfuse, (size_t)NL * ((size_t)H * C * 104 + (size_t)F * (C + 8)));
-        ALLOC(e->acc, 4 * (size_t)C);
-    }
+    ALLOC(e->acc, 4 * (size_t)C);
     e->sc_len = er::score_scratch_len(e->nkb, e->S, V);
     {
         er::DecodeParams p{}; p.C = C; p.F = F; p.H = H; p.V = V; p.S = e->S; p.sc_len = e->sc_len;
         int smem_max = 0;
         CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
         e->nstage = er_decode_pick_stages(p, (size_t)smem_max - 1024);
-        if (e->nstage < 2) { delete e; return set_err(ER_ERR_CAPACITY, "not enough shared memory for the decode ring (limit %d)", smem_max); }
+        if (e->nstage < 2) { return set_err(ER_ERR_CAPACITY, "not enough shared memory for the decode ring (limit %d)", smem_max); }
         p.nstage = e->nstage;
         e->dec_smem = er_decode_smem_bytes(p);
-        if (er_decode_max_grid(e->dec_smem) < sms) { delete e; return set_err(ER_ERR_CAPACITY, "decode kernel cannot be co-resident on %d SMs (smem %zu)", sms, e->dec_smem); }
+        if (er_decode_max_grid(e->dec_smem) < sms) { return set_err(ER_ERR_CAPACITY, "decode kernel cannot be co-resident on %d SMs (smem %zu)", sms, e->dec_smem); }
     }
     // ---- dense workspace ----------------------------------------------------------------------------------------------------------
-    const int maxrows = e->maxrows = std::max(P + 4096, cfg->max_tf_rows) + 8;
+    const int maxrows = e->maxrows = std::max(P + 64, cfg->max_tf_rows) + 8;
     ALLOC(e->x32, (size_t)maxrows * C); ALLOC(e->x16, (size_t)maxrows * C); ALLOC(e->qkv16, (size_t)maxrows * 3 * C);
     ALLOC(e->a16, (size_t)maxrows * C); ALLOC(e->h16, (size_t)maxrows * F);
     e->logits_all = nullptr;
@@ -289,6 +320,16 @@ extern "C" int er_create(const er_config* cfg, er_engine** out) {
         ALLOC(e->ex1ln, (size_t)LQ * E); ALLOC(e->eff, (size_t)LQ * 8 * E); ALLOC(e->egg, (size_t)LQ * 4 * E); ALLOC(e->ex2, (size_t)LQ * E);
     }
     CK(cudaDeviceSynchronize());
+    return ER_OK;
+}
+
+extern "C" int er_create(const er_config* cfg, er_engine** out) {
+    if (!cfg || !out) return set_err(ER_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(cfg->device));
+    er_engine* e = new er_engine();
+    e->cfg = *cfg;
+    const int r = create_impl(e, cfg);
+    if (r) { er_destroy(e); return r; }      // frees every device allocation recorded so far (g_err keeps the message)
     *out = e;
     return ER_OK;
 }
@@ -342,6 +383,7 @@ extern "C" int er_finalize_weights(er_engine* e, void* stream) {
         }
         CK(pack(e->lm_head, e->V, C, (size_t)e->NL * UL));
         if (e->use_fuse) {
+            if (!e->wfuse) ALLOC(e->wfuse, (size_t)e->NL * ((size_t)e->H * C * 104 + (size_t)F * us));
             const size_t per_layer = (size_t)e->H * C * 104 + (size_t)F * us;
             for (int l = 0; l < e->NL; l++) {
                 __half* dst = e->wfuse + (size_t)l * per_layer;
@@ -455,7 +497,8 @@ extern "C" int er_prefill(er_engine* e, const int32_t* prompt_ids_host, int32_t 
     if (!e->finalized) return set_err(ER_ERR_STATE, "weights not finalized");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = e->P + n_prompt, C = e->C;
-    if (N > e->maxrows || N > e->Lmax || N > e->cfg.max_positions || n_prompt > 65536) return set_err(ER_ERR_CAPACITY, "prefix of %d rows exceeds capacity", N);
+    if (N > e->Lmax || N > e->cfg.max_positions || n_prompt > 65536) return set_err(ER_ERR_CAPACITY, "prefix of %d rows exceeds the cache capacity %d", N, e->Lmax);
+    { int r = ensure_dense_rows(e, N); if (r) return r; }
     for (int i = 0; i < n_prompt; i++)
         if (prompt_ids_host[i] < 0 || prompt_ids_host[i] >= e->V) return set_err(ER_ERR_INVALID, "prompt id %d out of range", prompt_ids_host[i]);
     CK(cudaMemcpyAsync(e->ids_dev, prompt_ids_host, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, st));
@@ -468,6 +511,7 @@ extern "C" int er_prefill(er_engine* e, const int32_t* prompt_ids_host, int32_t 
     init_state_kernel<<<1, 1, 0, st>>>(e->st, N);
     CK(cudaGetLastError());
     e->cache_rows = N;
+    e->cache_rows_stale = false;
     return ER_OK;
 }
 
@@ -476,8 +520,10 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
                          const int32_t* forced_ids_dev, void* stream) {
     if (!e || !out_ids_dev || max_new_tokens < 1) return set_err(ER_ERR_INVALID, "bad argument");
     if (e->cache_rows <= 0) return set_err(ER_ERR_STATE, "er_prefill has not run");
+    { int r = sync_cache_rows(e); if (r) return r; }
     if (e->cache_rows + max_new_tokens > e->Lmax || e->cache_rows + max_new_tokens > e->cfg.max_positions)
         return set_err(ER_ERR_CAPACITY, "cache rows %d + max_new_tokens %d exceed capacity %d", e->cache_rows, max_new_tokens, e->Lmax);
+    if (e->dbg_nosync && !forced_ids_dev) return set_err(ER_ERR_STATE, "debug 'nosync' produces garbage logits: a forced token stream is required");
     cudaStream_t st = (cudaStream_t)stream;
     const int C = e->C, F = e->F, V = e->V, G = e->grid;
     er::DecodeParams p{};
@@ -490,18 +536,15 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.w1 = e->w1; p.b1 = e->b1; p.w2 = e->w2; p.b2 = e->b2; p.ln2_w = e->ln2w; p.ln2_b = e->ln2b;
     p.lm_head = e->lm_head; p.embd = e->embd; p.pos = e->pos;
     p.wdec = e->wdec; p.ustride = e->ustride; p.upstage = e->upstage; p.use_mma = e->use_mma;
-    p.split_handicap = 4;
-    if (const char* v = getenv("ER_SPLIT_HANDICAP")) p.split_handicap = std::max(0, std::min(7, atoi(v)));
+    p.split_handicap = e->split_handicap;
     p.kc = e->kc; p.vc = e->vc; p.attn16 = e->attn16; p.head_cnt = e->bar + 64; p.q16 = e->q16; p.y1 = e->y1; p.h1 = e->h1; p.y2 = e->y2; p.part = e->part; p.logits = e->logits;
     p.ll_q = e->ll; p.ll_attn = p.ll_q + 3 * C / 2; p.ll_y1 = p.ll_attn + C / 2; p.ll_y2 = p.ll_y1 + C / 2; p.ll_h1 = p.ll_y2 + C / 2;
     p.ll_part = p.ll_h1 + F / 2; p.use_ll = e->use_ll && (C % 4 == 0) && (V % 2 == 0);
-    p.poll_rounds = 4;
-    p.use_fuse = e->use_fuse; p.wfuse = e->wfuse; p.acc = e->acc;
-    p.xrep = 1;
-    if (const char* v = getenv("ER_XREP")) p.xrep = std::max(1, std::min(8, atoi(v)));
-    p.hint = e->hint; p.use_hint = 1;
-    if (const char* v = getenv("ER_DECODE_HINT")) p.use_hint = atoi(v) != 0;
-    if (const char* v = getenv("ER_POLL_ROUNDS")) p.poll_rounds = std::max(0, atoi(v));
+    p.poll_rounds = e->poll_rounds;
+    p.use_fuse = e->use_fuse && e->wfuse != nullptr; p.wfuse = e->wfuse; p.acc = e->acc;
+    p.xrep = e->xrep;
+    p.hint = e->hint; p.use_hint = e->use_hint;
+    p.pf_dist = e->pf_dist; p.dbg_nosync = e->dbg_nosync;
     p.st = e->st; p.bar = e->bar;
     p.out_ids = out_ids_dev; p.out_logits = out_logits_dev; p.forced = forced_ids_dev;
     p.max_new = max_new_tokens; p.mode = mode; p.top_k = top_k > 0 ? top_k : 10; p.use_fsm = use_tokenizer_fsm; p.eos = e->cfg.eos_token_id;
@@ -520,7 +563,8 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
         finish_decode_kernel<<<1, 1, 0, st>>>(e->st, out_len_dev);
         CK(cudaGetLastError());
     }
-    e->cache_rows += max_new_tokens - 1;   // upper bound; exact value lives in the device state
+    e->cache_rows += max_new_tokens - 1;   // upper bound until the next query reads the exact value back from the device state
+    e->cache_rows_stale = true;
     return ER_OK;
 }
 
@@ -588,7 +632,7 @@ extern "C" int64_t er_weight_bytes_per_token(const er_engine* e) {
     return 2 * (per_layer * e->NL + (int64_t)e->V * C);
 }
 extern "C" int64_t er_kv_bytes_per_row(const er_engine* e) { return (int64_t)e->NL * 2 * e->C * 2; }
-extern "C" int32_t er_cache_rows(const er_engine* e) { return e->cache_rows; }
+extern "C" int32_t er_cache_rows(const er_engine* e) { sync_cache_rows(const_cast<er_engine*>(e)); return e->cache_rows; }
 extern "C" int64_t er_kernel_launches(const er_engine* e) { return e->launches; }
 
 extern "C" int er_attention_bnhd(const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev, int32_t B, int32_t Nq, int32_t Nk,
@@ -602,6 +646,34 @@ extern "C" int er_attention_bnhd(const void* q_dev, const void* k_dev, const voi
     a.q_bs = a.o_bs = (long long)Nq * H * D; a.k_bs = a.v_bs = (long long)Nk * H * D;
     a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.D = D; a.causal = causal;
     CK(er_attention(a, (cudaStream_t)stream));
+    return ER_OK;
+}
+
+// Experiment / diagnostic switches of the decode kernel.  The product path never reads the environment: everything that is not the
+// production configuration is set explicitly through this entry point (scripts/, tests).  Keys that change the weight packing
+// ("decode_fuse", "gemv_cuda") must be set before er_finalize_weights.
+extern "C" int er_debug_set(er_engine* e, const char* key, int64_t value) {
+    if (!key) return set_err(ER_ERR_INVALID, "null key");
+    const std::string k = key;
+    if (k == "poison_alloc") { g_poison_alloc = (int)value; return ER_OK; }      // process-wide; e may be NULL
+    if (!e) return set_err(ER_ERR_INVALID, "null engine");
+    const int v = (int)value;
+    if (k == "decode_ll") { e->use_ll = v != 0; if (v) e->use_fuse = 0; }
+    else if (k == "decode_fuse") { if (e->finalized && v && !e->wfuse) return set_err(ER_ERR_STATE, "decode_fuse must be set before er_finalize_weights"); e->use_fuse = v != 0; if (v) e->use_ll = 0; }
+    else if (k == "gemv_cuda") { if (e->finalized) return set_err(ER_ERR_STATE, "gemv_cuda must be set before er_finalize_weights"); e->use_mma = (v == 0 && e->C % 256 == 0) ? 1 : 0; e->upstage = e->use_mma ? 8 : er_decode_stage_bytes() / (e->ustride * 2) / 8 * 8; }
+    else if (k == "split_handicap") e->split_handicap = std::max(0, std::min(7, v));
+    else if (k == "xrep") e->xrep = std::max(1, std::min(8, v));
+    else if (k == "hint") e->use_hint = v != 0;
+    else if (k == "poll_rounds") e->poll_rounds = std::max(0, v);
+    else if (k == "pf_dist") e->pf_dist = std::max(0, v);
+    else if (k == "nosync") e->dbg_nosync = v != 0;
+    else if (k == "cache_rows") {       // timing experiments at a chosen context length: pretend the cache holds `value` rows (contents: whatever is there)
+        if (e->cache_rows <= 0 || v < 1 || v >= e->Lmax) return set_err(ER_ERR_INVALID, "cache_rows: prefill first, 1 <= rows < capacity");
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(&e->st->L, &v, 4, cudaMemcpyHostToDevice));
+        e->cache_rows = v; e->cache_rows_stale = false;
+    }
+    else return set_err(ER_ERR_INVALID, "unknown debug key '%s'", key);
     return ER_OK;
 }
 

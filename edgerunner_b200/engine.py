@@ -20,7 +20,8 @@ def _stream():
 
 
 class Engine:
-    def __init__(self, opt, device: torch.device, max_new_tokens: int, max_points: Optional[int] = None, max_tf_rows: int = 0):
+    def __init__(self, opt, device: torch.device, max_new_tokens: int, max_points: Optional[int] = None, max_tf_rows: int = 0,
+                 debug: Optional[Dict[str, int]] = None):
         if not torch.cuda.is_available():
             raise RuntimeError('edgerunner_b200: no CUDA device; this path has no CPU fallback')
         if opt.cond_mode not in ('point', 'point_latent'):
@@ -53,6 +54,11 @@ class Engine:
             _lib.check(self.lib.er_create(C.byref(cfg), C.byref(h)))
         self.h = h
         self._keep = []
+        for k, v in (debug or {}).items():      # experiment switches (scripts/, tests): explicit, never from the environment
+            self.debug_set(k, v)
+
+    def debug_set(self, key: str, value: int):
+        _lib.check(self.lib.er_debug_set(self.h, key.encode(), int(value)))
 
     def __del__(self):
         h, self.h = getattr(self, 'h', None), None

@@ -110,6 +110,13 @@ int64_t er_kv_bytes_per_row(const er_engine* e);         /* K+V bytes one cached
 int32_t er_cache_rows(const er_engine* e);               /* rows currently in the KV cache */
 int64_t er_kernel_launches(const er_engine* e);          /* kernels launched by this engine so far */
 
+/* Experiment / diagnostic switches of the decode kernel (scripts/, tests; the library never reads the environment).  Keys:
+ * "decode_ll", "decode_fuse", "gemv_cuda" (alternative kernel variants; the last two before er_finalize_weights), "split_handicap",
+ * "xrep", "hint", "poll_rounds", "pf_dist" (bytes of L2 run-ahead per CTA), "nosync" (timing diagnostics: grid barriers skipped,
+ * results are garbage), "cache_rows" (pretend the cache holds that many rows; timing at a chosen context length),
+ * "poison_alloc" (process-wide, e may be NULL: fill later allocations with 0xFF).  Unknown key: ER_ERR_INVALID. */
+int er_debug_set(er_engine* e, const char* key, int64_t value);
+
 /* Profiling aid (profiles/): phase timeline of one CTA for one generated token of the next er_decode call. Slots (ns):
  * [0] token start, then for each layer 15 stamps (phase / exchange boundaries, see decode_kernel.cu), then (lm_head end,
  * barrier end); slots [4096 + 16 * cta + k]: the same 15 stamps of layer 5 for every CTA.  n <= 8192. */

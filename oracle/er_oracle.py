@@ -118,12 +118,28 @@ class Oracle:
     def attention(self, q, k, v, causal):
         """q [N,H,D], k/v [M,H,D] -> [N,H,D]; attention.py:47-62 (fp32 softmax; scale 1/sqrt(D))."""
         N, M = q.shape[0], k.shape[0]
-        s = torch.einsum('nhd,mhd->hnm', q, k) / (self.dim_sqrt(q.shape[-1]))
         if causal and N > 1:
             assert N == M
-            s = s + torch.triu(torch.full((N, M), float('-inf')), diagonal=1)
+            return self.attention_rows(q, k, v, 0)
+        s = torch.einsum('nhd,mhd->hnm', q, k) / (self.dim_sqrt(q.shape[-1]))
         p = torch.softmax(s, dim=-1)
         return self.r(torch.einsum('hnm,mhd->nhd', p, v))
+
+    def attention_rows(self, q, k, v, q0, chunk=512):
+        """Causal attention of query rows q0 .. q0+N-1 over keys 0 .. (own position), in row chunks so that the score matrix of a long
+        sequence fits in memory (same arithmetic per row as the one-shot form: fp32 scores + triu(-inf) mask, softmax, P @ V)."""
+        N = q.shape[0]
+        scale = self.dim_sqrt(q.shape[-1])
+        outs = []
+        for c0 in range(0, N, chunk):
+            c1 = min(N, c0 + chunk)
+            m = q0 + c1                                            # keys visible to the last row of the chunk
+            s = torch.einsum('nhd,mhd->hnm', q[c0:c1], k[:m]) / scale
+            rows = torch.arange(q0 + c0, q0 + c1)[:, None]
+            s = s.masked_fill(torch.arange(m)[None, :] > rows, float('-inf'))
+            p = torch.softmax(s, dim=-1)
+            outs.append(torch.einsum('hnm,mhd->nhd', p, v[:m]))
+        return self.r(torch.cat(outs, dim=0))
 
     @staticmethod
     def dim_sqrt(d):
@@ -171,7 +187,7 @@ class Oracle:
         self.kv = torch.zeros(self.layers, 2, max_len, self.H, self.D)
         self.L = 0
 
-    def decoder_rows(self, hidden: torch.Tensor, first_residual_fp16: bool, all_logits: bool = False):
+    def decoder_rows(self, hidden: torch.Tensor, first_residual_fp16: bool, all_logits: bool = False, replay: bool = False):
         """Run ``hidden`` [N,C] (already embeds + positions) through all layers, appending to the KV cache.
 
         first_residual_fp16: decode steps enter layer 0 with an fp16 hidden state, so the first
@@ -189,9 +205,14 @@ class Oracle:
             self.kv[i, 1, L0:L0 + N] = v
             if N == 1:
                 a = self.attention(q, self.kv[i, 0, :L0 + 1], self.kv[i, 1, :L0 + 1], causal=True)
-            else:
-                assert L0 == 0, 'multi-row pass must start from an empty cache (attention.py:40-41)'
+            elif L0 == 0:
                 a = self.attention(q, k, v, causal=True)
+            else:
+                # test-only replay (replay_steps): N consecutive decode steps evaluated together; row j attends to keys 0 .. L0+j.  The
+                # reference itself never does this (attention.py:40-41 asserts N == 1 or N == M); per row it is the same arithmetic as N
+                # calls of step().
+                assert replay, 'multi-row pass must start from an empty cache (attention.py:40-41)'
+                a = self.attention_rows(q, self.kv[i, 0, :L0 + N], self.kv[i, 1, :L0 + N], L0)
             o = self.linear(a.reshape(N, self.C), lp + 'self_attn.out_proj')
             h = h + o
             if first_residual_fp16 and i == 0:
@@ -216,6 +237,18 @@ class Oracle:
         w = self.w
         x = w['mesh_decoder.model.embd.weight'][token] + w['mesh_decoder.model.embed_positions.weight'][self.L]
         return self.decoder_rows(self.r(x)[None], first_residual_fp16=True)
+
+    def replay_steps(self, tokens: List[int], chunk: int = 2048):
+        """Teacher-forced replay of len(tokens) consecutive DECODE steps (fed tokens known in advance), evaluated chunk-wise instead of one
+        by one: identical per-row arithmetic to step() (fp16 entry, fp16 first residual, causal attention over the cache), used by the
+        long-context GPU tests to check every position of a 16k-token stream in a minute instead of hours.  -> logits_pre [n, V]."""
+        w = self.w
+        outs = []
+        for c0 in range(0, len(tokens), chunk):
+            ids = torch.tensor(tokens[c0:c0 + chunk], dtype=torch.long)
+            x = w['mesh_decoder.model.embd.weight'][ids] + w['mesh_decoder.model.embed_positions.weight'][self.L:self.L + len(ids)]
+            outs.append(self.decoder_rows(self.r(x), first_residual_fp16=True, all_logits=True, replay=True))
+        return torch.cat(outs, dim=0)
 
     # ---- HF-4.46.2 _sample restated ---------------------------------------------------------------
     def generate(self, conds: torch.Tensor, num_faces: int = 1000, max_new_tokens: int = 64,

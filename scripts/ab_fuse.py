@@ -1,4 +1,4 @@
-"""GPU (round 2, first call): validate and time the fused decode phases (ER_DECODE_FUSE=1) against the default kernel.
+"""GPU (round 2, first call): validate and time the fused decode phases (er_debug_set decode_fuse=1) against the default kernel.
 The fused kernel sums the K-split partials in a different order (exact fixed-point sum of fp32 partials), so logits agree within the
 fp16-rounding noise band, not bit for bit; each mode must be bit-reproducible run to run.  Prints tokens/s of both at the given lengths."""
 import os, sys, json, time
@@ -11,8 +11,7 @@ from edgerunner_b200.engine import Engine
 
 
 def make(opt, sd, T, fuse):
-    os.environ['ER_DECODE_FUSE'] = str(fuse)
-    eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=T)
+    eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=T, debug={'decode_fuse': fuse})
     eng.load_state_dict(sd)
     return eng
 

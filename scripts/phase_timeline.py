@@ -10,10 +10,11 @@ from edgerunner_b200.engine import Engine
 def main():
     tokens = [int(x) for x in (sys.argv[1].split(',') if len(sys.argv) > 1 else ['200', '8000'])]
     out_path = sys.argv[2] if len(sys.argv) > 2 else 'gpurun_out/phase_timeline.json'
+    dbg = dict((kv.split('=')[0], int(kv.split('=')[1])) for kv in sys.argv[3:])       # er_debug_set switches: key=value ...
     opt = replace(config_defaults['ArAE'], generate_mode='greedy')
     sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0)
     T = max(tokens) + 8
-    eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=T)
+    eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=T, debug=dbg)
     eng.load_state_dict(sd); del sd
     cond = synth.synth_point_cloud(0, opt.point_num)
     res = {}

@@ -1,16 +1,16 @@
-"""Helper for test_gpu_parity.py::test_poisoned_memory_and_repeatability — runs in its own process because ER_POISON_ALLOC is read
-when the engine library makes its first allocation.  Every device allocation starts as 0xFF bytes (NaN in fp16 and fp32): a read of
+"""Helper for test_gpu_parity.py::test_poisoned_memory_and_repeatability — runs in its own process because the allocation poisoning
+(`er_debug_set(NULL, "poison_alloc", 1)`) is process-wide.  Every device allocation starts as 0xFF bytes (NaN in fp16 and fp32): a read of
 anything the engine did not write first turns the logits into NaN; three decodes from the same state must agree bit for bit."""
 import json
 import os
 import sys
 
-os.environ['ER_POISON_ALLOC'] = '1'
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from edgerunner_b200 import synth
 from edgerunner_b200.engine import Engine
+from edgerunner_b200 import _lib
 
 
 def main():
@@ -21,6 +21,7 @@ def main():
         from dataclasses import replace
         from core.options import config_defaults
         opt, T = replace(config_defaults['ArAE'], generate_mode='greedy'), 80
+    _lib.check(_lib.load().er_debug_set(None, b'poison_alloc', 1))
     sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0)
     eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=T + 8, max_points=opt.point_num)
     eng.load_state_dict(sd)
