@@ -13,8 +13,10 @@ core/models.py:215): N GPUs = N requests, no collective on the data path; "scali
 Output: ONE JSON line on rank 0 (see the task contract): value = whole-job tokens/s with inputs resident in HBM,
 e2e = the same through LMM.generate with host buffers (H2D of the cloud and D2H of the ids inside the timed region),
 roofline = algorithmic HBM bytes of the decode kernel / its CUDA-event duration vs MEASURED_PEAKS.json,
-cpu_baseline = the CPU oracle (a port of the reference algorithm) timed on this box's host cores on a bounded sample.
-`--impl reference` times that CPU port alone (the Python reference cannot travel to the GPU box).
+cpu_baseline = the REFERENCE's own modules (oracle/_ref/py, copied by `make -C oracle refpy`; kind "reference") on this box's host
+cores on a bounded sample (cached decode steps at three context lengths, extrapolated to the 16k request with t(L) = a + bL); if
+that copy is absent, the CPU oracle port (kind "port").  reference_gpu = the same modules on the GPU exactly as infer.py runs them
+(model.half() + autocast(fp16) + flash-attn), the ">= 10x" denominator.  `--impl reference` prints the CPU reference arm alone.
 """
 
 import argparse
@@ -116,19 +118,39 @@ def thread_candidates():
     return sorted({c for c in (4, 8, 16, 32, 64, n) if c <= n})
 
 
-def cpu_port_tokens_per_s(opt, sd, seconds_budget, threads):
-    """The CPU oracle (fp32 port of the reference's CPU path: same ops, naive attention, fp32) on a bounded sample:
-    decode steps from a prefilled 2050-row cache."""
+def ref_leg(kind, steps, warmup, tokens, tiny=False, timeout=900):
+    """Run oracle/ref_leg.py (the reference's own modules) in its own process -> dict | None.  Its package is called `core` like this
+    repository's drop-in mirror, so it cannot share a process with the product path."""
+    script = os.path.join(REPO, 'oracle', 'ref_leg.py')
+    if not os.path.isdir(os.path.join(REPO, 'oracle', '_ref', 'py', 'core')):
+        return None
+    cmd = [sys.executable, script, kind, '--steps', str(steps), '--warmup', str(warmup), '--tokens', str(tokens)] + (['--tiny'] if tiny else [])
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'TORCHELASTIC_RUN_ID'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        return {'error': f'reference {kind} leg timed out after {timeout}s'}
+    for line in out.stdout.splitlines():
+        if line.startswith('REF_LEG '):
+            return json.loads(line[8:])
+    return {'error': (out.stderr or out.stdout)[-400:]}
+
+
+def cpu_port_tokens_per_s(opt, seconds_budget, threads):
+    """Fallback when oracle/_ref/py is absent: the CPU oracle (fp32 port of the reference's CPU path) on a bounded sample."""
     from edgerunner_b200 import synth
     from oracle.er_oracle import Oracle     # bench.py's cpu_baseline leg is allowed to execute the oracle
     torch.set_num_threads(min(threads, 32))
+    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0)
     orc = Oracle(opt, sd, mode='fp32')
+    del sd
     cond = synth.synth_point_cloud(0, opt.point_num)
     ce = orc.encode_cond(cond, 4000)[0]
     n_max = 256 + 32
     orc.reset_cache(ce.shape[0] + 1 + n_max + 1)
     orc.prefill(ce, [opt.bos_token_id])
-    L0 = orc.L
     state = {'tok': 5}
 
     def one():
@@ -146,55 +168,38 @@ def cpu_port_tokens_per_s(opt, sd, seconds_budget, threads):
                    f'prefill/encoder excluded; short-L sample flatters the CPU'
 
 
+def cpu_baseline_leg(args, opt, steps=1, warmup=1):
+    """-> the `cpu_baseline` object: the reference's own CPU path when its copy travelled to this box, else the oracle port."""
+    r = ref_leg('cpu', steps, warmup, tokens=2 if not args.tiny else 4, tiny=args.tiny)
+    if r is not None and 'error' not in r:
+        return {'value': r['tok_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'reference', 'sample': r['sample'] + f"; {r['path']}; "
+                f"{r['threads']} of {r['host_threads']} host threads; per-window tokens/s {r['windows_tok_s']}; {r['model']}",
+                'extrapolated_request_s': r['extrapolated_request_s'], 'sample_s_per_step': r['sample_s_per_step'], 'windows_tok_s': r['windows_tok_s']}
+    threads = os.cpu_count() or 1
+    v, used, sample = cpu_port_tokens_per_s(opt, 15.0, threads)
+    why = 'oracle/_ref/py absent' if r is None else 'reference leg failed: ' + r['error']
+    return {'value': v, 'unit': UNIT, 'cores': used, 'kind': 'port', 'sample': sample + f' ({why}; thread count picked from {thread_candidates()} of {threads} host threads)'}
+
+
 def run_reference_arm(args):
-    """`--impl reference`: the reference's CPU implementation of the path, as the oracle port, on the host cores."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores (oracle/_ref/py when it travelled with
+    the snapshot, else the oracle port), same metric / unit / config as our arm.  Each step = one bounded sample of the 16k request
+    (see oracle/ref_leg.py); value = 16000 tokens / the extrapolated request time.  Rank 0 alone runs it (the host cores are shared by
+    all replicas: CPU throughput does not grow with --gpus)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from edgerunner_b200 import synth
     opt, wl, T, nf = workload(args)
-    threads = os.cpu_count() or 1
-    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0)
-    from oracle.er_oracle import Oracle
-    torch.set_num_threads(min(threads, 32))
-    orc = Oracle(opt, sd, mode='fp32')
-    del sd
-    cond = synth.synth_point_cloud(0, opt.point_num)
-    ce = orc.encode_cond(cond, nf)[0]
-    per_step = 24 if not args.tiny else 16
-    total = (args.steps + args.warmup) * per_step
-    orc.reset_cache(ce.shape[0] + 1 + total + 2 + 3 * len(thread_candidates()) + 4)
-    orc.prefill(ce, [opt.bos_token_id])
-    L0 = orc.L
-    tok = 5
-
-    def one_step():
-        nonlocal tok
-        for _ in range(per_step):
-            pre = orc.step(tok)
-            tok = 6 + int(torch.argmax(pre[0, 6:]))
-
-    def one_token():
-        nonlocal tok
-        pre = orc.step(tok)
-        tok = 6 + int(torch.argmax(pre[0, 6:]))
-
-    host_threads = threads
-    threads = pick_threads(one_token, thread_candidates())
-    for _ in range(args.warmup):
-        one_step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one_step()
-    dt = time.perf_counter() - t0
-    v = args.steps * per_step / dt
-    sample = (f'{per_step} greedy decode tokens per step from a prefilled {L0}-row cache (cache grows to {orc.L}); fp32 torch CPU ops, '
-              f'{threads} threads (best of {thread_candidates()} on {host_threads} host threads); CPU port of the reference path (oracle/er_oracle.py) — the Python reference cannot travel to this box')
+    cb = cpu_baseline_leg(args, opt, steps=args.steps, warmup=args.warmup)
+    v = cb['value']
+    ms = cb.get('sample_s_per_step', 0.0) * 1e3
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': {'workload': wl, 'sample': sample},
-        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': {'workload': wl, 'tokens_per_step_per_gpu': T, 'prefix_rows': opt.num_cond_tokens + 1,
+                                        'sample': cb['sample'], 'note': 'ms_per_step is the measured bounded sample; value extrapolates it to the full request; '
+                                        'the host cores are shared by all replicas, so the CPU arm does not scale with --gpus'},
+        'cpu_baseline': cb,
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }), flush=True)
 
@@ -210,6 +215,8 @@ def main():
     ap.add_argument('--tiny', action='store_true', help='debug: tiny model')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-reference-gpu', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=3, help='timed LMM.generate calls of the e2e leg (bounded: each is a full 16k request)')
     args = ap.parse_args()
 
     if args.impl == 'reference':
@@ -230,9 +237,13 @@ def main():
     from edgerunner_b200 import synth
 
     opt, wl, T, nf = workload(args)
-    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0)
-    model = LMM(opt)
-    model.load_state_dict(sd, strict=True)
+    # synthetic checkpoint straight into fp16 (model.half() of infer.py:56 is exact on it); the module is built on the meta device and
+    # the tensors are assigned, so that N ranks do not each run a 766 M-parameter random init + a 3 GB fp32 copy on the shared host
+    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
+    with torch.device('meta'):
+        model = LMM(opt)
+    model.load_state_dict(sd, strict=True, assign=True)
+    del sd
     model = model.half().eval().to(dev)
     tokenizer, _ = get_tokenizer(opt)
     eng = model.get_engine(max_new_tokens=T)
@@ -298,16 +309,17 @@ def main():
                 meshes, toks = model.generate(c, num_faces=nf, max_new_tokens=T, tokenizer=tokenizer, clean=True)   # D2H of ids inside
             return toks[0]
         import contextlib, io
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
         with contextlib.redirect_stdout(io.StringIO()):
             step_e2e()
             barrier()
             t0 = time.perf_counter()
-            for _ in range(args.steps):
+            for _ in range(e2e_steps):
                 toks = step_e2e()
             torch.cuda.synchronize()
             dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {'value': world * args.steps * len(toks) / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(cond_host.numel() * 4),
-               'd2h_bytes_per_step': int(len(toks) * 4 + 4), 'ms_per_step': dt / args.steps * 1e3,
+        e2e = {'value': world * e2e_steps * len(toks) / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(cond_host.numel() * 4),
+               'd2h_bytes_per_step': int(len(toks) * 4 + 4), 'ms_per_step': dt / e2e_steps * 1e3, 'steps': e2e_steps,
                'api': 'core.models.LMM.generate(cond, num_faces, max_new_tokens, tokenizer, clean=True) incl. meto detokenize + mesh clean-up'}
 
     if world > 1:
@@ -337,10 +349,18 @@ def main():
                 'peak_source': peak_src, 'frac_of_nominal_8TBs': achieved / 8000.0,
                 'decode_only_tokens_per_s': (n_tok - 1) / (dec_ms_avg / 1e3), 'traffic_note': traffic_note}
     cpu = None
-    if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, used, sample = cpu_port_tokens_per_s(opt, sd, 15.0, threads)
-        cpu = {'value': v, 'unit': UNIT, 'cores': used, 'kind': 'port', 'sample': sample + f' (thread count picked from {thread_candidates()} of {threads} host threads)'}
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_baseline_leg(args, opt)
+    ref_gpu = None
+    if not args.no_reference_gpu and world == 1:
+        del model, eng
+        torch.cuda.empty_cache()
+        r = ref_leg('gpu', 2, 1, tokens=32 if not args.tiny else 8, tiny=args.tiny, timeout=600)
+        if r is not None and 'error' not in r:
+            ref_gpu = {'value': r['tok_s'], 'unit': UNIT, 'kind': 'reference', 'path': r['path'], 'windows_tok_s': r['windows_tok_s'], 'sample': r['sample'],
+                       'model': r['model'], 'ours_over_reference_gpu': value / r['tok_s']}
+        else:
+            ref_gpu = {'unavailable': 'oracle/_ref/py absent' if r is None else r['error']}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16',
@@ -348,7 +368,7 @@ def main():
         'config': {'workload': wl, 'tokens_per_step_per_gpu': n_tok, 'prefix_rows': L0, 'parallelism': f'replicas x{world}',
                    'l2': 'inputs larger than L2: 1.36 GB weights + up to 2.66 GB KV cache streamed per token vs 126 MB L2',
                    'weights': 'seeded synthetic, fp16 (edgerunner_b200.synth)'},
-        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'reference_gpu': ref_gpu,
     }
     print(json.dumps(line), flush=True)
 

@@ -194,13 +194,11 @@ cudaError_t er_attention(const er::AttnArgs& a, cudaStream_t stream) {
     dim3 grid((a.Nq + AQ - 1) / AQ, a.H, a.B);
     if (a.D == 96) {
         const int smem = (AQ + 4 * AK) * (96 * 2 + 16);
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(attention_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+        cudaFuncSetAttribute(attention_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per call: per-device state, microseconds
         attention_kernel<96><<<grid, ATT_THREADS, smem, stream>>>(a);
     } else if (a.D == 64) {
         const int smem = (AQ + 4 * AK) * (64 * 2 + 16);
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+        cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attention_kernel<64><<<grid, ATT_THREADS, smem, stream>>>(a);
     } else {
         return cudaErrorInvalidValue;

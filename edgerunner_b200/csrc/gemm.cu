@@ -147,12 +147,14 @@ cudaError_t er_gemm(const er::GemmArgs& g, cudaStream_t stream) {
     using namespace er;
     if (g.M <= 0 || g.N <= 0) return cudaSuccess;
     if ((g.K & 7) || (g.lda & 7) || (g.ldw & 7)) return cudaErrorInvalidValue;
-    static bool attr = false;
+    static bool attr[64] = {};                 // per DEVICE: the attribute belongs to the function on the current device's context
     const int smem = STAGES * (BM + BN) * 64;
-    if (!attr) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
     gemm_f16_kernel<<<grid, GEMM_THREADS, smem, stream>>>(g);

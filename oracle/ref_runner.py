@@ -181,14 +181,26 @@ def prefix_embeds(model, cond, num_faces):
 
 
 @torch.no_grad()
-def decode_window(model, L, n_steps, warm=2, autocast=True):
-    """Time n_steps cached decode steps of the reference decoder from a FABRICATED cache of L rows (random K/V in the model's dtype:
-    timing only) -> seconds per token.  This is ShapeOPT.forward with past_key_values, exactly what HF's loop calls per token."""
+def make_past(model, L, randn=True):
+    """A FABRICATED cache of L rows in the model's dtype (timing only): the tuple-of-tuples layout ShapeOPTDecoder returns
+    (modeling_opt.py:400-426), 24 x (K, V) each [1, H, L, D]."""
+    p = next(model.mesh_decoder.parameters())
+    H, D, NL = model.opt.num_heads, model.opt.hidden_dim // model.opt.num_heads, model.opt.num_layers
+    mk = (lambda: torch.randn(1, H, L, D, device=p.device, dtype=p.dtype) * 0.1) if randn else (lambda: torch.zeros(1, H, L, D, device=p.device, dtype=p.dtype))
+    return tuple((mk(), mk()) for _ in range(NL))
+
+
+@torch.no_grad()
+def decode_window(model, L, n_steps, warm=2, autocast=True, past=None):
+    """Time n_steps cached decode steps of the reference decoder from a cache of L rows (fabricated unless `past` is given) -> seconds
+    per token.  One step = ShapeOPT.forward with past_key_values (modeling_opt.py:464-517: 24 x [q/k/v Linear, torch.cat of the whole
+    cache :191-192, attention(), out_proj, LN, fc1, ReLU, fc2, LN], lm_head) + the argmax and its host sync, i.e. what HF's loop runs
+    per generated token."""
     dec = model.mesh_decoder
     p = next(dec.parameters())
-    dev, dt = p.device, p.dtype
-    H, D, NL = model.opt.num_heads, model.opt.hidden_dim // model.opt.num_heads, model.opt.num_layers
-    past = tuple((torch.randn(1, H, L, D, device=dev, dtype=dt) * 0.1, torch.randn(1, H, L, D, device=dev, dtype=dt) * 0.1) for _ in range(NL))
+    dev = p.device
+    if past is None:
+        past = make_past(model, L)
     ids = torch.full((1, 1), 100, dtype=torch.long, device=dev)
     am = torch.ones((1, L + 1), dtype=torch.long, device=dev)
 
