@@ -42,7 +42,7 @@ constexpr int kConsumerWarps = ER_CONSUMER_WARPS;   // 8 or 16
 constexpr int kUnitDiv = 1;                       // a weight unit is one K-slice of C fp16
 static_assert(kConsumerWarps == 8, "the GEMV consumers assume 8 warps (one K-eighth / one unit per warp)");
 constexpr int kConsumers = kConsumerWarps * 32;   // 256 compute threads
-constexpr int kThreads = kConsumers + 64;         // + one producer warp + one L2 run-ahead warp
+constexpr int kThreads = kConsumers + 96;         // + producer warp + L2 run-ahead warp + accumulator janitor warp
 constexpr int HD = 96;                            // decoder head_dim (ArAE: 1536 / 16)
 constexpr int HV = HD / 8;                        // 16-byte vectors per head row (12)
 constexpr int kStageBytes = 24704;                // 8 padded weight units of (1536 + 8) fp16; also holds 4 K blocks / 128 V rows
@@ -50,7 +50,7 @@ constexpr int kKVChunk = 24576;                   // bytes per stage of the K / 
 constexpr int kMaxStages = 8;
 constexpr int kKBlockBytes = HV * 32 * 16;        // 6144: one 32-key block of the blocked K cache
 constexpr int kHoStride = HD + 8;                 // fused phases: fp16 per (head, row) unit of the per-head out_proj copy (208 B)
-constexpr int kHoUnitsPerStage = kStageBytes / (kHoStride * 2);   // 118
+constexpr int kHoUnitsPerStage = 112;            // (head, row) units per stage: 14 groups of 8 (23,296 B <= kStageBytes)
 constexpr int kMaxUnits = 64 * kUnitDiv;          // weight units a CTA owns in one phase
 constexpr int kPartStride = kMaxUnits + 1;        // lane-partial matrix [32][kPartStride] (odd stride: conflict-free both ways)
 
@@ -170,27 +170,6 @@ __device__ __forceinline__ uint4 ll_load2(const unsigned long long* ptr) {   // 
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(ptr) : "memory");
     return make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
 }
-// Arrival hint.  148 CTAs x 256 threads polling every word of a 24 KB vector delay the very stores they wait for (measured: 3.3 us
-// from the last publish to the last fetch).  So each publishing warp also adds its word count to a per-(vector, layer) counter
-// with a relaxed reduction; readers spin on that ONE word with one lane per warp and only then fetch the vector.  The counter
-// carries no ordering (no fence): the flags in the data words remain the only thing correctness rests on, a fetch that comes
-// too early simply retries the words still missing.  Counters are zeroed by the host before each launch; after the launch's
-// (iter+1)-th token the layer's counter reads (iter+1) * words.
-__device__ __forceinline__ void hint_add(unsigned* counter, unsigned n) {
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(n) : "memory");
-}
-__device__ __forceinline__ void hint_wait(const unsigned* counter, unsigned target) {   // all lanes of the warp call it
-    if ((threadIdx.x & 31) == 0) {
-        int spins = 0;
-        for (;;) {
-            unsigned v;
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if ((int)(v - target) >= 0) break;
-            if (++spins > kSpinLimit) asm volatile("trap;");
-        }
-    }
-    __syncwarp();
-}
 // Poll up to N words per thread (bit j of `mask`: word j wanted).  Must be called by ALL lanes of a warp (mask 0 = nothing wanted).
 // All loads of a round are in flight together.  After `rounds` unsuccessful rounds the warp stops hammering the L2 with 32 x N
 // loads per round: one lane that still misses a word spins on that word alone and the others wait for it at a warp barrier.
@@ -244,33 +223,14 @@ __device__ __forceinline__ void ll_poll2(uint32_t (&out)[2 * N], uint32_t mask, 
         }
     }
 }
-// fetch a whole published fp16 vector (ndw double-words = 4 fp16 each, <= 6 per thread) into shared memory
-__device__ __noinline__ void ll_fetch(const unsigned long long* src, uint32_t dst_s, int ndw, uint32_t flag, int rounds, const unsigned* hint, unsigned target) {
-    const int tid = threadIdx.x;
-    if (hint) hint_wait(hint, target);
-    uint32_t w[12];
-    uint32_t mask = 0;
-#pragma unroll
-    for (int j = 0; j < 6; j++) mask |= (tid + kConsumers * j < ndw) ? (1u << j) : 0u;
-    const uint32_t want = mask;
-    ll_poll2<6>(w, mask, flag, rounds, [&](int j) { return src + 2 * (tid + kConsumers * j); });
-#pragma unroll
-    for (int j = 0; j < 6; j++)
-        if ((want >> j) & 1u)
-            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(dst_s + (uint32_t)(tid + kConsumers * j) * 8), "r"(w[2 * j]), "r"(w[2 * j + 1]) : "memory");
-}
 // a consumer thread holding the fp16 output of row (r0 + tid / nu_row) on threads with tid % nu_row == 0 publishes row pairs;
 // every lane of a publishing warp must call it
-__device__ __forceinline__ void ll_publish_rows(unsigned long long* dst, int r0, int nu, int nu_row, __half hv, uint32_t flag, unsigned* hint) {
+__device__ __forceinline__ void ll_publish_rows(unsigned long long* dst, int r0, int nu, int nu_row, __half hv, uint32_t flag) {
     const uint32_t mine = __half_as_ushort(hv);
     const uint32_t other = __shfl_down_sync(0xffffffffu, mine, nu_row);
     const int tid = threadIdx.x;
     const bool wr = tid < nu && (tid % (2 * nu_row)) == 0;
     if (wr) ll_store(dst + ((r0 + tid / nu_row) >> 1), mine | (other << 16), flag);
-    if (hint) {
-        const unsigned n = __popc(__ballot_sync(0xffffffffu, wr));
-        if ((tid & 31) == 0 && n) hint_add(hint, n);
-    }
 }
 
 // the same barrier in two halves: work placed between them overlaps the counter round trip
@@ -316,6 +276,21 @@ __device__ __forceinline__ void prof_all(const DecodeParams& p, int k, bool on) 
 __device__ __forceinline__ RowRange cta_rows(int R) { return cta_rows_of(R, blockIdx.x, gridDim.x); }
 __device__ __forceinline__ bool attn_range(int H, int S, int split_handicap, int L, AttnRange& a) {
     return attn_range_of(H, S, split_handicap, L, blockIdx.x, a);
+}
+
+// P1 rows of this CTA in the 3C-row qkv matrix.  Five-exchange layer: an even 148-way split.  Tensor-parallel layer: CTA (head h, split s)
+// computes 288 / S rows of ITS head (q96 | k96 | v96; the host picks S in {6, 9, 12}: a range never straddles two matrices, <= 48 rows).
+template <bool FUSE>
+__device__ __forceinline__ RowRange p1_rows(const DecodeParams& p) {
+    if (!FUSE) return cta_rows(3 * p.C);
+    RowRange rr{0, 0};
+    const int S = p.S, b = (int)blockIdx.x;
+    if (b >= p.H * S) return rr;
+    const int h = b / S, s = b % S, per = 3 * HD / S;
+    const int j0 = per * s, m = j0 / HD;
+    rr.r0 = m * p.C + h * HD + (j0 - m * HD);
+    rr.r1 = rr.r0 + per;
+    return rr;
 }
 
 struct Ring {          // passed by value (registers): shared-space addresses of the stage data and the mbarrier arrays
@@ -373,13 +348,13 @@ __device__ __forceinline__ void walk_jobs(const DecodeParams& p, const int t0, i
     const uint32_t wchunk = (uint32_t)(p.upstage * ub);
     const int nuf = F / C;
     const size_t UL = (size_t)4 * C + 2 * (size_t)F;
-    const RowRange rq = cta_rows(3 * C), rc = cta_rows(C), rf = cta_rows(F), rv = cta_rows(V);
+    const RowRange rq = p1_rows<FUSE>(p), rc = cta_rows(C), rf = cta_rows(F), rv = cta_rows(V);
     for (int pass = 0; pass < n_fwd && ok; ++pass, ++L) {
         AttnRange a;
         const bool has_attn = attn_range(H, S, handicap, L, a);
         for (int layer = 0; layer < layers && ok; ++layer) {
             const __half* wl = wdec + (size_t)layer * UL * ustride;
-            ok = job(wl + (size_t)rq.r0 * ustride, (size_t)(rq.r1 - rq.r0) * ub, wchunk, 0);
+            if (rq.r1 > rq.r0) ok = job(wl + (size_t)rq.r0 * ustride, (size_t)(rq.r1 - rq.r0) * ub, wchunk, 0);
             if (ok && has_attn) {
                 const __half* kbase = kc + (((size_t)layer * H + a.h) * nkb + a.b0) * (size_t)(HV * 256);
                 ok = job(kbase, (size_t)(a.b1 - a.b0) * kKBlockBytes, kKVChunk, layer == 0 ? pass : 0);
@@ -627,27 +602,150 @@ __device__ __forceinline__ float reduce_rows(uint32_t part_s, int n_units, int n
     return s;
 }
 
-// ---- fused phases (experimental, FUSE = true): K-split GEMVs reduced in L2 instead of exchanged -------------------------------------------
-// Two of the five exchanges of a layer exist only because a GEMV's input is spread over all CTAs:
-//   * out_proj needs the whole attention vector.  Its K dimension is the concatenation of the heads, so the S CTAs of head h (which
-//     hold that head's output after a 9-CTA flagged-word merge) multiply it by the matching 96 columns of Wo, each for ~C/S output
-//     rows, and add the fp32 partial rows into a fixed-point accumulator (16 addends per row);
-//   * fc2 needs the whole fc1 output.  A CTA multiplies ITS OWN 40-42 fc1 outputs by the matching columns of W2 (stored transposed,
-//     one unit per column) and adds the 1536 partial sums into a second accumulator (148 addends per element).
-// The accumulators are u64 fixed point (2^-40): integer addition is associative, so the result does not depend on arrival order
-// and runs stay bit-reproducible.  Measured beforehand (scripts/microbench/atomic_reduce.cu): +1.5 us on the barrier that follows
-// instead of a 3 us exchange.  Each accumulator has two copies used by alternating layers; the copy a layer has finished with is
-// zeroed, slice by slice, after the next layer's first barrier.
-constexpr float kFixScale = 1099511627776.0f;      // 2^40
-constexpr float kFixInv = 1.0f / 1099511627776.0f;
-__device__ __forceinline__ void fix_add(unsigned long long* acc, float v) {
-    const long long q = __float2ll_rn(v * kFixScale);            // exact: power-of-two scaling of a 24-bit significand
-    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc), "l"(q) : "memory");
+// ---- tensor-parallel layer (FUSE = true): K-split GEMVs whose partial sums meet in L2, arrival counted INSIDE the data words ----
+// Measured on the B200 (profiles/r02_diag_runahead_nosync_fuse.json): with the grid barriers switched off the default kernel runs a
+// layer in 16 us at L = 2050, with them in 28 us — five exchanges of ~2.4 us each (drain stores for the release, atomic, polled
+// acquire, then fetch the vector: four dependent L2 trips), none of which can overlap anything because the layer is one dependency
+// chain.  This variant cuts the layer the way tensor-parallel training cuts it, so that a vector only crosses CTAs where it must:
+//   * q/k/v rows of head h are computed BY the S CTAs that attend for head h (288 rows / S each): q, the new k and the new v travel
+//     as flagged words among S CTAs (no storm: 9 pollers per word), no grid barrier;
+//   * out_proj is row-parallel per head: after an S-way flagged-word merge every CTA of the head multiplies the head's output by ITS
+//     rows of the head's 96 out_proj columns (tensor cores) and adds the partial rows into an accumulator in L2;
+//   * fc2 is row-parallel over fc1's column split: a CTA multiplies ITS 41-42 fc1 outputs by the matching columns of W2 (stored
+//     transposed, one unit per column; ldmatrix.trans + mma.m16n8k8) and adds the 1536 partial sums into a second accumulator.
+// The accumulators are u64 words: bits 0..55 hold a biased fixed-point sum (2^-32; integer addition is associative, so the result
+// is independent of arrival order and runs stay bit-reproducible), bits 56..63 COUNT the addends.  A reader polls the words it needs
+// until the count is complete: the data is its own flag — no release fence, no barrier, no separate fetch.  Two head-local
+// exchanges + two L2 all-reduces per layer, zero grid barriers (one per token remains, after lm_head).
+// Accumulator reuse: reduction k uses copy k & 3, and EVERY CTA adds to every word of every reduction (a CTA with nothing to add adds
+// zero).  A CTA that has seen reduction k complete knows every CTA has finished reading reduction k-2 (everybody reads k-2 before adding
+// to k-1, and k-1 completed before k could), so its janitor warp zeroes this CTA's slice of copy (k+2) & 3 and fences; the CTA adds to
+// reduction k+1 only after its janitor has caught up.  Whoever adds to reduction k+2 has seen k+1 complete, i.e. every CTA added to
+// k+1, i.e. every slice of copy (k+2) & 3 was zeroed at L2 before.
+constexpr float kFixScale = 4294967296.0f;         // 2^32
+constexpr float kFixInv = 1.0f / 4294967296.0f;
+constexpr unsigned long long kFixBias = 1ull << 47;        // every addend is non-negative and < 2^48: 255 of them cannot carry into the count
+constexpr unsigned long long kFixOne = 1ull << 56;
+constexpr unsigned long long kFixMask = (1ull << 56) - 1;
+__device__ __forceinline__ void fix_add_cnt(unsigned long long* acc, float v) {
+    v = fminf(fmaxf(v, -32000.f), 32000.f);                 // also maps NaN to a number: the count must always arrive
+    const long long q = __float2ll_rn(v * kFixScale);       // exact for |v| >= 2^-9, rounded to 2^-32 below
+    const unsigned long long w = kFixOne + kFixBias + (unsigned long long)q;
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc), "l"(w) : "memory");
 }
-__device__ __forceinline__ float fix_get(const unsigned long long* acc) {
-    long long q;
-    asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(q) : "l"(acc));
-    return __ll2float_rn(q) * kFixInv;
+// thread polls 8 consecutive accumulator words until each has `target` addends; -> the 8 sums.  All lanes of a warp must call it
+// (act = false: nothing wanted); the exit is warp-uniform.  nosync (diagnostics): take whatever is there.
+__device__ __forceinline__ void acc_poll8(const unsigned long long* acc, const int target, float* out, const bool act, const bool nosync) {
+    const unsigned long long bias = (unsigned long long)target * kFixBias;
+    int spins = 0;
+    for (;;) {
+        bool ok = true;
+        if (act) {
+            unsigned long long w[8];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w[2 * j]), "=l"(w[2 * j + 1]) : "l"(acc + 2 * j) : "memory");
+#pragma unroll
+            for (int e = 0; e < 8; e++) ok = ok && ((int)(w[e] >> 56) == target);
+            if (ok || nosync) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) out[e] = __ll2float_rn((long long)((w[e] & kFixMask) - bias)) * kFixInv;
+            }
+        }
+        if (__all_sync(0xffffffffu, ok) || nosync) break;
+        if (++spins > kSpinLimit) asm volatile("trap;");
+    }
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_1688(float* d, uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+
+// out_proj, row-parallel per head: this CTA's n rows of the head's 96 out_proj columns (units of HD fp16 padded to kHoStride) times the
+// head's merged attention output o16[96].  A group of 8 units is the B operand of 6 k16 steps; the full K lives in one warp, so there
+// is no cross-warp reduction: lanes 0..3 of the warp that owns a group hold its 8 outputs.  Warp w takes groups w, w+8, ... of a stage.
+__device__ __forceinline__ Cursor outproj_job_mma(const Ring r, Cursor cur, const int n, const uint32_t o16_s, const uint32_t out_s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & 3;
+    uint32_t xa[HD / 16][2];
+#pragma unroll
+    for (int s = 0; s < HD / 16; s++) { xa[s][0] = lds_u32(o16_s + (uint32_t)(16 * s + 2 * t) * 2); xa[s][1] = lds_u32(o16_s + (uint32_t)(16 * s + 8 + 2 * t) * 2); }
+    const uint32_t row_off = (uint32_t)(lane & 7) * (kHoStride * 2) + (uint32_t)(lane >> 3) * 16;
+    const int nch = (n + kHoUnitsPerStage - 1) / kHoUnitsPerStage;
+    for (int c = 0; c < nch; ++c, cur.advance(r.nstage)) {
+        mbar_wait(r.fullb(cur.stage), cur.parity);
+        const int here = min(kHoUnitsPerStage, n - c * kHoUnitsPerStage);
+        const int ngrp = (here + 7) >> 3;
+        for (int gi = warp; gi < ngrp; gi += kConsumerWarps) {
+            const uint32_t base = r.stage(cur.stage) + (uint32_t)gi * (8 * kHoStride * 2) + row_off;
+            uint32_t b[HD / 32][4];
+#pragma unroll
+            for (int i = 0; i < HD / 32; i++) ldmatrix_x4(base + i * 64, b[i][0], b[i][1], b[i][2], b[i][3]);
+            float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < HD / 32; i++) {
+                mma_16816(d0, xa[2 * i][0], xa[2 * i][1], b[i][0], b[i][1]);
+                mma_16816(d1, xa[2 * i + 1][0], xa[2 * i + 1][1], b[i][2], b[i][3]);
+            }
+            if (lane < 4) {     // row 0 of D (all 16 rows carry the same x): columns 2t, 2t+1 = units 8 gi + 2t (+1)
+                const int u = c * kHoUnitsPerStage + gi * 8 + 2 * t;
+                if (u < n) sts32(out_s + (uint32_t)u * 4, d0[0] + d1[0]);
+                if (u + 1 < n) sts32(out_s + (uint32_t)(u + 1) * 4, d0[1] + d1[1]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
+    }
+    return cur;
+}
+
+// fc2, row-parallel over fc1's column split: y2_partial[C] = sum over this CTA's nr fc1 outputs h[j] of column j of W2.  The columns
+// arrive as transposed units (one column = C fp16 + pad, 8 per stage).  ldmatrix.trans turns an 8-column x 8-row patch into the A
+// fragment of mma.m16n8k8 (output rows x columns-as-k); the B operand carries h in its column 0.  Warp w owns output rows
+// [w C/8, (w+1) C/8): MT = C/128 m-tiles of 16 rows, accumulated in registers over the whole phase.
+template <int MT>
+__device__ __forceinline__ Cursor fc2_job_mma(const Ring r, Cursor cur, const int nr, const int C, const int ustride, const uint32_t h_s, const uint32_t out_s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ubytes = ustride * 2;
+    const int ib = warp * (C >> 3);
+    float acc[MT][4];
+#pragma unroll
+    for (int m = 0; m < MT; m++) { acc[m][0] = 0.f; acc[m][1] = 0.f; acc[m][2] = 0.f; acc[m][3] = 0.f; }
+    const uint32_t lane_off = (uint32_t)(lane & 7) * ubytes + (uint32_t)(ib + (lane >> 3) * 8) * 2;
+    const int nch = (nr + 7) >> 3;
+    for (int c = 0; c < nch; ++c, cur.advance(r.nstage)) {
+        mbar_wait(r.fullb(cur.stage), cur.parity);
+        const uint32_t b0 = (g == 0) ? lds_u32(h_s + (uint32_t)(8 * c + 2 * t) * 2) : 0u;      // h is zero-padded to a multiple of 8
+        const uint32_t base = r.stage(cur.stage) + lane_off;
+#pragma unroll
+        for (int m2 = 0; m2 < MT / 2; m2++) {
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4_trans(base + m2 * 64, a0, a1, a2, a3);
+            mma_1688(acc[2 * m2], a0, a1, b0);
+            mma_1688(acc[2 * m2 + 1], a2, a3, b0);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
+    }
+    if (t == 0) {          // column 0 of D
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+            sts32(out_s + (uint32_t)(ib + 16 * m + g) * 4, acc[m][0]);
+            sts32(out_s + (uint32_t)(ib + 16 * m + g + 8) * 4, acc[m][2]);
+        }
+    }
+    return cur;
+}
+__device__ __noinline__ Cursor fc2_job(const Ring r, Cursor cur, const int nr, const int C, const int ustride, const uint32_t h_s, const uint32_t out_s) {
+    if (C == 1536) return fc2_job_mma<12>(r, cur, nr, C, ustride, h_s, out_s);
+    if (C == 1024) return fc2_job_mma<8>(r, cur, nr, C, ustride, h_s, out_s);
+    if (C == 768) return fc2_job_mma<6>(r, cur, nr, C, ustride, h_s, out_s);
+    if (C == 512) return fc2_job_mma<4>(r, cur, nr, C, ustride, h_s, out_s);
+    return fc2_job_mma<2>(r, cur, nr, C, ustride, h_s, out_s);      // C == 256
 }
 
 // ---- fused residual + LayerNorm --------------------------------------------------------------------------------------------------------------
@@ -672,28 +770,27 @@ __device__ __forceinline__ void unpack8(const uint4 u, float* f) {
     t = h2f2(u.z); f[4] = t.x; f[5] = t.y;
     t = h2f2(u.w); f[6] = t.x; f[7] = t.y;
 }
-__device__ __forceinline__ void residual_layer_norm(uint32_t xres_s, uint32_t x16_s, const __half* y, const unsigned long long* yll, uint32_t flag,
-                                                 int rounds, const unsigned* hint, unsigned target, bool round_first, const LnParams lp, int C, float inv_c, float* red,
-                                                 const unsigned long long* yacc = nullptr, const __half* ybias = nullptr) {
+// yacc != nullptr (tensor-parallel layer): y = fp16(all-reduced sum + bias); the sum is polled from the counting accumulator.
+__device__ __forceinline__ void residual_layer_norm(uint32_t xres_s, uint32_t x16_s, const __half* y, bool round_first, const LnParams lp, int C, float inv_c,
+                                                 float* red, const unsigned long long* yacc = nullptr, const int target = 0,
+                                                 const __half* ybias = nullptr, const bool nosync = false) {
     const int t = threadIdx.x;
     const bool act = t < (C >> 3);
     float v[8];
     float s = 0.f, q = 0.f;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    if (yll && hint) hint_wait(hint, target);
-    if (yll) ll_poll2<2>(w, act ? 3u : 0u, flag, rounds, [&](int j) { return yll + 4 * t + 2 * j; });
-    if (act) {
-        float yv[8];
-        if (yacc) {                       // fused phases: y = fp16(sum of the K-split partials + bias), read from the fixed-point accumulator
-            float bv[8];
-            unpack8(*reinterpret_cast<const uint4*>(ybias + 8 * t), bv);
+    float yv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (yacc) {
+        uint4 bvv = make_uint4(0, 0, 0, 0);
+        if (act) bvv = *reinterpret_cast<const uint4*>(ybias + 8 * t);     // in flight during the poll
+        acc_poll8(yacc + 8 * t, target, yv, act, nosync);
+        float bv[8];
+        unpack8(bvv, bv);
 #pragma unroll
-            for (int e = 0; e < 8; e++) yv[e] = round_f16(fix_get(yacc + 8 * t + e) + bv[e]);
-        } else if (yll) {
-            unpack8(make_uint4(w[0], w[1], w[2], w[3]), yv);
-        } else {
-            unpack8(ldg_cg(reinterpret_cast<const uint4*>(y) + t), yv);
-        }
+        for (int e = 0; e < 8; e++) yv[e] = round_f16(yv[e] + bv[e]);
+    } else if (act) {
+        unpack8(ldg_cg(reinterpret_cast<const uint4*>(y) + t), yv);
+    }
+    if (act) {
         const float4 a = lds_f4(xres_s + t * 32), b = lds_f4(xres_s + t * 32 + 16);
         v[0] = a.x + yv[0]; v[1] = a.y + yv[1]; v[2] = a.z + yv[2]; v[3] = a.w + yv[3];
         v[4] = b.x + yv[4]; v[5] = b.y + yv[5]; v[6] = b.z + yv[6]; v[7] = b.w + yv[7];
@@ -841,10 +938,10 @@ __device__ __forceinline__ float dot_k8(const uint4 kv, const float4 qa, const f
 #else
 #define ER_ATTN_INLINE __forceinline__
 #endif
-template <bool LL, bool FUSE>
+template <bool FUSE>
 __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ring r, Cursor cur, int layer, int L, float* qs,
                                                float* sc, float* vred, float* red, int* s_flag, float* mg, uint32_t flag,
-                                               unsigned long long* acc_y1) {
+                                               unsigned long long* acc_y1, volatile int* zeroed, const int red_idx, const bool nosync) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     AttnRange a;
     if (!attn_range(p.H, p.S, p.split_handicap, L, a)) return cur;
@@ -856,21 +953,21 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
     const int new_slot = nb * 32;                            // score slot just past the old blocks
     const uint32_t qs_s = s_addr(qs), sc_s = s_addr(sc);
     float M = -INFINITY;
-    // the new key / value row (written by P1 of this step, visible after the grid barrier) are fetched NOW and used at the end of
-    // the K pass / at publish time, so their L2 round trips hide behind the streamed passes
+    // the new key / value row (written by P1 of this step) are fetched NOW and used at the end of the K pass / at publish time, so
+    // their L2 round trips hide behind the streamed passes
     uint4 knew = make_uint4(0, 0, 0, 0);
     unsigned short vnew = 0;
-    if (LL) {
-        // q / new k / new v of this head arrive as flagged words from the CTAs that own those qkv rows: threads 128..175 take the 48 q
-        // words, (last split only) lanes 0..11 of warp 0 the new key (4 words each) and threads 0..95 the new value (word tid / 2)
+    if (FUSE) {
+        // q / new k / new v of this head arrive as flagged words from the CTAs of the SAME head that own those qkv rows: threads 128..175
+        // take the 48 q words, (last split only) lanes 0..11 of warp 0 the new key (4 words each) and threads 0..95 the new value (word tid / 2)
         if (nk > 0) {
             const bool qrole = tid >= 128 && tid < 128 + HD / 2;
             const unsigned long long* kq = p.ll_q + ((p.C + a.h * HD) >> 1) + tid * 4;
             const unsigned long long* vq = p.ll_q + ((2 * p.C + a.h * HD) >> 1) + (tid >> 1);
             const unsigned long long* qq = p.ll_q + ((a.h * HD) >> 1) + (tid - 128);
-            uint32_t w[5];
+            uint32_t w[5] = {0u, 0u, 0u, 0u, 0u};
             const uint32_t mask = ((a.is_new && tid < HV) ? 0xFu : 0u) | (((a.is_new && tid < HD) || qrole) ? 0x10u : 0u);
-            ll_poll<5>(w, mask, flag, p.poll_rounds, [&](int j) { return j < 4 ? kq + j : (qrole ? qq : vq); });
+            ll_poll<5>(w, nosync ? 0u : mask, flag, p.poll_rounds, [&](int j) { return j < 4 ? kq + j : (qrole ? qq : vq); });
             if (a.is_new && tid < HV) knew = make_uint4(w[0], w[1], w[2], w[3]);
             if (a.is_new && tid < HD) vnew = (unsigned short)((tid & 1) ? (w[4] >> 16) : (w[4] & 0xffffu));
             if (qrole) {
@@ -883,7 +980,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
         if (tid < HD) vnew = ldg_cg_u16(p.q16 + 2 * p.C + a.h * HD + tid);
     }
     if (nk > 0) {
-        if (!LL && tid < HD) qs[tid] = __half2float(__ushort_as_half(ldg_cg_u16(p.q16 + a.h * HD + tid)));
+        if (!FUSE && tid < HD) qs[tid] = __half2float(__ushort_as_half(ldg_cg_u16(p.q16 + a.h * HD + tid)));
         cbar();
 
         // ---- K pass ----
@@ -916,7 +1013,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
                 if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
             }
         }
-        // the new key: q . k_L straight from the cache line P1 just wrote (visible after the grid barrier); owned by warp 0
+        // the new key: q . k_L; owned by warp 0
         if (a.is_new && warp == 0) {
             float acc = 0.f;
             if (lane < HV) acc = dot_k8(knew, lds_f4(qs_s + lane * 32), lds_f4(qs_s + lane * 32 + 16), 0.f);
@@ -974,7 +1071,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
         }
         cbar();
     }
-    if (warp >= 4 && !LL && !FUSE) return cur;           // warps 0..3 publish; the others go on to the grid barrier
+    if (warp >= 4 && !FUSE) return cur;           // warps 0..3 publish; the others go on to the grid barrier
     // ---- publish the split partial ----
     unsigned long long* outl = p.ll_part + ((size_t)a.h * p.S + (blockIdx.x % p.S)) * 100;
     if (tid < HD) {
@@ -984,7 +1081,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
             for (int g = 0; g < 2 * kConsumerWarps; g++) acc += vred[g * HD + tid];
             if (a.is_new) acc = fmaf(sc[new_slot] * red[32], __half2float(__ushort_as_half(vnew)), acc);   // new key: normalised by warp 0
         }
-        if (LL || FUSE) ll_store(outl + tid, __float_as_uint(acc), flag); else outp[tid] = acc;
+        if (FUSE) ll_store(outl + tid, __float_as_uint(acc), flag); else outp[tid] = acc;
     } else if (tid == HD) {
         float l = 0.f;
         if (nk > 0) {
@@ -992,29 +1089,30 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
             if (a.is_new) l += sc[new_slot] * red[32];
         }
         const float mval = (nk > 0) ? M * rsqrtf((float)HD) : -INFINITY;        // max in softmax (scaled) units
-        if (LL || FUSE) { ll_store(outl + HD, __float_as_uint(mval), flag); ll_store(outl + HD + 1, __float_as_uint(l), flag); }
+        if (FUSE) { ll_store(outl + HD, __float_as_uint(mval), flag); ll_store(outl + HD + 1, __float_as_uint(l), flag); }
         else { outp[HD] = mval; outp[HD + 1] = l; }
     }
     if (FUSE) {
-        // ---- fused tail: every CTA of the head merges the S partials itself (flagged words, 9 pollers per head: no storm), then
-        // multiplies the head's output by ITS rows of the per-head out_proj copy and adds the partial rows to the y1 accumulator ----
+        // ---- tensor-parallel tail: every CTA of the head merges the S partials itself (flagged words, S pollers per word: no storm),
+        // then multiplies the head's output by ITS rows of the head's out_proj columns and adds the partial rows to the y1 accumulator ----
         const int S = p.S, s = blockIdx.x % S;
         float* pm = mg;                                   // [S][100] merged-partial staging (aliases the GEMV partials)
         cbar();
         {
             const unsigned long long* src = p.ll_part + (size_t)a.h * S * 100;
             const int nw = S * (HD + 2);
-            uint32_t w[7];
+            uint32_t w[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
             uint32_t mask = 0;
 #pragma unroll
             for (int j = 0; j < 7; j++) mask |= (tid + kConsumers * j < nw) ? (1u << j) : 0u;
             const uint32_t want = mask;
-            ll_poll<7>(w, mask, flag, p.poll_rounds, [&](int j) { const int i = tid + kConsumers * j; return src + (i / (HD + 2)) * 100 + i % (HD + 2); });
+            ll_poll<7>(w, nosync ? 0u : mask, flag, p.poll_rounds, [&](int j) { const int i = tid + kConsumers * j; return src + (i / (HD + 2)) * 100 + i % (HD + 2); });
 #pragma unroll
             for (int j = 0; j < 7; j++)
                 if ((want >> j) & 1u) { const int i = tid + kConsumers * j; pm[(i / (HD + 2)) * 100 + i % (HD + 2)] = __uint_as_float(w[j]); }
         }
         cbar();
+        __half* o16 = reinterpret_cast<__half*>(qs);      // the head's attention output, fp16 as in the reference; q is no longer needed
         if (tid < HD) {                                   // same fold as the single-merger path, split order
             float Mx = -INFINITY;
             for (int q = 0; q < S; q++) Mx = fmaxf(Mx, pm[q * 100 + HD]);
@@ -1025,79 +1123,19 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
                 den = fmaf(w8, pm[q * 100 + HD + 1], den);
                 num = fmaf(w8, pm[q * 100 + tid], num);
             }
-            qs[tid] = round_f16(num / den);               // the attention output is an fp16 tensor in the reference; q is no longer needed
+            o16[tid] = __float2half_rn(num / den);
+        }
+        if (tid == 0) {                                   // the janitor has recycled every copy this CTA has been told about (see fix_add_cnt)
+            int spins = 0;
+            while (*zeroed < red_idx) { if (++spins > kSpinLimit) asm volatile("trap;"); }
         }
         cbar();
         const RowRange rs = cta_rows_of(p.C, (unsigned)s, (unsigned)S);
         const int n = rs.r1 - rs.r0;
-        const int u = tid >> 1, hf = tid & 1;             // two threads per output row, 48 of the head's 96 columns each
-        float xa[HD / 2];
-#pragma unroll
-        for (int e = 0; e < HD / 2; e++) xa[e] = qs[hf * (HD / 2) + e];
-        const int nch = (n + kHoUnitsPerStage - 1) / kHoUnitsPerStage;
-        for (int c = 0; c < nch; ++c, cur.advance(r.nstage)) {
-            mbar_wait(r.fullb(cur.stage), cur.parity);
-            const int here = min(kHoUnitsPerStage, n - c * kHoUnitsPerStage);
-            float part = 0.f;
-            if (u < here) {
-                const uint32_t wb = r.stage(cur.stage) + (uint32_t)u * (kHoStride * 2) + (uint32_t)hf * HD;
-#pragma unroll
-                for (int v = 0; v < HD / 16; v++) {
-                    const uint4 wv = lds128(wb + v * 16);
-                    float2 f;
-                    f = h2f2(wv.x); part = fmaf(f.x, xa[8 * v + 0], part); part = fmaf(f.y, xa[8 * v + 1], part);
-                    f = h2f2(wv.y); part = fmaf(f.x, xa[8 * v + 2], part); part = fmaf(f.y, xa[8 * v + 3], part);
-                    f = h2f2(wv.z); part = fmaf(f.x, xa[8 * v + 4], part); part = fmaf(f.y, xa[8 * v + 5], part);
-                    f = h2f2(wv.w); part = fmaf(f.x, xa[8 * v + 6], part); part = fmaf(f.y, xa[8 * v + 7], part);
-                }
-            }
-            const float tot = part + __shfl_xor_sync(0xffffffffu, part, 1);
-            if (hf == 0 && u < here) fix_add(acc_y1 + rs.r0 + c * kHoUnitsPerStage + u, tot);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
-        }
-        return cur;
-    }
-    if (LL) {
-        // ---- merge, spread over the S CTAs of the head: split s owns output pairs [48 s / S, 48 (s+1) / S).  Thread (d, s') polls
-        // partial s' for dimension d (16 splits x 16 dimensions per round), the sixteen values of a dimension meet in shared memory and
-        // one lane folds them in split order (same arithmetic as the single-merger path below) ----
-        const int S = p.S, s = blockIdx.x % S;
-        const int pr0 = (HD / 2 * s) / S, pr1 = (HD / 2 * (s + 1)) / S;
-        const int nd = 2 * (pr1 - pr0);
-        const int sp = tid & 15;
-        float* my = mg + (tid >> 4) * 48;
-        cbar();   // mg aliases the GEMV partials: warp 0 may still be summing P1's when this split had no keys to stream
-        for (int d0 = 0; d0 < nd; d0 += 16) {
-            const int d = d0 + (tid >> 4);
-            const bool act = d < nd && sp < S;
-            const unsigned long long* src = p.ll_part + ((size_t)a.h * S + sp) * 100;
-            uint32_t w[3];
-            ll_poll<3>(w, act ? 7u : 0u, flag, p.poll_rounds, [&](int j) { return src + (j == 0 ? 2 * pr0 + d : HD + j - 1); });
-            if (act) { my[sp * 3] = __uint_as_float(w[0]); my[sp * 3 + 1] = __uint_as_float(w[1]); my[sp * 3 + 2] = __uint_as_float(w[2]); }
-            __syncwarp();
-            float val = 0.f;
-            if (sp == 0 && d < nd) {
-                float Mx = -INFINITY;
-                for (int q = 0; q < S; q++) Mx = fmaxf(Mx, my[q * 3 + 1]);
-                float den = 0.f, num = 0.f;
-                for (int q = 0; q < S; q++) {
-                    const float ms = my[q * 3 + 1];
-                    const float w8 = (ms == -INFINITY) ? 0.f : __expf(ms - Mx);
-                    den = fmaf(w8, my[q * 3 + 2], den);
-                    num = fmaf(w8, my[q * 3], num);
-                }
-                val = num / den;
-            }
-            const uint32_t mine = __half_as_ushort(__float2half_rn(val));
-            const uint32_t other = __shfl_sync(0xffffffffu, mine, 16);
-            if (lane == 0 && d < nd) ll_store(p.ll_attn + ((a.h * HD) >> 1) + pr0 + (d >> 1), mine | (other << 16), flag);
-            __syncwarp();
-        }
-        if (p.use_hint) {   // one reduction per CTA (six per CTA on one address would serialise at the L2)
-            cbar();
-            if (tid == 0) hint_add(p.hint + 0 * p.layers + layer, (unsigned)(pr1 - pr0));
-        }
+        const uint32_t out_s = s_addr(vred);              // n <= C / 3 <= 512 floats
+        cur = outproj_job_mma(r, cur, n, s_addr(o16), out_s);
+        cbar();
+        for (int u = tid; u < n; u += kConsumers) fix_add_cnt(acc_y1 + rs.r0 + u, vred[u]);
         return cur;
     }
     // ---- last split of this head to finish merges the S partials (release/acquire ticket on a monotonic counter) ----
@@ -1138,7 +1176,8 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------------------
 // PROF: the timeline instrumentation is a separate instantiation so that the production kernel carries neither its registers nor its branches
-template <bool PROF, bool LL, bool FUSE>
+// FUSE: the tensor-parallel layer (see above); false = the five-exchange layer (grid barrier between dependent phases)
+template <bool PROF, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __grid_constant__ DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C, F = p.F, H = p.H, V = p.V;
@@ -1150,10 +1189,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
     ring.full = s_addr(q);
     ring.empty = ring.full + kMaxStages * 8;
     float* xres = reinterpret_cast<float*>(q + 2 * kMaxStages * 8);   // [C]   residual stream (fp32)
-    float* part = xres + C;                                           // [32][kPartStride] GEMV lane partials
+    float* part = xres + C;                                           // [32][kPartStride] GEMV lane partials / merge staging / fc2 partial sums
     float* red = part + 32 * kPartStride;                             // [128] block-reduction scratch
-    float* qs = red + 128;                                            // [96] query of this CTA's head (fp32)
-    float* vred = qs + HD;                                            // [16*96] V-pass cross-warp reduction
+    float* qs = red + 128;                                            // [96] query of this CTA's head (fp32); later the head's output (fp16) / the fc1 slice
+    float* vred = qs + HD;                                            // [16*96] V-pass cross-warp reduction / out_proj partial rows
     float* sc = vred + 2 * kConsumerWarps * HD;                       // [sc_len] scores / sampler scratch
     __half* xin = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(sc + p.sc_len) + 15) & ~uintptr_t(15));   // [max(C,F)] GEMV input (fp16)
     __shared__ int s_tok;
@@ -1161,9 +1200,12 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
     __shared__ uint32_t s_cons_it;
     __shared__ int s_flag;
     __shared__ int s_tok_done;   // tokens of this launch whose token-end grid barrier the consumers have passed
-    __shared__ int s_rows[8];   // this CTA's row ranges of the 3C / C / F / V phases (computed once; registers are scarce)
+    __shared__ int s_rows[10];  // this CTA's row ranges of the qkv / C / F / V phases (+ out_proj slice); computed once (registers are scarce)
     __shared__ SnapState s_snap; // ONE snapshot of the device state per CTA: producer, run-ahead warp and consumers must agree on `done`
     __shared__ unsigned long long s_issued;   // bytes the ring producer has requested so far (read by the L2 run-ahead warp)
+    __shared__ int s_red_done;   // FUSE: L2 reductions this CTA has seen complete
+    __shared__ int s_zeroed;     // FUSE: ... and whose recycled accumulator slice the janitor has zeroed (and fenced)
+    __shared__ int s_exit;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool nosync = p.dbg_nosync != 0;
@@ -1173,10 +1215,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
         s_cons_it = 0;
         s_tok_done = 0;
         s_issued = 0ull;
+        s_red_done = 0; s_zeroed = 0; s_exit = 0;
         s_snap.t = p.st->t; s_snap.L = p.st->L; s_snap.counter = p.st->counter; s_snap.last_tok = p.st->last_tok; s_snap.done = p.st->done;
-        const RowRange r3 = cta_rows(3 * C), r1 = cta_rows(C), rf = cta_rows(F), rv = cta_rows(V);
+        const RowRange r3 = p1_rows<FUSE>(p), r1 = cta_rows(C), rf = cta_rows(F), rv = cta_rows(V);
         s_rows[0] = r3.r0; s_rows[1] = r3.r1; s_rows[2] = r1.r0; s_rows[3] = r1.r1; s_rows[4] = rf.r0; s_rows[5] = rf.r1; s_rows[6] = rv.r0; s_rows[7] = rv.r1;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (FUSE) {
+        // the fc2 consumer reads whole 8-column stages through ldmatrix: a partially filled last stage must not hold NaN bit patterns left
+        // behind by an earlier kernel (0 x NaN = NaN); stale finite weights are harmless (their h is zero)
+        for (uint32_t o = tid * 16; o < (uint32_t)p.nstage * kStageBytes; o += kThreads * 16) sts128(ring.data + o, make_uint4(0, 0, 0, 0));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
@@ -1187,6 +1236,27 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
     } else if (warp == kConsumerWarps + 1) {
         // ===== L2 run-ahead warp =====
         if (lane == 0 && p.pf_dist > 0) prefetch_loop<FUSE>(p, &s_snap, &s_stop, &s_issued);
+    } else if (warp == kConsumerWarps + 2) {
+        // ===== accumulator janitor (FUSE): zero this CTA's slice of the copy that reduction k + 2 will use once reduction k is complete =====
+        if (FUSE && !s_snap.done) {
+            const RowRange rz = cta_rows(C);
+            const int zn = rz.r1 - rz.r0;                      // <= 32 for every supported shape (host-checked)
+            int seen = 0;
+            for (;;) {
+                const int k = *(volatile int*)&s_red_done;
+                if (k > seen) {
+                    for (int j = seen; j < k; ++j)
+                        if (lane < zn) p.acc[(size_t)((j + 2) & 3) * C + rz.r0 + lane] = 0ull;
+                    __threadfence();                           // the zeros are performed at L2 before anybody is told
+                    __syncwarp();
+                    if (lane == 0) *(volatile int*)&s_zeroed = k;
+                    seen = k;
+                } else {
+                    if (*(volatile int*)&s_exit) break;
+                    __nanosleep(200);
+                }
+            }
+        }
     } else {
         // ===== consumers =====
         unsigned epoch = 0;
@@ -1239,9 +1309,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 const int pb = 1 + 16 * layer;
                 const uint32_t flag = (uint32_t)(t * p.layers + layer + 1);   // exchange-word flag of this (token, layer)
                 const bool all_on = PROF && p.prof != nullptr && t == p.prof_token && layer == 5;
-                const int gl = iter * p.layers + layer;                          // layers run by this launch so far: parity picks the accumulator copy
-                unsigned long long* const acc_y1 = FUSE ? p.acc + (size_t)(gl & 1) * 2 * C : nullptr;
-                unsigned long long* const acc_y2 = FUSE ? acc_y1 + C : nullptr;
+                const int gl = iter * p.layers + layer;                          // layers run by this launch so far
+                // FUSE: reduction 2 gl (y1) uses accumulator copy (2 gl) & 3, reduction 2 gl + 1 (y2) copy (2 gl + 1) & 3
+                unsigned long long* const acc_y1 = FUSE ? p.acc + (size_t)((2 * gl) & 3) * C : nullptr;
+                unsigned long long* const acc_y2 = FUSE ? p.acc + (size_t)((2 * gl + 1) & 3) * C : nullptr;
                 // ---------------- P1: q,k,v = x16 @ Wqkv^T + b ; KV append in place ----------------------------------------------
                 {
                     const RowRange rr{s_rows[0], s_rows[1]};
@@ -1250,21 +1321,21 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     const int nu = nr * nu1;
                     const bool own = tid < nu && (tid % nu1) == 0;
                     const float bias = own ? __half2float(p.bqkv[(size_t)layer * 3 * C + rr.r0 + tid / nu1]) : 0.f;   // in flight during the GEMV
-                    cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
+                    if (nu > 0 || !FUSE) cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
                     prof_stamp(p, pb + 1, prof_on); prof_all(p, 1, all_on);
-                    // q, new k, new v go to a small dense vector the attention CTAs read (q16[3C]) — or to flagged words; the K/V CACHE rows
-                    // (scattered 2-byte stores into pages only this token touches: TLB misses that hold the storing warp for ~1 us)
-                    // are only needed by later tokens and are written after this CTA has arrived at the barrier
+                    // q, new k, new v go to a small dense vector the attention CTAs read (q16[3C]) — or, FUSE, as flagged words to the CTAs of the
+                    // same head; the K/V CACHE rows (scattered 2-byte stores into pages only this token touches: TLB misses that hold the storing
+                    // warp for ~1 us) are only needed by later tokens and are written after the values are on their way
                     __half hv = __float2half_rn(0.f);
                     const int r = rr.r0 + tid / nu1;
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu1, nparts);
                         hv = __float2half_rn(sum + bias);
-                        if (LL) ll_publish_rows(p.ll_q, rr.r0, nu, nu1, hv, flag, nullptr);
+                        if (FUSE) ll_publish_rows(p.ll_q, rr.r0, nu, nu1, hv, flag);
                         else if (own) p.q16[r] = hv;
                     }
                     prof_stamp(p, pb + 2, prof_on); prof_all(p, 2, all_on);
-                    if (!LL) grid_arrive(p.bar, epoch, nosync);
+                    if (!FUSE) grid_arrive(p.bar, epoch, nosync);
                     if (own && r >= C) {
                         if (r < 2 * C) {
                             const int c = r - C, h = c / HD, d = c % HD;
@@ -1275,27 +1346,28 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                             p.vc[(((size_t)layer * H + h) * p.Lmax + L) * HD + d] = hv;
                         }
                     }
-                    if (!LL) grid_wait(p.bar, epoch, nosync);
-                    if (FUSE) {   // everybody has finished with the other copy of the accumulators (previous layer): zero this CTA's slice of it
-                        unsigned long long* const other = p.acc + (size_t)((gl + 1) & 1) * 2 * C;
-                        const int z0 = s_rows[2], zn = s_rows[3] - s_rows[2];
-                        if (tid < zn) { other[z0 + tid] = 0ull; other[C + z0 + tid] = 0ull; }
-                    }
+                    if (!FUSE) grid_wait(p.bar, epoch, nosync);
                 }
                 prof_stamp(p, pb + 3, prof_on); prof_all(p, 3, all_on);
-                // ---------------- P2: attention -----------------------------------------------------------------------------------------
-                cur = attention_phase<LL, FUSE>(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag, part, flag, acc_y1);
+                // ---------------- P2: attention (+ FUSE: head merge, row-parallel out_proj into the y1 accumulator) ------------------------
+                cur = attention_phase<FUSE>(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag, part, flag, acc_y1, &s_zeroed, 2 * gl, nosync);
+                if (FUSE && (int)blockIdx.x >= H * p.S) {
+                    // CTAs without an attention role still ADD (zero) to every y1 word: every reduction then has an addend from every CTA, which
+                    // is what makes "reduction k+1 complete" imply "every CTA has recycled its slice for reduction k+2"
+                    if (tid == 0) {
+                        int spins = 0;
+                        while (*(volatile int*)&s_zeroed < 2 * gl) { if (++spins > kSpinLimit) asm volatile("trap;"); }
+                    }
+                    cbar();
+                    for (int u = tid; u < C; u += kConsumers) fix_add_cnt(acc_y1 + u, 0.f);
+                }
                 prof_stamp(p, pb + 4, prof_on); prof_all(p, 4, all_on);
-                if (!LL && !FUSE) grid_barrier(p.bar, epoch, nosync);
+                if (!FUSE) grid_barrier(p.bar, epoch, nosync);
                 prof_stamp(p, pb + 5, prof_on); prof_all(p, 5, all_on);
                 // ---------------- P3: out_proj on the merged attention output -----------------------------------------------------------
                 if (!FUSE) {
-                    if (LL) {
-                        ll_fetch(p.ll_attn, xin_s, C / 4, flag, p.poll_rounds, p.use_hint ? p.hint + 0 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2));
-                    } else {
-                        for (int i = tid; i < C / 8; i += kConsumers)
-                            reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.attn16 + (size_t)xcopy * C) + i);
-                    }
+                    for (int i = tid; i < C / 8; i += kConsumers)
+                        reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.attn16 + (size_t)xcopy * C) + i);
                     cbar();
                     const RowRange rr{s_rows[2], s_rows[3]};
                     const int nr = rr.r1 - rr.r0;
@@ -1306,17 +1378,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu1, nparts);
-                        if (LL) ll_publish_rows(p.ll_y1, rr.r0, nu, nu1, __float2half_rn(sum + bias), flag, p.use_hint ? p.hint + 1 * p.layers + layer : nullptr);
-                        else if (own) { const __half yv = __float2half_rn(sum + bias); for (int c = 0; c < p.xrep; c++) p.y1[(size_t)c * C + rr.r0 + tid / nu1] = yv; }
+                        if (own) { const __half yv = __float2half_rn(sum + bias); for (int c = 0; c < p.xrep; c++) p.y1[(size_t)c * C + rr.r0 + tid / nu1] = yv; }
                     }
                 }
-                const LnParams lp1 = ln_load(p.ln1_w + (size_t)layer * C, p.ln1_b + (size_t)layer * C, C);   // lands while we wait at the barrier
+                const LnParams lp1 = ln_load(p.ln1_w + (size_t)layer * C, p.ln1_b + (size_t)layer * C, C);   // lands while we wait
                 prof_stamp(p, pb + 7, prof_on); prof_all(p, 7, all_on);
-                if (!LL) grid_barrier(p.bar, epoch, nosync);
+                if (!FUSE) grid_barrier(p.bar, epoch, nosync);
                 prof_stamp(p, pb + 8, prof_on); prof_all(p, 8, all_on);
                 // ---------------- P4: x = LN1(x + y1) ; h1 = relu(fc1(x)) -----------------------------------------------------------
                 {
-                    residual_layer_norm(xres_s, xin_s, p.y1 + (size_t)xcopy * C, LL ? p.ll_y1 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 1 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), layer == 0, lp1, C, inv_c, red, acc_y1, FUSE ? p.bo + (size_t)layer * C : nullptr);
+                    residual_layer_norm(xres_s, xin_s, p.y1 + (size_t)xcopy * C, layer == 0, lp1, C, inv_c, red, acc_y1, H + (int)gridDim.x - H * p.S, FUSE ? p.bo + (size_t)layer * C : nullptr, nosync);
+                    if (FUSE && tid == 0) *(volatile int*)&s_red_done = 2 * gl + 1;
                     const RowRange rr{s_rows[4], s_rows[5]};
                     const int nr = rr.r1 - rr.r0;
                     prof_stamp(p, pb + 9, prof_on); prof_all(p, 9, all_on);
@@ -1324,55 +1396,33 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     const bool own = tid < nu && (tid % nu1) == 0;
                     const float bias = own ? __half2float(p.b1[(size_t)layer * F + rr.r0 + tid / nu1]) : 0.f;
                     cur = gemv_job(ring, cur, nu, nu1, gc, xin_s, part_s);
+                    __half* const h1s = reinterpret_cast<__half*>(qs);      // FUSE: this CTA's slice of h1 stays on chip (<= 64 fp16, zero padded)
+                    if (FUSE && tid >= nu && tid < kMaxUnits) h1s[tid] = __float2half_rn(0.f);
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu1, nparts);
                         const __half hv = __float2half_rn(fmaxf(round_f16(sum + bias), 0.f));
-                        if (FUSE) { if (own) vred[tid] = __half2float(hv); }                  // this CTA's slice of h1 stays on chip
-                        else if (LL) ll_publish_rows(p.ll_h1, rr.r0, nu, nu1, hv, flag, p.use_hint ? p.hint + 2 * p.layers + layer : nullptr);
+                        if (FUSE) { if (own) h1s[tid] = hv; }
                         else if (own) for (int c = 0; c < p.xrep; c++) p.h1[(size_t)c * F + rr.r0 + tid / nu1] = hv;
                     }
                     if (FUSE) {
-                        // fc2, K-split: y2 += W2[:, j] * h1[j] over this CTA's columns j (one transposed unit per column, `upstage` per stage);
-                        // thread t < C/8 owns output elements 8t .. 8t+7, then adds them to the fixed-point accumulator
+                        // fc2, row-parallel: y2 += W2[:, j] * h1[j] over this CTA's columns j, then into the counting accumulator
+                        if (tid == 0) {
+                            int spins = 0;
+                            while (*(volatile int*)&s_zeroed < 2 * gl + 1) { if (++spins > kSpinLimit) asm volatile("trap;"); }
+                        }
                         cbar();
-                        float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        const int ups = p.upstage, ubytes = p.ustride * 2;
-                        const int nch = (nr + ups - 1) / ups;
-                        for (int c = 0; c < nch; ++c, cur.advance(ring.nstage)) {
-                            mbar_wait(ring.fullb(cur.stage), cur.parity);
-                            const int here = min(ups, nr - c * ups);
-                            if (tid < C / 8) {
-                                const uint32_t wb = ring.stage(cur.stage) + (uint32_t)tid * 16;
-                                for (int u = 0; u < here; ++u) {
-                                    const uint4 wv = lds128(wb + (uint32_t)u * ubytes);
-                                    const float hj = vred[c * ups + u];
-                                    float2 f;
-                                    f = h2f2(wv.x); a8[0] = fmaf(hj, f.x, a8[0]); a8[1] = fmaf(hj, f.y, a8[1]);
-                                    f = h2f2(wv.y); a8[2] = fmaf(hj, f.x, a8[2]); a8[3] = fmaf(hj, f.y, a8[3]);
-                                    f = h2f2(wv.z); a8[4] = fmaf(hj, f.x, a8[4]); a8[5] = fmaf(hj, f.y, a8[5]);
-                                    f = h2f2(wv.w); a8[6] = fmaf(hj, f.x, a8[6]); a8[7] = fmaf(hj, f.y, a8[7]);
-                                }
-                            }
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(ring.emptyb(cur.stage));
-                        }
-                        if (tid < C / 8) {
-#pragma unroll
-                            for (int e = 0; e < 8; e++) fix_add(acc_y2 + 8 * tid + e, a8[e]);
-                        }
+                        cur = fc2_job(ring, cur, nr, C, p.ustride, s_addr(h1s), part_s);
+                        cbar();
+                        for (int u = tid; u < C; u += kConsumers) fix_add_cnt(acc_y2 + u, part[u]);
                     }
                 }
                 prof_stamp(p, pb + 10, prof_on); prof_all(p, 10, all_on);
-                if (!LL && !FUSE) grid_barrier(p.bar, epoch, nosync);
+                if (!FUSE) grid_barrier(p.bar, epoch, nosync);
                 prof_stamp(p, pb + 11, prof_on); prof_all(p, 11, all_on);
                 // ---------------- P5: y2 = fc2(h1) -----------------------------------------------------------------------------------------
                 if (!FUSE) {
-                    if (LL) {
-                        ll_fetch(p.ll_h1, xin_s, F / 4, flag, p.poll_rounds, p.use_hint ? p.hint + 2 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(F / 2));
-                    } else {
-                        for (int i = tid; i < F / 8; i += kConsumers)
-                            reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.h1 + (size_t)xcopy * F) + i);
-                    }
+                    for (int i = tid; i < F / 8; i += kConsumers)
+                        reinterpret_cast<uint4*>(xin)[i] = ldg_cg(reinterpret_cast<const uint4*>(p.h1 + (size_t)xcopy * F) + i);
                     cbar();
                     const RowRange rr{s_rows[2], s_rows[3]};
                     const int nr = rr.r1 - rr.r0, nu = nr * nu_fc2;
@@ -1381,16 +1431,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     cur = gemv_job(ring, cur, nu, nu_fc2, gc, xin_s, part_s);
                     if (warp * 32 < nu) {
                         const float sum = reduce_rows(part_s, nu, nu_fc2, nparts);
-                        if (LL) ll_publish_rows(p.ll_y2, rr.r0, nu, nu_fc2, __float2half_rn(sum + bias), flag, p.use_hint ? p.hint + 3 * p.layers + layer : nullptr);
-                        else if (tid < nu && (tid % nu_fc2) == 0) { const __half yv = __float2half_rn(sum + bias); for (int c = 0; c < p.xrep; c++) p.y2[(size_t)c * C + rr.r0 + tid / nu_fc2] = yv; }
+                        if (tid < nu && (tid % nu_fc2) == 0) { const __half yv = __float2half_rn(sum + bias); for (int c = 0; c < p.xrep; c++) p.y2[(size_t)c * C + rr.r0 + tid / nu_fc2] = yv; }
                     }
                 }
                 const LnParams lp2 = ln_load(p.ln2_w + (size_t)layer * C, p.ln2_b + (size_t)layer * C, C);
                 prof_stamp(p, pb + 13, prof_on); prof_all(p, 13, all_on);
-                if (!LL) grid_barrier(p.bar, epoch, nosync);
+                if (!FUSE) grid_barrier(p.bar, epoch, nosync);
                 prof_stamp(p, pb + 14, prof_on); prof_all(p, 14, all_on);
                 // ---------------- x = LN2(x + y2) ------------------------------------------------------------------------------------------
-                residual_layer_norm(xres_s, xin_s, p.y2 + (size_t)xcopy * C, LL ? p.ll_y2 : nullptr, flag, p.poll_rounds, p.use_hint ? p.hint + 3 * p.layers + layer : nullptr, (unsigned)(iter + 1) * (unsigned)(C / 2), false, lp2, C, inv_c, red, acc_y2, FUSE ? p.b2 + (size_t)layer * C : nullptr);
+                residual_layer_norm(xres_s, xin_s, p.y2 + (size_t)xcopy * C, false, lp2, C, inv_c, red, acc_y2, (int)gridDim.x, FUSE ? p.b2 + (size_t)layer * C : nullptr, nosync);
+                if (FUSE && tid == 0) *(volatile int*)&s_red_done = 2 * gl + 2;
             }
             // ================= lm_head: logits_pre = fp16(x) @ W^T (fp32 value before the fp16 store) ================
             {
@@ -1410,6 +1460,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
             prof_stamp(p, 2 + 16 * p.layers, prof_on);
         }
         if (!state_written && blockIdx.x == 0 && tid == 0) { p.st->t = t; p.st->L = L; p.st->counter = counter; p.st->last_tok = last_tok; }
+        if (tid == 0) *(volatile int*)&s_exit = 1;
     }
     __syncthreads();   // nobody leaves while bulk copies into this CTA's shared memory may still be in flight
 }
@@ -1432,13 +1483,12 @@ int er_decode_pick_stages(const er::DecodeParams& p, size_t smem_limit) {
 int er_decode_max_units() { return er::kMaxUnits; }
 int er_decode_stage_bytes() { return er::kStageBytes; }
 
-static const void* er_decode_kernel_fn(bool prof, bool ll, bool fuse) {
-    if (fuse) return prof ? (const void*)er::decode_persistent_kernel<true, false, true> : (const void*)er::decode_persistent_kernel<false, false, true>;
-    if (prof) return ll ? (const void*)er::decode_persistent_kernel<true, true, false> : (const void*)er::decode_persistent_kernel<true, false, false>;
-    return ll ? (const void*)er::decode_persistent_kernel<false, true, false> : (const void*)er::decode_persistent_kernel<false, false, false>;
+static const void* er_decode_kernel_fn(bool prof, bool fuse) {
+    if (fuse) return prof ? (const void*)er::decode_persistent_kernel<true, true> : (const void*)er::decode_persistent_kernel<false, true>;
+    return prof ? (const void*)er::decode_persistent_kernel<true, false> : (const void*)er::decode_persistent_kernel<false, false>;
 }
 cudaError_t er_decode_launch(const er::DecodeParams& p, int grid, size_t smem, cudaStream_t stream) {
-    const void* fn = er_decode_kernel_fn(p.prof != nullptr, p.use_ll != 0, p.use_fuse != 0);
+    const void* fn = er_decode_kernel_fn(p.prof != nullptr, p.use_fuse != 0);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&p};
@@ -1450,8 +1500,8 @@ int er_decode_max_grid(size_t smem) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int ok = 1;
-    for (int v = 0; v < 6; ++v) {
-        const void* fn = v < 4 ? er_decode_kernel_fn((v & 1) != 0, (v & 2) != 0, false) : er_decode_kernel_fn((v & 1) != 0, false, true);
+    for (int v = 0; v < 4; ++v) {
+        const void* fn = er_decode_kernel_fn((v & 1) != 0, (v & 2) != 0);
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, er::kThreads, smem) != cudaSuccess || per < 1) ok = 0;
     }

@@ -37,12 +37,10 @@ struct DecodeParams {
     unsigned *head_cnt;   // [H] monotonic split-completion tickets (zeroed with the barrier counter)
     float *part;      // [H][S][100]: o[96], m, l
     float *logits;    // [V] fp32 lm_head output before the fp16 rounding
-    // flagged exchange (use_ll): the same vectors as 8-byte {payload, flag} words that readers poll instead of meeting at a grid
-    // barrier; payload = two fp16 (q|k|v, attn, y1, h1, y2) or one fp32 (split partials).  Zeroed by the host before each launch.
-    unsigned long long *ll_q, *ll_attn, *ll_y1, *ll_h1, *ll_y2, *ll_part;
-    int use_ll;
-    unsigned *hint;    // [4][layers] arrival-hint counters (attn, y1, h1, y2), zeroed before each launch
-    int use_hint;
+    // flagged exchange (tensor-parallel layer): 8-byte {payload, flag} words that the S CTAs of a head poll instead of meeting at a
+    // barrier; ll_q: [3C/2] two fp16 each (q | new k | new v), ll_part: [H][S][100] one fp32 each (split partials).  Zeroed by the
+    // host before each launch; flags are unique per (token, layer).
+    unsigned long long *ll_q, *ll_part;
     int poll_rounds;   // all-thread polling rounds before a warp falls back to one spinning lane
     DecodeState *st;
     unsigned *bar;    // grid barrier counter (zeroed by the host before each launch)
@@ -54,8 +52,8 @@ struct DecodeParams {
     unsigned long long seed;
     // optional phase timeline: slot 0 = token start, then (end of phase, end of barrier) x 5 per layer, + lm_head pair
     unsigned long long *prof; int prof_token, prof_cta;
-    // fused phases (use_fuse, experimental): per layer [H][C][HD+8] per-head out_proj units, then [F][ustride] transposed fc2 units;
-    // acc: u64 fixed-point accumulators [2 copies][y1 | y2][C], zeroed by the host before each launch
+    // tensor-parallel layer (use_fuse): per layer [H][C][HD+8] per-head out_proj units, then [F][ustride] transposed fc2 units;
+    // acc: four copies of [C] u64 counting fixed-point accumulators (reduction k uses copy k & 3), zeroed by the host before each launch
     const __half *wfuse; unsigned long long *acc; int use_fuse;
     // L2 run-ahead: a second streaming warp issues cp.async.bulk.prefetch.L2 for this CTA's future ring bytes, staying at most
     // pf_dist bytes ahead of the ring producer, so that HBM keeps streaming while the consumers sit in an exchange (0 = off)

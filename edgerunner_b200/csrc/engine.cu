@@ -17,7 +17,10 @@
 #include "kernels.h"
 
 #ifndef ER_DEFAULT_PF_DIST
-#define ER_DEFAULT_PF_DIST 0
+#define ER_DEFAULT_PF_DIST (128 * 1024)   // L2 run-ahead per CTA: +3..5 % measured (profiles/r02_diag_runahead_nosync_fuse.json); >= 512 KB thrashes L2
+#endif
+#ifndef ER_DEFAULT_FUSE
+#define ER_DEFAULT_FUSE 0
 #endif
 
 static thread_local char g_err[512] = "";
@@ -110,8 +113,8 @@ struct er_engine {
     // cache + decode scratch
     __half *kc, *vc, *q16, *y1, *h1, *y2, *attn16;
     float *part, *logits, *cond32;
-    unsigned long long* ll = nullptr; size_t ll_words = 0; int use_ll = 0; unsigned* hint = nullptr;
-    __half* wfuse = nullptr; unsigned long long* acc = nullptr; int use_fuse = 0;   // fused decode phases (experimental, ER_DECODE_FUSE=1)   // flagged exchange words of the decode kernel
+    unsigned long long* ll = nullptr; size_t ll_words = 0;      // flagged exchange words of the tensor-parallel decode layer
+    __half* wfuse = nullptr; unsigned long long* acc = nullptr; int use_fuse = ER_DEFAULT_FUSE, S_fuse = 0;   // tensor-parallel decode layer
     er::DecodeState* st;
     unsigned* bar;
     int32_t* ids_dev;
@@ -128,7 +131,7 @@ struct er_engine {
     bool cache_rows_stale = false;     // a decode ran since cache_rows was set: the exact row count lives in the device state
     unsigned long long* prof = nullptr; int prof_token = -1, prof_cta = 0;
     // decode-kernel knobs (defaults = the production configuration; changed only through er_debug_set)
-    int split_handicap = 4, xrep = 1, use_hint = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
+    int split_handicap = 4, xrep = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
     int lat_batch_cap = 1;
 };
 
@@ -288,12 +291,18 @@ static int create_impl(er_engine* e, const er_config* cfg) {
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     e->grid = sms;
     e->S = sms / H; if (e->S > 16) e->S = 16; if (e->S < 1) { return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
-    ALLOC(e->part, (size_t)H * e->S * 100);
-    e->ll_words = (size_t)3 * C / 2 + 3 * (size_t)(C / 2) + F / 2 + (size_t)H * e->S * 100;
+    ALLOC(e->part, (size_t)H * 16 * 100);
+    e->ll_words = (size_t)3 * C / 2 + (size_t)H * 16 * 100;
     ALLOC(e->ll, e->ll_words);
-    ALLOC(e->hint, 4 * (size_t)NL);
     ALLOC(e->acc, 4 * (size_t)C);
+    // tensor-parallel layer: S in {12, 9, 6} so that a CTA's 288 / S qkv rows stay inside one of q | k | v; needs the tensor-core
+    // GEMV shapes (C % 256), <= 64 fc1 rows and <= 32 accumulator words per CTA
+    e->S_fuse = 0;
+    for (int cand : {12, 9, 6}) if (cand * H <= sms) { e->S_fuse = cand; break; }
+    if (C % 256 || (F + sms - 1) / sms + 1 > 64 || (C + sms - 1) / sms + 1 > 32 || (C & 1)) e->S_fuse = 0;
+    if (!e->S_fuse) e->use_fuse = 0;
     e->sc_len = er::score_scratch_len(e->nkb, e->S, V);
+    if (e->S_fuse) e->sc_len = std::max(e->sc_len, er::score_scratch_len(e->nkb, e->S_fuse, V));
     {
         er::DecodeParams p{}; p.C = C; p.F = F; p.H = H; p.V = V; p.S = e->S; p.sc_len = e->sc_len;
         int smem_max = 0;
@@ -527,7 +536,8 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     cudaStream_t st = (cudaStream_t)stream;
     const int C = e->C, F = e->F, V = e->V, G = e->grid;
     er::DecodeParams p{};
-    p.C = C; p.H = e->H; p.F = F; p.V = V; p.layers = e->NL; p.S = e->S; p.Lmax = e->Lmax; p.nkb = e->nkb;
+    const bool fuse = e->use_fuse && e->wfuse != nullptr && e->S_fuse > 0;
+    p.C = C; p.H = e->H; p.F = F; p.V = V; p.layers = e->NL; p.S = fuse ? e->S_fuse : e->S; p.Lmax = e->Lmax; p.nkb = e->nkb;
     p.nstage = e->nstage; p.sc_len = e->sc_len;
     // red_units holds 2 partial sums per unit of C elements: the widest phases are qkv (rows) and fc2 (rows * F/C)
     const int max_units = std::max(std::max((3 * C + G - 1) / G + 1, (F + G - 1) / G + 1), ((C + G - 1) / G + 1) * (F / C));
@@ -538,12 +548,10 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.wdec = e->wdec; p.ustride = e->ustride; p.upstage = e->upstage; p.use_mma = e->use_mma;
     p.split_handicap = e->split_handicap;
     p.kc = e->kc; p.vc = e->vc; p.attn16 = e->attn16; p.head_cnt = e->bar + 64; p.q16 = e->q16; p.y1 = e->y1; p.h1 = e->h1; p.y2 = e->y2; p.part = e->part; p.logits = e->logits;
-    p.ll_q = e->ll; p.ll_attn = p.ll_q + 3 * C / 2; p.ll_y1 = p.ll_attn + C / 2; p.ll_y2 = p.ll_y1 + C / 2; p.ll_h1 = p.ll_y2 + C / 2;
-    p.ll_part = p.ll_h1 + F / 2; p.use_ll = e->use_ll && (C % 4 == 0) && (V % 2 == 0);
+    p.ll_q = e->ll; p.ll_part = p.ll_q + 3 * C / 2;
     p.poll_rounds = e->poll_rounds;
-    p.use_fuse = e->use_fuse && e->wfuse != nullptr; p.wfuse = e->wfuse; p.acc = e->acc;
+    p.use_fuse = fuse; p.wfuse = e->wfuse; p.acc = e->acc;
     p.xrep = e->xrep;
-    p.hint = e->hint; p.use_hint = e->use_hint;
     p.pf_dist = e->pf_dist; p.dbg_nosync = e->dbg_nosync;
     p.st = e->st; p.bar = e->bar;
     p.out_ids = out_ids_dev; p.out_logits = out_logits_dev; p.forced = forced_ids_dev;
@@ -554,8 +562,7 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     for (int done = 0; done < max_new_tokens; done += chunk) {
         p.steps = std::min(chunk, max_new_tokens - done);
         CK(cudaMemsetAsync(e->bar, 0, (64 + 64) * 4, st));
-        if (p.use_ll || p.use_fuse) { CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st)); CK(cudaMemsetAsync(e->hint, 0, 4 * (size_t)e->NL * 4, st)); }
-        if (p.use_fuse) CK(cudaMemsetAsync(e->acc, 0, 4 * (size_t)C * 8, st));
+        if (p.use_fuse) { CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st)); CK(cudaMemsetAsync(e->acc, 0, 4 * (size_t)C * 8, st)); }
         CKL(e, er_decode_launch(p, G, e->dec_smem, st));
     }
     if (out_len_dev) {
@@ -658,12 +665,14 @@ extern "C" int er_debug_set(er_engine* e, const char* key, int64_t value) {
     if (k == "poison_alloc") { g_poison_alloc = (int)value; return ER_OK; }      // process-wide; e may be NULL
     if (!e) return set_err(ER_ERR_INVALID, "null engine");
     const int v = (int)value;
-    if (k == "decode_ll") { e->use_ll = v != 0; if (v) e->use_fuse = 0; }
-    else if (k == "decode_fuse") { if (e->finalized && v && !e->wfuse) return set_err(ER_ERR_STATE, "decode_fuse must be set before er_finalize_weights"); e->use_fuse = v != 0; if (v) e->use_ll = 0; }
+    if (k == "decode_fuse") {
+        if (v && !e->S_fuse) return set_err(ER_ERR_CAPACITY, "the tensor-parallel decode layer does not support this model shape / SM count");
+        if (e->finalized && v && !e->wfuse) return set_err(ER_ERR_STATE, "decode_fuse must be set before er_finalize_weights");
+        e->use_fuse = v != 0;
+    }
     else if (k == "gemv_cuda") { if (e->finalized) return set_err(ER_ERR_STATE, "gemv_cuda must be set before er_finalize_weights"); e->use_mma = (v == 0 && e->C % 256 == 0) ? 1 : 0; e->upstage = e->use_mma ? 8 : er_decode_stage_bytes() / (e->ustride * 2) / 8 * 8; }
     else if (k == "split_handicap") e->split_handicap = std::max(0, std::min(7, v));
     else if (k == "xrep") e->xrep = std::max(1, std::min(8, v));
-    else if (k == "hint") e->use_hint = v != 0;
     else if (k == "poll_rounds") e->poll_rounds = std::max(0, v);
     else if (k == "pf_dist") e->pf_dist = std::max(0, v);
     else if (k == "nosync") e->dbg_nosync = v != 0;

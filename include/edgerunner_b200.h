@@ -111,8 +111,8 @@ int32_t er_cache_rows(const er_engine* e);               /* rows currently in th
 int64_t er_kernel_launches(const er_engine* e);          /* kernels launched by this engine so far */
 
 /* Experiment / diagnostic switches of the decode kernel (scripts/, tests; the library never reads the environment).  Keys:
- * "decode_ll", "decode_fuse", "gemv_cuda" (alternative kernel variants; the last two before er_finalize_weights), "split_handicap",
- * "xrep", "hint", "poll_rounds", "pf_dist" (bytes of L2 run-ahead per CTA), "nosync" (timing diagnostics: grid barriers skipped,
+ * "decode_fuse" (1: tensor-parallel decode layer, 0: five-exchange layer), "gemv_cuda" (CUDA-core GEMV consumers) — both before
+ * er_finalize_weights —, "split_handicap", "xrep", "poll_rounds", "pf_dist" (bytes of L2 run-ahead per CTA), "nosync" (timing diagnostics: grid barriers skipped,
  * results are garbage), "cache_rows" (pretend the cache holds that many rows; timing at a chosen context length),
  * "poison_alloc" (process-wide, e may be NULL: fill later allocations with 0xFF).  Unknown key: ER_ERR_INVALID. */
 int er_debug_set(er_engine* e, const char* key, int64_t value);

@@ -80,13 +80,14 @@ def check_stream(cuda_tokens, cuda_logits_pre, ref_logits_pre, V, label):
     return len(mism)
 
 
-@pytest.fixture(scope='module')
-def wide_setup():
+@pytest.fixture(scope='module', params=['five_exchange', 'tensor_parallel'])
+def wide_setup(request):
+    """both decode-layer variants of the kernel (er_debug_set decode_fuse)"""
     from edgerunner_b200.engine import Engine
     from oracle.er_oracle import Oracle
     opt = replace(config_defaults['ArAE'], generate_mode='greedy', num_layers=2)
     sd = synth.synth_state_dict(opt, seed=5, eos_logit=-30.0)
-    eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=16000)
+    eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=16000, debug={'decode_fuse': int(request.param == 'tensor_parallel')})
     eng.load_state_dict(sd)
     return opt, sd, eng, Oracle(opt, sd, mode='ledger'), synth.synth_point_cloud(2, opt.point_num)
 

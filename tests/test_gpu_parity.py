@@ -354,31 +354,40 @@ def test_arae_long_run_properties(arae_setup):
     assert len(v) >= len(f)
 
 
-@pytest.mark.parametrize('switch', ['decode_ll', 'decode_fuse'])
-def test_alternative_exchange_variants_against_default(switch):
-    """The flagged-word exchange (bit-identical by construction) and the fused out_proj / fc2 phases (different summation order: within
-    the logit tolerance, run-to-run identical) against the default kernel, teacher-forced on the default kernel's stream."""
+def test_tensor_parallel_layer_against_five_exchange_layer():
+    """The two decode-layer variants of the kernel (er_debug_set decode_fuse 0 / 1) on the mid configuration (C = 768: the smallest shape
+    the tensor-parallel layer supports), teacher-forced on the five-exchange kernel's stream: logits within the fp16-rounding noise band
+    (different summation order of the K-split GEMVs), each variant bit-reproducible run to run and across chunked launches."""
     from edgerunner_b200.engine import Engine
-    opt = synth.tiny_options()
-    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0)
-    cond = synth.synth_point_cloud(0, opt.point_num)[0].cuda()
+    from oracle.er_oracle import Oracle
+    opt = synth.tiny_options(hidden_dim=768, num_heads=8, num_layers=3)
+    sd = synth.synth_state_dict(opt, seed=3, eos_logit=-30.0)
+    cond = synth.synth_point_cloud(1, opt.point_num)
     res = {}
+    T = 160
     for mode in (0, 1):
-        eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=200, max_points=opt.point_num, debug={switch: mode})
+        eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=300, max_points=opt.point_num, debug={'decode_fuse': mode})
         eng.load_state_dict(sd)
         runs = []
-        for rep in range(2):
-            eng.encode_cond(cond, 1000); eng.prefill([1])
-            runs.append(eng.decode(160, mode='greedy', want_logits=True, forced=res.get('tokens')))
+        for chunk in (0, 0, 23):
+            eng.encode_cond(cond[0].cuda(), 3000); eng.prefill([1])
+            runs.append(eng.decode(T, mode='greedy', want_logits=True, forced=res.get('tokens'), tokens_per_launch=chunk))
+        assert not torch.isnan(runs[0]['logits_pre']).any()
         assert torch.equal(runs[0]['logits_pre'], runs[1]['logits_pre'])
+        assert torch.equal(runs[0]['logits_pre'], runs[2]['logits_pre'])
+        np.testing.assert_array_equal(runs[0]['tokens'], runs[2]['tokens'])
         if mode == 0:
             res['tokens'] = [int(x) for x in runs[0]['tokens']]
             res['base'] = runs[0]['logits_pre'].clone()
         else:
             d = (runs[0]['logits_pre'] - res['base']).abs()
-            assert not torch.isnan(runs[0]['logits_pre']).any()
-            if switch == 'decode_ll':
-                assert d.max().item() == 0.0
-            else:
-                assert d.max().item() <= LOGIT_TOL and d.mean().item() <= MEAN_TOL, (d.max().item(), d.mean().item())
+            print(f'[tensor-parallel vs five-exchange, mid] max |dlogit| {d.max().item():.3e} mean {d.mean().item():.3e}')
+            assert d.max().item() <= 4e-3 and d.mean().item() <= 6e-4, (d.max().item(), d.mean().item())
+            # and against the oracle, free-running
+            eng.encode_cond(cond[0].cuda(), 3000); eng.prefill([1])
+            out = eng.decode(T, mode='greedy', want_logits=True)
+            ref = Oracle(opt, sd, mode='ledger').generate(cond, 3000, max_new_tokens=T, generate_mode='greedy', forced_tokens=list(out['tokens']))
+            d = (out['logits_pre'].cpu() - ref['logits_pre']).abs()
+            assert d.max().item() <= 4e-3 and d.mean().item() <= 6e-4, (d.max().item(), d.mean().item())
+            _check_ids(out['tokens'], ref, 4e-3)
         del eng
