@@ -941,7 +941,8 @@ __device__ __forceinline__ float dot_k8(const uint4 kv, const float4 qa, const f
 template <bool FUSE>
 __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ring r, Cursor cur, int layer, int L, float* qs,
                                                float* sc, float* vred, float* red, int* s_flag, float* mg, uint32_t flag,
-                                               unsigned long long* acc_y1, volatile int* zeroed, const int red_idx, const bool nosync) {
+                                               unsigned long long* acc_y1, volatile int* zeroed, const int red_idx, const bool nosync,
+                                               const bool prof_on, const int pb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     AttnRange a;
     if (!attn_range(p.H, p.S, p.split_handicap, L, a)) return cur;
@@ -979,6 +980,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
         if (warp == 0 && lane < HV) knew = ldg_cg(reinterpret_cast<const uint4*>(p.q16 + p.C + a.h * HD) + lane);
         if (tid < HD) vnew = ldg_cg_u16(p.q16 + 2 * p.C + a.h * HD + tid);
     }
+    if (FUSE) prof_stamp(p, pb + 5, prof_on);          // q (and the new k / v) polled
     if (nk > 0) {
         if (!FUSE && tid < HD) qs[tid] = __half2float(__ushort_as_half(ldg_cg_u16(p.q16 + a.h * HD + tid)));
         cbar();
@@ -1071,6 +1073,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
         }
         cbar();
     }
+    if (FUSE) prof_stamp(p, pb + 6, prof_on);          // K / V passes done
     if (warp >= 4 && !FUSE) return cur;           // warps 0..3 publish; the others go on to the grid barrier
     // ---- publish the split partial ----
     unsigned long long* outl = p.ll_part + ((size_t)a.h * p.S + (blockIdx.x % p.S)) * 100;
@@ -1125,6 +1128,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
             }
             o16[tid] = __float2half_rn(num / den);
         }
+        prof_stamp(p, pb + 15, prof_on);                  // partials of the S splits polled and merged
         if (tid == 0) {                                   // the janitor has recycled every copy this CTA has been told about (see fix_add_cnt)
             int spins = 0;
             while (*zeroed < red_idx) { if (++spins > kSpinLimit) asm volatile("trap;"); }
@@ -1134,6 +1138,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
         const int n = rs.r1 - rs.r0;
         const uint32_t out_s = s_addr(vred);              // n <= C / 3 <= 512 floats
         cur = outproj_job_mma(r, cur, n, s_addr(o16), out_s);
+        prof_stamp(p, pb + 12, prof_on);                  // out_proj rows computed (atomics follow)
         cbar();
         for (int u = tid; u < n; u += kConsumers) fix_add_cnt(acc_y1 + rs.r0 + u, vred[u]);
         return cur;
@@ -1350,7 +1355,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 }
                 prof_stamp(p, pb + 3, prof_on); prof_all(p, 3, all_on);
                 // ---------------- P2: attention (+ FUSE: head merge, row-parallel out_proj into the y1 accumulator) ------------------------
-                cur = attention_phase<FUSE>(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag, part, flag, acc_y1, &s_zeroed, 2 * gl, nosync);
+                cur = attention_phase<FUSE>(p, ring, cur, layer, L, qs, sc, vred, red, &s_flag, part, flag, acc_y1, &s_zeroed, 2 * gl, nosync, prof_on, pb);
                 if (FUSE && (int)blockIdx.x >= H * p.S) {
                     // CTAs without an attention role still ADD (zero) to every y1 word: every reduction then has an addend from every CTA, which
                     // is what makes "reduction k+1 complete" imply "every CTA has recycled its slice for reduction k+2"
@@ -1363,7 +1368,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 }
                 prof_stamp(p, pb + 4, prof_on); prof_all(p, 4, all_on);
                 if (!FUSE) grid_barrier(p.bar, epoch, nosync);
-                prof_stamp(p, pb + 5, prof_on); prof_all(p, 5, all_on);
+                if (!FUSE) prof_stamp(p, pb + 5, prof_on);
+                prof_all(p, 5, all_on);
                 // ---------------- P3: out_proj on the merged attention output -----------------------------------------------------------
                 if (!FUSE) {
                     for (int i = tid; i < C / 8; i += kConsumers)
@@ -1405,6 +1411,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                         else if (own) for (int c = 0; c < p.xrep; c++) p.h1[(size_t)c * F + rr.r0 + tid / nu1] = hv;
                     }
                     if (FUSE) {
+                        prof_stamp(p, pb + 11, prof_on);      // fc1 done
                         // fc2, row-parallel: y2 += W2[:, j] * h1[j] over this CTA's columns j, then into the counting accumulator
                         if (tid == 0) {
                             int spins = 0;
@@ -1412,13 +1419,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                         }
                         cbar();
                         cur = fc2_job(ring, cur, nr, C, p.ustride, s_addr(h1s), part_s);
+                        prof_stamp(p, pb + 13, prof_on);      // fc2 partial sums computed (atomics follow)
                         cbar();
                         for (int u = tid; u < C; u += kConsumers) fix_add_cnt(acc_y2 + u, part[u]);
                     }
                 }
                 prof_stamp(p, pb + 10, prof_on); prof_all(p, 10, all_on);
                 if (!FUSE) grid_barrier(p.bar, epoch, nosync);
-                prof_stamp(p, pb + 11, prof_on); prof_all(p, 11, all_on);
+                if (!FUSE) prof_stamp(p, pb + 11, prof_on);
+                prof_all(p, 11, all_on);
                 // ---------------- P5: y2 = fc2(h1) -----------------------------------------------------------------------------------------
                 if (!FUSE) {
                     for (int i = tid; i < F / 8; i += kConsumers)
@@ -1435,7 +1444,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     }
                 }
                 const LnParams lp2 = ln_load(p.ln2_w + (size_t)layer * C, p.ln2_b + (size_t)layer * C, C);
-                prof_stamp(p, pb + 13, prof_on); prof_all(p, 13, all_on);
+                if (!FUSE) prof_stamp(p, pb + 13, prof_on);
+                prof_all(p, 13, all_on);
                 if (!FUSE) grid_barrier(p.bar, epoch, nosync);
                 prof_stamp(p, pb + 14, prof_on); prof_all(p, 14, all_on);
                 // ---------------- x = LN2(x + y2) ------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@
 #define ER_DEFAULT_PF_DIST (128 * 1024)   // L2 run-ahead per CTA: +3..5 % measured (profiles/r02_diag_runahead_nosync_fuse.json); >= 512 KB thrashes L2
 #endif
 #ifndef ER_DEFAULT_FUSE
-#define ER_DEFAULT_FUSE 0
+#define ER_DEFAULT_FUSE 1   // tensor-parallel layer where the shape allows it (parity: tests/test_gpu_longctx.py, both variants)
 #endif
 
 static thread_local char g_err[512] = "";
