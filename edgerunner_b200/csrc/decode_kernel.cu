@@ -333,7 +333,7 @@ struct SnapState { int t, L, counter, last_tok, done; };     // one snapshot of 
 template <bool FUSE, typename Job>
 __device__ __forceinline__ void walk_jobs(const DecodeParams& p, const int t0, int L, Job job) {
     const int C = p.C, F = p.F, H = p.H, S = p.S, V = p.V, layers = p.layers, ustride = p.ustride, handicap = p.split_handicap;
-    const int nkb = p.nkb, Lmax = p.Lmax;
+    const int nkb = p.nkb;
     const __half* const wdec = p.wdec;
     const __half* const wfuse = FUSE ? p.wfuse : nullptr;
     const size_t fuse_layer = FUSE ? (size_t)H * C * kHoStride + (size_t)F * ustride : 0;   // fp16 per layer of the fused-phase weight copies
@@ -358,8 +358,8 @@ __device__ __forceinline__ void walk_jobs(const DecodeParams& p, const int t0, i
             if (ok && has_attn) {
                 const __half* kbase = kc + (((size_t)layer * H + a.h) * nkb + a.b0) * (size_t)(HV * 256);
                 ok = job(kbase, (size_t)(a.b1 - a.b0) * kKBlockBytes, kKVChunk, layer == 0 ? pass : 0);
-                const __half* vbase = vc + (((size_t)layer * H + a.h) * Lmax + a.k0) * HD;
-                if (ok) ok = job(vbase, (size_t)(a.k1 - a.k0) * HD * 2, kKVChunk, 0);
+                const __half* vbase = vc + (((size_t)layer * H + a.h) * nkb + a.b0) * (size_t)(HV * 256);
+                if (ok) ok = job(vbase, (size_t)(a.b1 - a.b0) * kKBlockBytes, kKVChunk, 0);
                 if (FUSE && ok) {   // this split's rows of the head's out_proj columns
                     const RowRange rs = cta_rows_of(C, blockIdx.x % (unsigned)S, (unsigned)S);
                     ok = job(wfuse + (size_t)layer * fuse_layer + ((size_t)a.h * C + rs.r0) * kHoStride, (size_t)(rs.r1 - rs.r0) * kHoStride * 2,
@@ -953,6 +953,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
     const int nb = a.b1 - a.b0;
     const int new_slot = nb * 32;                            // score slot just past the old blocks
     const uint32_t qs_s = s_addr(qs), sc_s = s_addr(sc);
+    __half* const q16s = reinterpret_cast<__half*>(red + 80);   // [96] the query as the fp16 tensor it is (A operand of the K pass)
     float M = -INFINITY;
     // the new key / value row (written by P1 of this step) are fetched NOW and used at the end of the K pass / at publish time, so
     // their L2 round trips hide behind the streamed passes
@@ -974,6 +975,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
             if (qrole) {
                 const float2 f = h2f2(w[4]);
                 qs[2 * (tid - 128)] = f.x; qs[2 * (tid - 128) + 1] = f.y;
+                reinterpret_cast<uint32_t*>(q16s)[tid - 128] = w[4];
             }
         }
     } else if (a.is_new) {
@@ -982,34 +984,49 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
     }
     if (FUSE) prof_stamp(p, pb + 5, prof_on);          // q (and the new k / v) polled
     if (nk > 0) {
-        if (!FUSE && tid < HD) qs[tid] = __half2float(__ushort_as_half(ldg_cg_u16(p.q16 + a.h * HD + tid)));
+        if (!FUSE && tid < HD) {
+            const unsigned short qh = ldg_cg_u16(p.q16 + a.h * HD + tid);
+            qs[tid] = __half2float(__ushort_as_half(qh));
+            q16s[tid] = __ushort_as_half(qh);
+        }
         cbar();
-
-        // ---- K pass ----
+        // Both passes run on the tensor cores (mma.sync m16n8k16, fp16 operands, fp32 accumulate — the arithmetic of the flash kernel the
+        // reference calls: S = Q K^T in fp32, P rounded to fp16 for P V).  K and V share one blocked cache layout
+        // [key/32][d/8][key%32][8]; a stage holds 4 blocks = 128 keys and warp w owns keys 16 w .. 16 w + 15 of EVERY stage in both passes,
+        // so the per-warp softmax maximum it normalises its scores with is the one it rescales its own P V partial with.
+        const int t4 = lane & 3, g8 = lane >> 2;
+        const uint32_t blk_off = (uint32_t)(warp >> 1) * kKBlockBytes;
+        // ---- K pass: scores[key] = q . k.  B operand = two key groups x two 8-dim chunks per ldmatrix.x4 (rows = keys: conflict-free) ----
         float lmax = -INFINITY;
         {
+            uint32_t qa[HD / 16][2];
+            const uint32_t q16_s = s_addr(q16s);
+#pragma unroll
+            for (int s = 0; s < HD / 16; s++) { qa[s][0] = lds_u32(q16_s + (uint32_t)(16 * s + 2 * t4) * 2); qa[s][1] = lds_u32(q16_s + (uint32_t)(16 * s + 8 + 2 * t4) * 2); }
+            const uint32_t k_off = blk_off + (uint32_t)((lane >> 3) & 1) * 512 + (uint32_t)((warp & 1) * 16 + (lane >> 4) * 8 + (lane & 7)) * 16;
             const int nch = (nb + 3) >> 2;
             for (int c = 0; c < nch; ++c, cur.advance(r.nstage)) {
                 mbar_wait(r.fullb(cur.stage), cur.parity);
-                const int here = min(4, nb - c * 4);
-                for (int bb = 0; bb < here; ++bb) {
-                    const int blk = c * 4 + bb;
-                    if ((blk & (kConsumerWarps - 1)) != warp) continue;
-                    const uint32_t kb = r.stage(cur.stage) + (uint32_t)bb * kKBlockBytes + lane * 16;
-                    uint4 kv[HV];
-                    lds128x4(kb, kv[0], kv[1], kv[2], kv[3]);
-                    lds128x4(kb + 2048, kv[4], kv[5], kv[6], kv[7]);
-                    lds128x4(kb + 4096, kv[8], kv[9], kv[10], kv[11]);
-                    float a0 = 0.f, a1 = 0.f;
+                if ((warp >> 1) < nb - c * 4) {
+                    uint32_t b[HD / 16][4];
+                    const uint32_t base = r.stage(cur.stage) + k_off;
 #pragma unroll
-                    for (int j = 0; j < HV; j += 2) {
-                        a0 = dot_k8(kv[j], lds_f4(qs_s + j * 32), lds_f4(qs_s + j * 32 + 16), a0);
-                        a1 = dot_k8(kv[j + 1], lds_f4(qs_s + j * 32 + 32), lds_f4(qs_s + j * 32 + 48), a1);
+                    for (int s = 0; s < HD / 16; s++) ldmatrix_x4(base + s * 1024, b[s][0], b[s][1], b[s][2], b[s][3]);
+                    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};      // key group 0 / 1 of this warp's 16 keys
+#pragma unroll
+                    for (int s = 0; s < HD / 16; s++) {
+                        mma_16816(d0, qa[s][0], qa[s][1], b[s][0], b[s][1]);
+                        mma_16816(d1, qa[s][0], qa[s][1], b[s][2], b[s][3]);
                     }
-                    const int key = (a.b0 + blk) * 32 + lane;
-                    const float sv = (key < a.k1) ? a0 + a1 : -INFINITY;      // slots >= L hold stale / unwritten data
-                    sts32(sc_s + (uint32_t)(blk * 32 + lane) * 4, sv);
-                    lmax = fmaxf(lmax, sv);
+                    // every row of D carries the same q: row 0 (lanes 0..3) holds keys 2 t4, 2 t4 + 1 of each group
+                    const int sl = c * 128 + 16 * warp + 2 * t4;                 // slot of d0[0]; key = a.k0 + slot (k0 is block aligned)
+                    const float s00 = (a.k0 + sl < a.k1) ? d0[0] : -INFINITY, s01 = (a.k0 + sl + 1 < a.k1) ? d0[1] : -INFINITY;   // slots >= L: stale data
+                    const float s10 = (a.k0 + sl + 8 < a.k1) ? d1[0] : -INFINITY, s11 = (a.k0 + sl + 9 < a.k1) ? d1[1] : -INFINITY;
+                    if (g8 == 0) {
+                        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(sc_s + (uint32_t)sl * 4), "f"(s00), "f"(s01) : "memory");
+                        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(sc_s + (uint32_t)(sl + 8) * 4), "f"(s10), "f"(s11) : "memory");
+                    }
+                    lmax = fmaxf(fmaxf(lmax, fmaxf(s00, s01)), fmaxf(s10, s11));
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
@@ -1026,51 +1043,65 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
         // per-warp maximum, and this warp's keys normalised by it: p = exp2((s - m_w) * cl2)
         const float mw = warp_max(lmax);
         __syncwarp();
-        for (int blk = warp; blk < nb; blk += kConsumerWarps) {
-            const uint32_t ad = sc_s + (uint32_t)(blk * 32 + lane) * 4;
-            sts32(ad, exp2f((lds32(ad) - mw) * cl2));                        // masked slots: exp2(-inf) = 0
+        for (int sl = (lane >> 4) * 128 + 16 * warp + (lane & 15); sl < nb * 32; sl += 256) {
+            const uint32_t ad = sc_s + (uint32_t)sl * 4;
+            sts32(ad, exp2f((lds32(ad) - mw) * cl2));                            // masked slots: exp2(-inf) = 0
         }
         if (a.is_new && warp == 0 && lane == 0) sts32(sc_s + (uint32_t)new_slot * 4, exp2f((lds32(sc_s + (uint32_t)new_slot * 4) - mw) * cl2));
         if (lane == 0) red[warp] = mw;
         cbar();
-        // merge the warp maxima; fw[w] rescales keys normalised by warp w
+        // merge the warp maxima; fw rescales keys normalised by this warp (red[32] = warp 0's factor, used for the new key at publish time)
 #pragma unroll
         for (int w = 0; w < kConsumerWarps; w++) M = fmaxf(M, red[w]);
-        if (tid < kConsumerWarps) red[32 + tid] = (red[tid] == -INFINITY) ? 0.f : exp2f((red[tid] - M) * cl2);
-        cbar();
-        const uint32_t fw_s = s_addr(red + 32);
-        // ---- V pass (also accumulates the softmax denominator on the vec == 0 lanes) ----
-        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const float fw = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * cl2);
+        if (tid == 0) red[32] = fw;
+        // ---- V pass: o[96] += p[key] * v[key][:]; A operand = p (fp16), B operand = ldmatrix.trans of (8 keys x 8 dims) patches ----
+        float o[HV][4];
+#pragma unroll
+        for (int j = 0; j < HV; j++) { o[j][0] = 0.f; o[j][1] = 0.f; o[j][2] = 0.f; o[j][3] = 0.f; }
         float lsum = 0.f;
-        const int sub = lane / HV, vec = lane % HV;            // lanes 0..23: 2 rows x 12 vectors; lanes 24..31 idle
         {
-            const int nch = (nold + 127) >> 7;
+            const uint32_t v_off = blk_off + (uint32_t)(lane >> 4) * 512 + (uint32_t)((warp & 1) * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * 16;
+            const int nch = (nb + 3) >> 2;
             for (int c = 0; c < nch; ++c, cur.advance(r.nstage)) {
                 mbar_wait(r.fullb(cur.stage), cur.parity);
-                const int here = min(128, nold - c * 128);
-                if (lane < 2 * HV) {
-                    const uint32_t st = r.stage(cur.stage) + vec * 16;
-                    for (int row = warp * 2 + sub; row < here; row += 2 * kConsumerWarps) {
-                        const int slot = c * 128 + row;                         // old key k0 + slot (k0 is block aligned)
-                        const uint4 vv = lds128(st + (uint32_t)row * (HD * 2));
-                        const float pp = lds32(sc_s + (uint32_t)slot * 4) * lds32(fw_s + (uint32_t)((slot >> 5) & (kConsumerWarps - 1)) * 4);
-                        float2 f;
-                        f = h2f2(vv.x); o[0] = fmaf(pp, f.x, o[0]); o[1] = fmaf(pp, f.y, o[1]);
-                        f = h2f2(vv.y); o[2] = fmaf(pp, f.x, o[2]); o[3] = fmaf(pp, f.y, o[3]);
-                        f = h2f2(vv.z); o[4] = fmaf(pp, f.x, o[4]); o[5] = fmaf(pp, f.y, o[5]);
-                        f = h2f2(vv.w); o[6] = fmaf(pp, f.x, o[6]); o[7] = fmaf(pp, f.y, o[7]);
-                        if (vec == 0) lsum += pp;
+                const int sl0 = c * 128 + 16 * warp;
+                if (sl0 < nold) {
+                    const uint32_t pa = sc_s + (uint32_t)(sl0 + 2 * t4) * 4;
+                    float p0, p1, p2, p3;
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(p0), "=f"(p1) : "r"(pa));
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(p2), "=f"(p3) : "r"(pa + 32));
+                    p0 *= fw; p1 *= fw; p2 *= fw; p3 *= fw;                      // slots in [nold, block end) hold exp2(-inf) = 0
+                    if (g8 == 0) lsum += (p0 + p1) + (p2 + p3);
+                    const __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+                    const uint32_t a_lo = *reinterpret_cast<const uint32_t*>(&h01), a_hi = *reinterpret_cast<const uint32_t*>(&h23);
+                    const uint32_t base = r.stage(cur.stage) + v_off;
+                    const int lim = nold - sl0;                                  // keys of this group that exist (>= 16: all)
+#pragma unroll
+                    for (int j2 = 0; j2 < HV / 2; j2++) {
+                        uint32_t b0, b1, b2, b3;
+                        ldmatrix_x4_trans(base + j2 * 1024, b0, b1, b2, b3);
+                        if (lim < 16) {
+                            // rows of the cache beyond the last key were never written (they may hold NaN bit patterns): 0 x NaN must not reach o
+                            const uint32_t m_lo = (2 * t4 < lim ? 0x0000ffffu : 0u) | (2 * t4 + 1 < lim ? 0xffff0000u : 0u);
+                            const uint32_t m_hi = (2 * t4 + 8 < lim ? 0x0000ffffu : 0u) | (2 * t4 + 9 < lim ? 0xffff0000u : 0u);
+                            b0 &= m_lo; b2 &= m_lo; b1 &= m_hi; b3 &= m_hi;
+                        }
+                        mma_16816(o[2 * j2], a_lo, a_hi, b0, b1);
+                        mma_16816(o[2 * j2 + 1], a_lo, a_hi, b2, b3);
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(r.emptyb(cur.stage));
             }
         }
-        if (lane < 2 * HV) {
+        if (g8 == 0) {
 #pragma unroll
-            for (int e = 0; e < 8; e++) vred[(warp * 2 + sub) * HD + vec * 8 + e] = o[e];
-            if (vec == 0) red[64 + warp * 2 + sub] = lsum;
+            for (int j = 0; j < HV; j++) { vred[warp * HD + 8 * j + 2 * t4] = o[j][0]; vred[warp * HD + 8 * j + 2 * t4 + 1] = o[j][1]; }
         }
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+        if (lane == 0) red[64 + warp] = lsum;
         cbar();
     }
     if (FUSE) prof_stamp(p, pb + 6, prof_on);          // K / V passes done
@@ -1080,15 +1111,15 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
     if (tid < HD) {
         float acc = 0.f;
         if (nk > 0) {
-#pragma unroll 4
-            for (int g = 0; g < 2 * kConsumerWarps; g++) acc += vred[g * HD + tid];
+#pragma unroll
+            for (int g = 0; g < kConsumerWarps; g++) acc += vred[g * HD + tid];
             if (a.is_new) acc = fmaf(sc[new_slot] * red[32], __half2float(__ushort_as_half(vnew)), acc);   // new key: normalised by warp 0
         }
         if (FUSE) ll_store(outl + tid, __float_as_uint(acc), flag); else outp[tid] = acc;
     } else if (tid == HD) {
         float l = 0.f;
         if (nk > 0) {
-            for (int g = 0; g < 2 * kConsumerWarps; g++) l += red[64 + g];
+            for (int g = 0; g < kConsumerWarps; g++) l += red[64 + g];
             if (a.is_new) l += sc[new_slot] * red[32];
         }
         const float mval = (nk > 0) ? M * rsqrtf((float)HD) : -INFINITY;        // max in softmax (scaled) units
@@ -1342,14 +1373,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                     prof_stamp(p, pb + 2, prof_on); prof_all(p, 2, all_on);
                     if (!FUSE) grid_arrive(p.bar, epoch, nosync);
                     if (own && r >= C) {
-                        if (r < 2 * C) {
-                            const int c = r - C, h = c / HD, d = c % HD;
-                            const size_t idx = ((((size_t)layer * H + h) * (size_t)p.nkb + (L >> 5)) * HV + (d >> 3)) * 256 + (size_t)(L & 31) * 8 + (d & 7);
-                            p.kc[idx] = hv;
-                        } else {
-                            const int c = r - 2 * C, h = c / HD, d = c % HD;
-                            p.vc[(((size_t)layer * H + h) * p.Lmax + L) * HD + d] = hv;
-                        }
+                        const int c = r < 2 * C ? r - C : r - 2 * C, h = c / HD, d = c % HD;     // K and V share the blocked layout
+                        const size_t idx = ((((size_t)layer * H + h) * (size_t)p.nkb + (L >> 5)) * HV + (d >> 3)) * 256 + (size_t)(L & 31) * 8 + (d & 7);
+                        (r < 2 * C ? p.kc : p.vc)[idx] = hv;
                     }
                     if (!FUSE) grid_wait(p.bar, epoch, nosync);
                 }

@@ -81,7 +81,7 @@ __global__ void f32_to_f16_kernel(const float* s, __half* d, size_t n) {
     if (i < n) d[i] = __float2half_rn(s[i]);
 }
 
-// ---- KV cache store: qkv16 [N][3C] -> K blocked [layer][h][key/32][d/8][key%32][8], V [layer][h][key][96] ------------
+// ---- KV cache store: qkv16 [N][3C] -> K and V, both blocked [layer][h][key/32][d/8][key%32][8] ------------------------------
 __global__ void kv_store_kernel(const __half* qkv16, int N, int C, int H, int layer, int pos0, int Lmax, int nkb, __half* kc, __half* vc) {
     const int D = C / H, DV = D / 8;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one 16-byte vector each
@@ -95,7 +95,7 @@ __global__ void kv_store_kernel(const __half* qkv16, int N, int C, int H, int la
     const uint4 vv = *reinterpret_cast<const uint4*>(qkv16 + (size_t)n * 3 * C + 2 * C + h * D + vec * 8);
     const size_t kidx = ((((size_t)layer * H + h) * nkb + (key >> 5)) * DV + vec) * 256 + (size_t)(key & 31) * 8;
     *reinterpret_cast<uint4*>(kc + kidx) = kv;
-    *reinterpret_cast<uint4*>(vc + (((size_t)layer * H + h) * Lmax + key) * D + vec * 8) = vv;
+    *reinterpret_cast<uint4*>(vc + kidx) = vv;
 }
 
 // ---- cross entropy on fp16-rounded logits, ignore_index = -100 (modeling_opt.py:500-505) ------------------------------

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 INFER = os.path.join(REPO, 'oracle', '_ref', 'drop_in', 'infer.py')
 
-DIMS = ['--hidden_dim', '768', '--num_heads', '8', '--num_layers', '2', '--point_hidden_dim', '128', '--point_num_heads', '2',
+DIMS = ['--generate_mode', 'greedy', '--hidden_dim', '768', '--num_heads', '8', '--num_layers', '2', '--point_hidden_dim', '128', '--point_num_heads', '2',
         '--point_latent_size', '64', '--point_latent_dim', '16', '--point_num', '256', '--num_cond_tokens', '65', '--max_seq_length', '512']
 
 
@@ -38,7 +38,7 @@ def test_reference_infer_py_runs_unmodified(tmp_path):
     from core.options import config_defaults
     from edgerunner_b200 import synth
     opt = replace(config_defaults['ArAE'], hidden_dim=768, num_heads=8, num_layers=2, point_hidden_dim=128, point_num_heads=2,
-                  point_latent_size=64, point_latent_dim=16, point_num=256, num_cond_tokens=65, max_seq_length=512)
+                  point_latent_size=64, point_latent_dim=16, point_num=256, num_cond_tokens=65, max_seq_length=512, generate_mode='greedy')
     sd = synth.synth_state_dict(opt, seed=9, eos_logit=-30.0)
     ckpt = str(tmp_path / 'synthetic.safetensors')
     save_file({k: v.contiguous() for k, v in sd.items()}, ckpt)
