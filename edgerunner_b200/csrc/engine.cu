@@ -114,7 +114,7 @@ struct er_engine {
     __half *kc, *vc, *q16, *y1, *h1, *y2, *attn16;
     float *part, *logits, *cond32;
     unsigned long long* ll = nullptr; size_t ll_words = 0;      // flagged exchange words of the tensor-parallel decode layer
-    __half* wfuse = nullptr; unsigned long long* acc = nullptr; int use_fuse = ER_DEFAULT_FUSE, S_fuse = 0;   // tensor-parallel decode layer
+    __half* wfuse = nullptr; int use_fuse = ER_DEFAULT_FUSE, S_fuse = 0;   // tensor-parallel decode layer
     er::DecodeState* st;
     unsigned* bar;
     int32_t* ids_dev;
@@ -292,14 +292,14 @@ static int create_impl(er_engine* e, const er_config* cfg) {
     e->grid = sms;
     e->S = sms / H; if (e->S > 16) e->S = 16; if (e->S < 1) { return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
     ALLOC(e->part, (size_t)H * 16 * 100);
-    e->ll_words = (size_t)3 * C / 2 + (size_t)H * 16 * 100;
+    // flagged words: q|k|v [3C/2], split partials [H][16][100], mailboxes [G][H][12] + [G][G][12], all-gather words 2 x [C/2]
+    e->ll_words = (size_t)3 * C / 2 + (size_t)H * 16 * 100 + (size_t)sms * H * 12 + (size_t)sms * sms * 12 + (size_t)C;
     ALLOC(e->ll, e->ll_words);
-    ALLOC(e->acc, 4 * (size_t)C);
     // tensor-parallel layer: S in {12, 9, 6} so that a CTA's 288 / S qkv rows stay inside one of q | k | v; needs the tensor-core
     // GEMV shapes (C % 256), <= 64 fc1 rows and <= 32 accumulator words per CTA
     e->S_fuse = 0;
     for (int cand : {12, 9, 6}) if (cand * H <= sms) { e->S_fuse = cand; break; }
-    if (C % 256 || (F + sms - 1) / sms + 1 > 64 || (C + sms - 1) / sms + 1 > 32 || (C & 1)) e->S_fuse = 0;
+    if (C % 256 || (F + sms - 1) / sms + 1 > 64 || 2 * ((C / 2 + sms - 1) / sms) > 12 || sms * 12 > 7 * 256 || sms > 255 || H > 16 * 16 || C > 1536) e->S_fuse = 0;
     if (!e->S_fuse) e->use_fuse = 0;
     e->sc_len = er::score_scratch_len(e->nkb, e->S, V);
     if (e->S_fuse) e->sc_len = std::max(e->sc_len, er::score_scratch_len(e->nkb, e->S_fuse, V));
@@ -549,8 +549,9 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.split_handicap = e->split_handicap;
     p.kc = e->kc; p.vc = e->vc; p.attn16 = e->attn16; p.head_cnt = e->bar + 64; p.q16 = e->q16; p.y1 = e->y1; p.h1 = e->h1; p.y2 = e->y2; p.part = e->part; p.logits = e->logits;
     p.ll_q = e->ll; p.ll_part = p.ll_q + 3 * C / 2;
+    p.mb1 = p.ll_part + (size_t)e->H * 16 * 100; p.mb2 = p.mb1 + (size_t)G * e->H * 12; p.g1 = p.mb2 + (size_t)G * G * 12; p.g2 = p.g1 + C / 2;
     p.poll_rounds = e->poll_rounds;
-    p.use_fuse = fuse; p.wfuse = e->wfuse; p.acc = e->acc;
+    p.use_fuse = fuse; p.wfuse = e->wfuse;
     p.xrep = e->xrep;
     p.pf_dist = e->pf_dist; p.dbg_nosync = e->dbg_nosync;
     p.st = e->st; p.bar = e->bar;
@@ -562,7 +563,7 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     for (int done = 0; done < max_new_tokens; done += chunk) {
         p.steps = std::min(chunk, max_new_tokens - done);
         CK(cudaMemsetAsync(e->bar, 0, (64 + 64) * 4, st));
-        if (p.use_fuse) { CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st)); CK(cudaMemsetAsync(e->acc, 0, 4 * (size_t)C * 8, st)); }
+        if (p.use_fuse) CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st));
         CKL(e, er_decode_launch(p, G, e->dec_smem, st));
     }
     if (out_len_dev) {
