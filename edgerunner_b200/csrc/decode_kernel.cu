@@ -1203,7 +1203,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
 // PROF: the timeline instrumentation is a separate instantiation so that the production kernel carries neither its registers nor its branches
 // FUSE: the tensor-parallel layer (see above); false = the five-exchange layer (grid barrier between dependent phases)
 template <bool PROF, bool FUSE>
-__global__ void __maxnreg__(200) decode_persistent_kernel(const __grid_constant__ DecodeParams p) {
+__global__ void __maxnreg__(192) decode_persistent_kernel(const __grid_constant__ DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C, F = p.F, H = p.H, V = p.V;
     // smem carve-up: ring first (128-byte aligned stages), then the small arrays

@@ -143,9 +143,16 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f16_kernel(GemmArgs g) {
 
 }  // namespace er
 
+cudaError_t er_gemm_tcgen05(const er::GemmArgs& a, cudaStream_t stream);   // gemm_tcgen05.cu: the tensor-memory kernel (production path)
+
 cudaError_t er_gemm(const er::GemmArgs& g, cudaStream_t stream) {
     using namespace er;
     if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+    {   // tcgen05 + TMA kernel whenever the operands meet the TMA alignment rules (every shape of the ArAE / tiny presets does); the
+        // mma.sync kernel below remains for odd strides
+        const cudaError_t e = er_gemm_tcgen05(g, stream);
+        if (e != cudaErrorNotSupported) return e;
+    }
     if ((g.K & 7) || (g.lda & 7) || (g.ldw & 7)) return cudaErrorInvalidValue;
     static bool attr[64] = {};                 // per DEVICE: the attribute belongs to the function on the current device's context
     const int smem = STAGES * (BM + BN) * 64;
