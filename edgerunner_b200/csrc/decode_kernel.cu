@@ -31,6 +31,8 @@
 #include "decode_kernel.h"
 #include "decode_partition.h"
 
+#include <cstdio>
+
 #include "common.cuh"
 
 namespace er {
@@ -1203,7 +1205,7 @@ __device__ ER_ATTN_INLINE Cursor attention_phase(const DecodeParams& p, const Ri
 // PROF: the timeline instrumentation is a separate instantiation so that the production kernel carries neither its registers nor its branches
 // FUSE: the tensor-parallel layer (see above); false = the five-exchange layer (grid barrier between dependent phases)
 template <bool PROF, bool FUSE>
-__global__ void __maxnreg__(192) decode_persistent_kernel(const __grid_constant__ DecodeParams p) {
+__global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __grid_constant__ DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C, F = p.F, H = p.H, V = p.V;
     // smem carve-up: ring first (128-byte aligned stages), then the small arrays
@@ -1486,6 +1488,23 @@ cudaError_t er_decode_launch(const er::DecodeParams& p, int grid, size_t smem, c
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&p};
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(er::kThreads), args, smem, stream);
+}
+
+// diagnostics: resource usage / occupancy of the four instantiations as the driver sees them
+extern "C" int er_debug_decode_report(char* buf, int n, unsigned long long smem) {
+    int off = 0;
+    for (int v = 0; v < 4; ++v) {
+        const void* fn = er_decode_kernel_fn((v & 1) != 0, (v & 2) != 0);
+        cudaFuncAttributes a{};
+        const cudaError_t e0 = cudaFuncGetAttributes(&a, fn);
+        const cudaError_t e1 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per = -1;
+        const cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, er::kThreads, smem);
+        off += snprintf(buf + off, n - off, "prof=%d fuse=%d: regs %d static_smem %zu local %zu maxThreads %d | getattr %d setattr %d occ %d -> blocks/SM %d (threads %d, dyn smem %llu)\n",
+                        v & 1, (v >> 1) & 1, a.numRegs, a.sharedSizeBytes, a.localSizeBytes, a.maxThreadsPerBlock, (int)e0, (int)e1, (int)e2, per, er::kThreads, smem);
+        cudaGetLastError();
+    }
+    return off;
 }
 
 int er_decode_max_grid(size_t smem) {
