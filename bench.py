@@ -322,8 +322,17 @@ def main():
                'd2h_bytes_per_step': int(len(toks) * 4 + 4), 'ms_per_step': dt / e2e_steps * 1e3, 'steps': e2e_steps,
                'api': 'core.models.LMM.generate(cond, num_faces, max_new_tokens, tokenizer, clean=True) incl. meto detokenize + mesh clean-up'}
 
+    comm = {'world_size': world, 'backend': 'none (single process)', 'gpus_active': 1}
     if world > 1:
         import torch.distributed as dist
+        # which GPUs actually ran a replica: one all_gather of (uuid, tokens generated) over the NCCL communicator used for the barriers
+        props = torch.cuda.get_device_properties(dev)
+        mine = {'rank': rank, 'gpu': props.name, 'uuid': str(getattr(props, 'uuid', local_rank)), 'tokens': int(n_tok)}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        comm = {'world_size': world, 'backend': dist.get_backend(), 'nccl_version': '.'.join(str(x) for x in torch.cuda.nccl.version()),
+                'gpus_active': len({r['uuid'] for r in allr}), 'tokens_per_rank': [r['tokens'] for r in allr],
+                'collectives_on_data_path': 0, 'note': 'replicas: NCCL carries only the timing barriers / max-reduce and this gather'}
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
@@ -368,7 +377,7 @@ def main():
         'config': {'workload': wl, 'tokens_per_step_per_gpu': n_tok, 'prefix_rows': L0, 'parallelism': f'replicas x{world}',
                    'l2': 'inputs larger than L2: 1.36 GB weights + up to 2.66 GB KV cache streamed per token vs 126 MB L2',
                    'weights': 'seeded synthetic, fp16 (edgerunner_b200.synth)'},
-        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'reference_gpu': ref_gpu,
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'reference_gpu': ref_gpu, 'comm': comm,
     }
     print(json.dumps(line), flush=True)
 

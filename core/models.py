@@ -115,14 +115,20 @@ class LMM(nn.Module):
         if self.training:
             raise NotImplementedError('training-mode forward (dropout, num-face dropout, autograd graph) is not on the B200 path: '
                                       'call model.eval(); the returned loss carries no graph')
-        masks = data.get('masks')
-        if masks is not None and not bool(masks.all()):
-            raise NotImplementedError('padded batches need the varlen attention path (not built yet)')
+        masks = data.get('masks')                      # [B, P+T] bool; right-padded batches (collate_fn) take the masked path
         tokens, labels = data['tokens'], data['labels']
         B, T = tokens.shape
         e = self.get_engine(max_new_tokens=getattr(self._engine, 'max_new_tokens', 64) if self._engine else 64,
                             max_tf_rows=B * (self.opt.num_cond_tokens + T))
-        losses, logits = e.forward_tf(data['conds'], tokens, labels, data['num_faces'].tolist(), self.opt.kl_weight, want_logits=True)
+        losses, logits, sums = e.forward_tf(data['conds'], tokens, labels, data['num_faces'].tolist(), self.opt.kl_weight, want_logits=True,
+                                            masks=masks, want_sums=True)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # data parallel over the batch (BASELINE configs[3]): ONE all-reduce of {sum of token CEs, token count, KL}; every rank gets
+            # the loss of the concatenated batch
+            from edgerunner_b200.dist import dp_reduce_losses
+            loss, loss_ce, loss_kl = dp_reduce_losses(sums[0], sums[1], sums[2], self.opt.kl_weight if self.opt.cond_mode == 'point' else 0.0)
+            losses = torch.stack([loss, loss_ce, loss_kl])
         out = {'loss': losses[0], 'loss_ce': losses[1], 'logits': logits}
         if self.opt.cond_mode == 'point':
             out['loss_kl'] = losses[2]

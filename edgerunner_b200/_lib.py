@@ -30,6 +30,7 @@ SIGNATURES = {
     'er_decode': (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_u64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'er_generate_host': (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_u64, c_i32, c_vp, c_vp]),
     'er_forward_tf': (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, C.POINTER(c_i32), c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    'er_forward_tf2': (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, C.POINTER(c_i32), c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]),
     'er_attention_bnhd': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     'er_weight_bytes_per_token': (c_i64, [c_vp]),
     'er_kv_bytes_per_row': (c_i64, [c_vp]),

@@ -41,9 +41,6 @@ struct DecodeParams {
     // barrier; ll_q: [3C/2] two fp16 each (q | new k | new v), ll_part: [H][S][100] one fp32 each (split partials).  Zeroed by the
     // host before each launch; flags are unique per (token, layer).
     unsigned long long *ll_q, *ll_part;
-    // reduce-scatter mailboxes [owner CTA][sender][12] (one fp32 each; mb1: senders = heads, mb2: senders = CTAs) and all-gather words
-    // [C/2] (two fp16 each) of the out_proj (g1) and fc2 (g2) outputs
-    unsigned long long *mb1, *mb2, *g1, *g2;
     int poll_rounds;   // all-thread polling rounds before a warp falls back to one spinning lane
     DecodeState *st;
     unsigned *bar;    // grid barrier counter (zeroed by the host before each launch)
@@ -55,8 +52,9 @@ struct DecodeParams {
     unsigned long long seed;
     // optional phase timeline: slot 0 = token start, then (end of phase, end of barrier) x 5 per layer, + lm_head pair
     unsigned long long *prof; int prof_token, prof_cta;
-    // tensor-parallel layer (use_fuse): per layer [H][C][HD+8] per-head out_proj units, then [F][ustride] transposed fc2 units
-    const __half *wfuse; int use_fuse;
+    // tensor-parallel layer (use_fuse): per layer [H][C][HD+8] per-head out_proj units, then [F][ustride] transposed fc2 units;
+    // acc: four copies of [C] u64 counting fixed-point accumulators (reduction k uses copy k & 3), zeroed by the host before each launch
+    const __half *wfuse; unsigned long long *acc; int use_fuse;
     // L2 run-ahead: a second streaming warp issues cp.async.bulk.prefetch.L2 for this CTA's future ring bytes, staying at most
     // pf_dist bytes ahead of the ring producer, so that HBM keeps streaming while the consumers sit in an exchange (0 = off)
     int pf_dist;

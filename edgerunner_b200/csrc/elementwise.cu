@@ -99,13 +99,15 @@ __global__ void kv_store_kernel(const __half* qkv16, int N, int C, int H, int la
 }
 
 // ---- cross entropy on fp16-rounded logits, ignore_index = -100 (modeling_opt.py:500-505) ------------------------------
-// row r of logits predicts labels[r] (the caller passes already-shifted views); one warp per row.
-__global__ void cross_entropy_kernel(const float* logits_pre, int ld, const int64_t* labels, int M, int V, float* loss_sum, int* count) {
+// row r of logits predicts labels[r] (the caller passes already-shifted views); one warp per row.  Per-row losses go to row_loss
+// (0 and valid = 0 for ignored rows); the sums are formed by reduce_rows_kernel in a FIXED order (no float atomics: the loss is
+// bit-reproducible run to run and independent of how rows are spread over ranks up to the final sum).
+__global__ void cross_entropy_kernel(const float* logits_pre, int ld, const int64_t* labels, int M, int V, float* row_loss, unsigned char* row_valid) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
     const long long lab = labels[row];
-    if (lab < 0) return;
+    if (lab < 0) { if (lane == 0) { row_loss[row] = 0.f; row_valid[row] = 0; } return; }
     const float* x = logits_pre + (size_t)row * ld;
     float mx = -INFINITY;
     for (int i = lane; i < V; i += 32) mx = fmaxf(mx, round_f16(x[i]));
@@ -113,20 +115,44 @@ __global__ void cross_entropy_kernel(const float* logits_pre, int ld, const int6
     float s = 0.f;
     for (int i = lane; i < V; i += 32) s += expf(round_f16(x[i]) - mx);
     s = warp_sum(s);
-    if (lane == 0) {
-        atomicAdd(loss_sum, logf(s) + mx - round_f16(x[lab]));
-        atomicAdd(count, 1);
+    if (lane == 0) { row_loss[row] = logf(s) + mx - round_f16(x[lab]); row_valid[row] = 1; }
+}
+// one block: sum[0] += sum of vals (double accumulation, fixed strided order + fixed tree), count[0] += number of valid rows
+__global__ void reduce_rows_kernel(const float* vals, const unsigned char* valid, int M, double* sum, int* count) {
+    __shared__ double sh[1024];
+    __shared__ int shc[1024];
+    double s = 0.0; int c = 0;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) { s += (double)vals[i]; c += valid ? valid[i] : 0; }
+    sh[threadIdx.x] = s; shc[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sh[threadIdx.x] += sh[threadIdx.x + o]; shc[threadIdx.x] += shc[threadIdx.x + o]; }
+        __syncthreads();
     }
+    if (threadIdx.x == 0) { *sum += sh[0]; if (count) *count += shc[0]; }
 }
 
-__global__ void sum_squares_kernel(const __half* x, size_t n, float* out) {
+// per-block partial sums of squares (fixed order inside a block), reduced by reduce_rows_kernel
+__global__ void sum_squares_kernel(const __half* x, size_t n, float* partial) {
+    __shared__ float sh[256];
     float s = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float v = __half2float(x[i]);
         s += v * v;
     }
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// flash_attn's pad_input (attention.py:88-93): rows of the attention output whose mask is false are zero
+__global__ void zero_masked_rows_kernel(__half* a16, const unsigned char* mask, int M, int C) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one 16-byte vector each
+    const size_t total = (size_t)M * (C >> 3);
+    if (i >= total) return;
+    const int row = (int)(i / (C >> 3));
+    if (!mask[row]) reinterpret_cast<uint4*>(a16)[i] = make_uint4(0, 0, 0, 0);
 }
 
 }  // namespace er
@@ -167,12 +193,19 @@ cudaError_t er_kv_store(const __half* qkv16, int N, int C, int H, int layer, int
     kv_store_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(qkv16, N, C, H, layer, pos0, Lmax, nkb, kc, vc);
     return cudaGetLastError();
 }
-cudaError_t er_cross_entropy(const float* logits_pre, int ld, const int64_t* labels, int M, int V, float* loss_sum, int* count,
-                             cudaStream_t stream) {
-    cross_entropy_kernel<<<(M + 7) / 8, 256, 0, stream>>>(logits_pre, ld, labels, M, V, loss_sum, count);
+cudaError_t er_cross_entropy(const float* logits_pre, int ld, const int64_t* labels, int M, int V, float* row_loss, unsigned char* row_valid,
+                             double* loss_sum, int* count, cudaStream_t stream) {
+    cross_entropy_kernel<<<(M + 7) / 8, 256, 0, stream>>>(logits_pre, ld, labels, M, V, row_loss, row_valid);
+    reduce_rows_kernel<<<1, 1024, 0, stream>>>(row_loss, row_valid, M, loss_sum, count);
     return cudaGetLastError();
 }
-cudaError_t er_sum_squares(const __half* x, size_t n, float* out, cudaStream_t stream) {
-    sum_squares_kernel<<<296, 256, 0, stream>>>(x, n, out);
+cudaError_t er_sum_squares(const __half* x, size_t n, float* partial296, double* out, cudaStream_t stream) {
+    sum_squares_kernel<<<296, 256, 0, stream>>>(x, n, partial296);
+    reduce_rows_kernel<<<1, 1024, 0, stream>>>(partial296, nullptr, 296, out, nullptr);
+    return cudaGetLastError();
+}
+cudaError_t er_zero_masked_rows(__half* a16, const unsigned char* mask, int M, int C, cudaStream_t stream) {
+    const size_t total = (size_t)M * (C >> 3);
+    zero_masked_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a16, mask, M, C);
     return cudaGetLastError();
 }

@@ -53,10 +53,12 @@ __global__ void init_state_kernel(er::DecodeState* st, int L) {
     st->t = 0; st->L = L; st->counter = 0; st->last_tok = 0; st->done = 0;
 }
 __global__ void finish_decode_kernel(const er::DecodeState* st, int32_t* out_len) { *out_len = st->t; }
-__global__ void tf_losses_kernel(const float* loss_sum, const int* count, const float* kl_sum, float kl_weight, int has_kl, float* losses) {
-    const float ce = *loss_sum / (float)max(*count, 1);
-    const float kl = has_kl ? 0.5f * *kl_sum : 0.f;
+// losses[0..2] = {loss, mean CE, KL}; sums[0..2] (optional) = {sum of token CEs, supervised tokens, KL}: what a data-parallel run all-reduces
+__global__ void tf_losses_kernel(const double* loss_sum, const int* count, const double* sq_sum, float kl_weight, int has_kl, float* losses, double* sums) {
+    const float ce = (float)(*loss_sum / (double)max(*count, 1));
+    const float kl = has_kl ? (float)(0.5 * *sq_sum) : 0.f;
     losses[1] = ce; losses[2] = kl; losses[0] = ce + (has_kl ? kl_weight * kl : 0.f);
+    if (sums) { sums[0] = *loss_sum; sums[1] = (double)*count; sums[2] = has_kl ? 0.5 * *sq_sum : 0.0; }
 }
 
 // row-major W[rows][K] -> decode units: unit (row * K/C + q) holds W[row][q*C .. (q+1)*C) followed by (ustride - C) zeros
@@ -114,7 +116,7 @@ struct er_engine {
     __half *kc, *vc, *q16, *y1, *h1, *y2, *attn16;
     float *part, *logits, *cond32;
     unsigned long long* ll = nullptr; size_t ll_words = 0;      // flagged exchange words of the tensor-parallel decode layer
-    __half* wfuse = nullptr; int use_fuse = ER_DEFAULT_FUSE, S_fuse = 0;   // tensor-parallel decode layer
+    __half* wfuse = nullptr; unsigned long long* acc = nullptr; int use_fuse = ER_DEFAULT_FUSE, S_fuse = 0;   // tensor-parallel decode layer
     er::DecodeState* st;
     unsigned* bar;
     int32_t* ids_dev;
@@ -123,7 +125,7 @@ struct er_engine {
     // dense workspace
     int maxrows;
     float* x32; __half *x16, *qkv16, *a16, *h16;
-    float* logits_all; float* tf_acc; int* tf_cnt;
+    float* logits_all; double* tf_acc; int* tf_cnt; float* tf_rows = nullptr; unsigned char* tf_valid = nullptr; float* tf_part = nullptr;
     __half* lat16;   // [B][LQ][LDP]
     // encoder workspace
     __half *emb16, *pf16, *kvx16, *kvo16, *qln16, *qq16, *ea16, *ex1, *ex1ln, *eff, *egg, *ex2, *pc16;
@@ -131,7 +133,7 @@ struct er_engine {
     bool cache_rows_stale = false;     // a decode ran since cache_rows was set: the exact row count lives in the device state
     unsigned long long* prof = nullptr; int prof_token = -1, prof_cta = 0;
     // decode-kernel knobs (defaults = the production configuration; changed only through er_debug_set)
-    int split_handicap = 4, xrep = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
+    int split_handicap = 4, split_handicap_fuse = 0, xrep = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
     int lat_batch_cap = 1;
 };
 
@@ -174,7 +176,11 @@ static int ensure_dense_rows(er_engine* e, int rows) {
     e->maxrows = 0;
     ALLOC(e->x32, (size_t)maxrows * C); ALLOC(e->x16, (size_t)maxrows * C); ALLOC(e->qkv16, (size_t)maxrows * 3 * C);
     ALLOC(e->a16, (size_t)maxrows * C); ALLOC(e->h16, (size_t)maxrows * F);
-    if (had_logits) ALLOC(e->logits_all, (size_t)maxrows * e->V);
+    if (had_logits) {
+        ALLOC(e->logits_all, (size_t)maxrows * e->V);
+        dev_free(e, &e->tf_rows); dev_free(e, &e->tf_valid);
+        ALLOC(e->tf_rows, maxrows); ALLOC(e->tf_valid, maxrows);
+    }
     e->maxrows = maxrows;
     return ER_OK;
 }
@@ -292,14 +298,14 @@ static int create_impl(er_engine* e, const er_config* cfg) {
     e->grid = sms;
     e->S = sms / H; if (e->S > 16) e->S = 16; if (e->S < 1) { return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
     ALLOC(e->part, (size_t)H * 16 * 100);
-    // flagged words: q|k|v [3C/2], split partials [H][16][100], mailboxes [G][H][12] + [G][G][12], all-gather words 2 x [C/2]
-    e->ll_words = (size_t)3 * C / 2 + (size_t)H * 16 * 100 + (size_t)sms * H * 12 + (size_t)sms * sms * 12 + (size_t)C;
+    e->ll_words = (size_t)3 * C / 2 + (size_t)H * 16 * 100;       // flagged words: q|k|v [3C/2], split partials [H][16][100]
     ALLOC(e->ll, e->ll_words);
+    ALLOC(e->acc, 4 * (size_t)C * 4);                               // four copies of C counting accumulators, one per 32-byte sector
     // tensor-parallel layer: S in {12, 9, 6} so that a CTA's 288 / S qkv rows stay inside one of q | k | v; needs the tensor-core
     // GEMV shapes (C % 256), <= 64 fc1 rows and <= 32 accumulator words per CTA
     e->S_fuse = 0;
     for (int cand : {12, 9, 6}) if (cand * H <= sms) { e->S_fuse = cand; break; }
-    if (C % 256 || (F + sms - 1) / sms + 1 > 64 || 2 * ((C / 2 + sms - 1) / sms) > 12 || sms * 12 > 7 * 256 || sms > 255 || H > 16 * 16 || C > 1536) e->S_fuse = 0;
+    if (C % 256 || (F + sms - 1) / sms + 1 > 64 || (C + sms - 1) / sms + 1 > 32 || (C & 1) || sms > 254) e->S_fuse = 0;
     if (!e->S_fuse) e->use_fuse = 0;
     e->sc_len = er::score_scratch_len(e->nkb, e->S, V);
     if (e->S_fuse) e->sc_len = std::max(e->sc_len, er::score_scratch_len(e->nkb, e->S_fuse, V));
@@ -319,7 +325,8 @@ static int create_impl(er_engine* e, const er_config* cfg) {
     ALLOC(e->a16, (size_t)maxrows * C); ALLOC(e->h16, (size_t)maxrows * F);
     e->logits_all = nullptr;
     if (cfg->max_tf_rows > 0) ALLOC(e->logits_all, (size_t)maxrows * V);
-    ALLOC(e->tf_acc, 4); ALLOC(e->tf_cnt, 4);
+    ALLOC(e->tf_acc, 4); ALLOC(e->tf_cnt, 4); ALLOC(e->tf_part, 296);
+    if (cfg->max_tf_rows > 0) { ALLOC(e->tf_rows, maxrows); ALLOC(e->tf_valid, maxrows); }
     e->lat_batch_cap = cfg->max_tf_rows > 0 ? std::max(1, cfg->max_tf_rows / (P + 2)) : 1;
     ALLOC(e->lat16, (size_t)e->lat_batch_cap * LQ * e->LDP); ALLOC(e->pc16, (size_t)LQ * C);
     if (cfg->has_point_encoder) {
@@ -478,7 +485,7 @@ extern "C" int er_encode_cond(er_engine* e, const float* conds_dev, int32_t n_po
 }
 
 // 24 x OPTDecoderLayer on M = B*N rows held in x32/x16 (modeling_opt.py:264-288, 185-232); store_kv: fill the decode cache
-static int decoder_layers(er_engine* e, int B, int N, bool store_kv, cudaStream_t st) {
+static int decoder_layers(er_engine* e, int B, int N, bool store_kv, cudaStream_t st, const unsigned char* row_mask = nullptr) {
     const int C = e->C, F = e->F, H = e->H, M = B * N;
     for (int l = 0; l < e->NL; l++) {
         er::GemmArgs g = mk_gemm(e->x16, C, e->wqkv + (size_t)l * 3 * C * C, C, e->bqkv + (size_t)l * 3 * C, M, 3 * C, C, er::GEMM_F16);
@@ -489,6 +496,7 @@ static int decoder_layers(er_engine* e, int B, int N, bool store_kv, cudaStream_
         a.ldq = a.ldk = a.ldv = 3 * C; a.ldo = C; a.q_bs = a.k_bs = a.v_bs = (long long)N * 3 * C; a.o_bs = (long long)N * C;
         a.B = B; a.H = H; a.Nq = N; a.Nk = N; a.D = 96; a.causal = 1;
         CKL(e, er_attention(a, st));
+        if (row_mask) CKL(e, er_zero_masked_rows(e->a16, row_mask, M, C, st));      // flash_attn pad_input: masked rows come back as zeros
         g = mk_gemm(e->a16, C, e->wo + (size_t)l * C * C, C, e->bo + (size_t)l * C, M, C, C, er::GEMM_F32_RES32);
         g.out32 = e->x32; g.ldo = C; g.res32 = e->x32; g.ldr = C; CKL(e, er_gemm(g, st));
         CKL(e, er_layernorm(e->x32, nullptr, C, e->ln1w + (size_t)l * C, e->ln1b + (size_t)l * C, e->x32, e->x16, C, M, C, st));
@@ -546,12 +554,13 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.w1 = e->w1; p.b1 = e->b1; p.w2 = e->w2; p.b2 = e->b2; p.ln2_w = e->ln2w; p.ln2_b = e->ln2b;
     p.lm_head = e->lm_head; p.embd = e->embd; p.pos = e->pos;
     p.wdec = e->wdec; p.ustride = e->ustride; p.upstage = e->upstage; p.use_mma = e->use_mma;
-    p.split_handicap = e->split_handicap;
+    // the last KV split also owns the new key; in the five-exchange layer it usually merges the head as well (worth ~4 blocks of streaming), in
+    // the tensor-parallel layer every split merges, so the splits are even
+    p.split_handicap = fuse ? e->split_handicap_fuse : e->split_handicap;
     p.kc = e->kc; p.vc = e->vc; p.attn16 = e->attn16; p.head_cnt = e->bar + 64; p.q16 = e->q16; p.y1 = e->y1; p.h1 = e->h1; p.y2 = e->y2; p.part = e->part; p.logits = e->logits;
     p.ll_q = e->ll; p.ll_part = p.ll_q + 3 * C / 2;
-    p.mb1 = p.ll_part + (size_t)e->H * 16 * 100; p.mb2 = p.mb1 + (size_t)G * e->H * 12; p.g1 = p.mb2 + (size_t)G * G * 12; p.g2 = p.g1 + C / 2;
     p.poll_rounds = e->poll_rounds;
-    p.use_fuse = fuse; p.wfuse = e->wfuse;
+    p.use_fuse = fuse; p.wfuse = e->wfuse; p.acc = e->acc;
     p.xrep = e->xrep;
     p.pf_dist = e->pf_dist; p.dbg_nosync = e->dbg_nosync;
     p.st = e->st; p.bar = e->bar;
@@ -563,7 +572,7 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     for (int done = 0; done < max_new_tokens; done += chunk) {
         p.steps = std::min(chunk, max_new_tokens - done);
         CK(cudaMemsetAsync(e->bar, 0, (64 + 64) * 4, st));
-        if (p.use_fuse) CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st));
+        if (p.use_fuse) { CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st)); CK(cudaMemsetAsync(e->acc, 0, 4 * (size_t)C * 4 * 8, st)); }
         CKL(e, er_decode_launch(p, G, e->dec_smem, st));
     }
     if (out_len_dev) {
@@ -600,14 +609,15 @@ extern "C" int er_generate_host(er_engine* e, const float* conds_host, int32_t n
     return ER_OK;
 }
 
-extern "C" int er_forward_tf(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, const int32_t* tokens_dev,
-                             const int64_t* labels_dev, const int32_t* num_faces_host, int32_t B, int32_t T, float kl_weight,
-                             float* losses_dev, float* logits_out_dev, void* stream) {
+extern "C" int er_forward_tf2(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, const int32_t* tokens_dev,
+                              const int64_t* labels_dev, const uint8_t* mask_dev, const int32_t* num_faces_host, int32_t B, int32_t T, float kl_weight,
+                              float* losses_dev, double* sums_dev, float* logits_out_dev, void* stream) {
     if (!e || !conds_dev || !tokens_dev || !labels_dev || !num_faces_host || !losses_dev) return set_err(ER_ERR_INVALID, "null argument");
     if (!e->finalized) return set_err(ER_ERR_STATE, "weights not finalized");
     cudaStream_t st = (cudaStream_t)stream;
     const int C = e->C, P = e->P, N = P + T, M = B * N, V = e->V;
-    if (M > e->maxrows || !e->logits_all || B > e->lat_batch_cap) return set_err(ER_ERR_CAPACITY, "teacher-forced batch of %d rows exceeds max_tf_rows", M);
+    if (!e->logits_all || B > e->lat_batch_cap) return set_err(ER_ERR_CAPACITY, "engine was created with max_tf_rows too small for a batch of %d samples", B);
+    { int r0 = ensure_dense_rows(e, M); if (r0) return r0; }
     if (N > e->cfg.max_positions) return set_err(ER_ERR_CAPACITY, "sequence longer than the position table");
     const size_t cstride = is_latent ? (size_t)e->LQ * e->LD : (size_t)n_points * 3;
     for (int b = 0; b < B; b++) {
@@ -617,21 +627,30 @@ extern "C" int er_forward_tf(er_engine* e, const float* conds_dev, int32_t n_poi
         if (r) return r;
         CKL(e, er_embed_prefix(cond_rows, P, tokens_dev + (size_t)b * T, T, e->embd, e->pos, C, cond_rows, e->x16 + (size_t)b * N * C, st));
     }
-    int r = decoder_layers(e, B, N, false, st);
+    int r = decoder_layers(e, B, N, false, st, mask_dev);
     if (r) return r;
     er::GemmArgs g = mk_gemm(e->x16, C, e->lm_head, C, nullptr, M, V, C, er::GEMM_F32);
     g.out32 = e->logits_all; g.ldo = V; CKL(e, er_gemm(g, st));
-    CK(cudaMemsetAsync(e->tf_acc, 0, 16, st));
+    CK(cudaMemsetAsync(e->tf_acc, 0, 32, st));
     CK(cudaMemsetAsync(e->tf_cnt, 0, 16, st));
-    for (int b = 0; b < B; b++)
-        CKL(e, er_cross_entropy(e->logits_all + (size_t)b * N * V, V, labels_dev + (size_t)b * N + 1, N - 1, V, e->tf_acc, e->tf_cnt, st));
+    for (int b = 0; b < B; b++) {       // shifted: row i of sample b predicts label i + 1 (modeling_opt.py:500-505); samples in order, fixed reduction order
+        e->launches++;
+        CKL(e, er_cross_entropy(e->logits_all + (size_t)b * N * V, V, labels_dev + (size_t)b * N + 1, N - 1, V, e->tf_rows, e->tf_valid, e->tf_acc, e->tf_cnt, st));
+    }
     const int has_kl = !is_latent;
-    if (has_kl) CKL(e, er_sum_squares(e->lat16, (size_t)B * e->LQ * e->LDP, e->tf_acc + 1, st));
+    if (has_kl) { e->launches++; CKL(e, er_sum_squares(e->lat16, (size_t)B * e->LQ * e->LDP, e->tf_part, e->tf_acc + 1, st)); }
     e->launches++;
-    tf_losses_kernel<<<1, 1, 0, st>>>(e->tf_acc, e->tf_cnt, e->tf_acc + 1, kl_weight, has_kl, losses_dev);
+    tf_losses_kernel<<<1, 1, 0, st>>>(e->tf_acc, e->tf_cnt, e->tf_acc + 1, kl_weight, has_kl, losses_dev, sums_dev);
     CK(cudaGetLastError());
     if (logits_out_dev) CK(cudaMemcpyAsync(logits_out_dev, e->logits_all, (size_t)M * V * 4, cudaMemcpyDeviceToDevice, st));
     return ER_OK;
+}
+
+extern "C" int er_forward_tf(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, const int32_t* tokens_dev,
+                             const int64_t* labels_dev, const int32_t* num_faces_host, int32_t B, int32_t T, float kl_weight,
+                             float* losses_dev, float* logits_out_dev, void* stream) {
+    return er_forward_tf2(e, conds_dev, n_points, is_latent, tokens_dev, labels_dev, nullptr, num_faces_host, B, T, kl_weight, losses_dev, nullptr,
+                          logits_out_dev, stream);
 }
 
 extern "C" int64_t er_weight_bytes_per_token(const er_engine* e) {
@@ -673,6 +692,7 @@ extern "C" int er_debug_set(er_engine* e, const char* key, int64_t value) {
     }
     else if (k == "gemv_cuda") { if (e->finalized) return set_err(ER_ERR_STATE, "gemv_cuda must be set before er_finalize_weights"); e->use_mma = (v == 0 && e->C % 256 == 0) ? 1 : 0; e->upstage = e->use_mma ? 8 : er_decode_stage_bytes() / (e->ustride * 2) / 8 * 8; }
     else if (k == "split_handicap") e->split_handicap = std::max(0, std::min(7, v));
+    else if (k == "split_handicap_fuse") e->split_handicap_fuse = std::max(0, std::min(7, v));
     else if (k == "xrep") e->xrep = std::max(1, std::min(8, v));
     else if (k == "poll_rounds") e->poll_rounds = std::max(0, v);
     else if (k == "pf_dist") e->pf_dist = std::max(0, v);

@@ -54,7 +54,11 @@ cudaError_t er_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t 
 // Scatter k,v rows of qkv16 [N][3C] (positions pos0..pos0+N) into the decode kernel's KV cache layouts
 cudaError_t er_kv_store(const __half* qkv16, int N, int C, int H, int layer, int pos0, int Lmax, int nkb, __half* kc, __half* vc,
                         cudaStream_t stream);
-// mean cross-entropy over rows with label != -100 on fp16-rounded logits (modeling_opt.py:500-505); loss_sum/count accumulate
-cudaError_t er_cross_entropy(const float* logits_pre, int ld, const int64_t* labels, int M, int V, float* loss_sum, int* count,
-                             cudaStream_t stream);
-cudaError_t er_sum_squares(const __half* x, size_t n, float* out, cudaStream_t stream);
+// cross-entropy over rows with label != -100 on fp16-rounded logits (modeling_opt.py:500-505): per-row losses -> row_loss / row_valid
+// (scratch, M entries), then *loss_sum += sum, *count += valid rows, in a fixed order (no float atomics)
+cudaError_t er_cross_entropy(const float* logits_pre, int ld, const int64_t* labels, int M, int V, float* row_loss, unsigned char* row_valid,
+                             double* loss_sum, int* count, cudaStream_t stream);
+// *out += sum of squares of x (partial296: scratch of 296 floats), fixed order
+cudaError_t er_sum_squares(const __half* x, size_t n, float* partial296, double* out, cudaStream_t stream);
+// rows of a16 [M][C] whose mask byte is 0 become zero (flash_attn pad_input)
+cudaError_t er_zero_masked_rows(__half* a16, const unsigned char* mask, int M, int C, cudaStream_t stream);

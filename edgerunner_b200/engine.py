@@ -135,8 +135,10 @@ class Engine:
                                                  int(bool(use_fsm)), out.ctypes.data, C.byref(n)))
         return out[:n.value].astype(np.int64)
 
-    def forward_tf(self, conds: torch.Tensor, tokens: torch.Tensor, labels: torch.Tensor, num_faces, kl_weight: float, want_logits=False):
-        """Teacher-forced forward (eval-mode LMM.forward).  conds [B,n,3] | [B,Lq,Ld]; tokens [B,T]; labels [B,P+T]."""
+    def forward_tf(self, conds: torch.Tensor, tokens: torch.Tensor, labels: torch.Tensor, num_faces, kl_weight: float, want_logits=False,
+                   masks: Optional[torch.Tensor] = None, want_sums=False):
+        """Teacher-forced forward (eval-mode LMM.forward).  conds [B,n,3] | [B,Lq,Ld]; tokens [B,T]; labels [B,P+T]; masks [B,P+T] bool
+        (right-padded) or None.  -> (losses[3], logits | None[, sums[3] = ce_sum, n_tokens, kl])."""
         B, T = tokens.shape
         is_latent = int(self.opt.cond_mode == 'point_latent')
         conds = conds.to(self.device, torch.float32).contiguous()
@@ -144,12 +146,23 @@ class Engine:
         lab = labels.to(self.device, torch.int64).contiguous()
         nf = (C.c_int32 * B)(*[int(x) for x in num_faces])
         losses = torch.zeros(3, dtype=torch.float32, device=self.device)
+        sums = torch.zeros(3, dtype=torch.float64, device=self.device)
         logits = torch.empty((B, self.P + T, self.V), dtype=torch.float32, device=self.device) if want_logits else None
+        m8 = None
+        if masks is not None:
+            m = masks.to(self.device).bool()
+            if m.shape != (B, self.P + T):
+                raise ValueError(f'masks must be [B, P+T] = {(B, self.P + T)}, got {tuple(m.shape)}')
+            if bool((m[:, 1:] & ~m[:, :-1]).any()):
+                raise NotImplementedError('only right-padded attention masks are supported (collate_fn pads at the end)')
+            if not bool(m.all()):
+                m8 = m.to(torch.uint8).contiguous()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.er_forward_tf(self.h, conds.data_ptr(), conds.shape[1], is_latent, tok.data_ptr(), lab.data_ptr(), nf, B, T,
-                                              C.c_float(kl_weight), losses.data_ptr(), logits.data_ptr() if logits is not None else None,
-                                              _stream()))
-        return losses, logits
+            _lib.check(self.lib.er_forward_tf2(self.h, conds.data_ptr(), conds.shape[1], is_latent, tok.data_ptr(), lab.data_ptr(),
+                                               m8.data_ptr() if m8 is not None else None, nf, B, T, C.c_float(kl_weight), losses.data_ptr(),
+                                               sums.data_ptr(), logits.data_ptr() if logits is not None else None, _stream()))
+        self._keep = [m8]
+        return (losses, logits, sums) if want_sums else (losses, logits)
 
     # ---- introspection ----------------------------------------------------------------------------------------------------
     def weight_bytes_per_token(self) -> int:

@@ -98,6 +98,17 @@ int er_forward_tf(er_engine* e, const float* conds_dev, int32_t n_points, int32_
                   const int64_t* labels_dev, const int32_t* num_faces_host, int32_t B, int32_t T, float kl_weight,
                   float* losses_dev, float* logits_out_dev, void* stream);
 
+/* er_forward_tf with the two things a data-parallel, padded batch needs (BASELINE configs[3]):
+ * mask_dev (optional) [B][P+T] bytes, the reference's `masks` (core/models.py:154) with the P condition rows prepended as ones: 1 = real token,
+ *   0 = padding.  Only RIGHT-padded masks are accepted by the Python layer (collate_fn pads at the end, provider.py:469-541): for those the
+ *   varlen flash path of the reference (attention.py:65-93: unpad -> causal varlen -> pad_input) equals dense causal attention with the
+ *   masked rows zeroed afterwards, which is what runs here.
+ * sums_dev (optional) double[3] = {sum of the supervised tokens' cross-entropies, number of supervised tokens, KL term} of this call: the ONE
+ *   vector a data-parallel run all-reduces (edgerunner_b200/dist.py::dp_reduce_losses); all reductions are fixed-order (bit-reproducible). */
+int er_forward_tf2(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, const int32_t* tokens_dev,
+                   const int64_t* labels_dev, const uint8_t* mask_dev, const int32_t* num_faces_host, int32_t B, int32_t T, float kl_weight,
+                   float* losses_dev, double* sums_dev, float* logits_out_dev, void* stream);
+
 /* The op seam core/transformer/attention.py:27-62 `attention(q, k, v, causal)` for unmasked fp16 inputs:
  * q [B][Nq][H][D], k/v [B][Nk][H][D] contiguous, out [B][Nq][H][D]; D in {64, 96}; causal requires Nq == Nk
  * (single-query causal attention over a cache is inside er_decode).  Engine-free. */
