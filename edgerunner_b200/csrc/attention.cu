@@ -188,9 +188,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnArgs a) {
 
 }  // namespace er
 
+cudaError_t er_attention_tcgen05(const er::AttnArgs& a, cudaStream_t stream);   // attention_tcgen05.cu: the tensor-memory kernel (production path)
+int g_er_dense_legacy = 0;      // er_debug_set(NULL, "dense_legacy", 1): force the mma.sync GEMM / attention kernels (A/B timing)
+
 cudaError_t er_attention(const er::AttnArgs& a, cudaStream_t stream) {
     using namespace er;
     if (a.Nq <= 0 || a.Nk <= 0) return cudaSuccess;
+    if (!g_er_dense_legacy) {
+        const cudaError_t e = er_attention_tcgen05(a, stream);
+        if (e != cudaErrorNotSupported) return e;
+    }
     dim3 grid((a.Nq + AQ - 1) / AQ, a.H, a.B);
     if (a.D == 96) {
         const int smem = (AQ + 4 * AK) * (96 * 2 + 16);

@@ -1,0 +1,315 @@
+// Multi-row attention (prefill / point encoder / teacher-forced forward) on the 5th-generation tensor cores: softmax(Q K^T / sqrt(D)) V with
+// fp16 operands, fp32 scores / statistics / accumulation, probabilities rounded to fp16 before P V — the arithmetic of the flash kernel the
+// reference calls (core/transformer/attention.py:44-46).  Replaces the mma.sync kernel of attention.cu where the operands meet the TMA rules.
+//
+// One CTA = one (batch, head, 128-query tile); key blocks of 64; 192 threads; two CTAs per SM (80 KB of shared memory and 256 TMEM columns
+// each), so one CTA's softmax overlaps the other's MMAs:
+//   warp 0      TMA producer: Q once, then per key block K and V as 3-D bulk tensor copies {64 dims, 1 head, 64|128 rows} with 128-byte swizzle.
+//               D = 96 is two 64-dim atoms, the second half-filled: the tensor's innermost extent IS the head dim, so the copy engine
+//               zero-fills dims 96..127 (K = 128 for Q K^T costs 33 % more MMA time there and nothing anywhere else)
+//   warp 1      MMA issuer (one elected lane): S[128 x 64] = Q K^T (tcgen05.mma M 128, N 64, K-major x K-major) into TMEM columns 0..63;
+//               O_blk[128 x D] = P V (A = P from shared memory, K-major; B = the V tile AS LOADED, i.e. MN-major: dims contiguous) into
+//               TMEM columns 64..64+D; tcgen05.commit publishes S / O_blk and frees the K / V buffers for the next copies
+//   warps 2..5  softmax: thread = query row (TMEM lane).  Pass 1 reads S for the row maximum, pass 2 re-reads it (TMEM reads are cheap,
+//               registers are not), exponentiates, rounds to fp16 and stores P in the K-major swizzled layout the MMA wants; then
+//               O = O * alpha + O_blk from TMEM.  K(j+1) streams in under softmax(j) / P V(j), V(j+1) under Q K^T(j+1) / softmax(j+1).
+// SASS: UTCHMMA, UTMALDG.3D, LDTM, UTCBAR.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace er {
+namespace fa {
+
+constexpr int BQ = 128, BKEY = 64, THREADS = 192;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr int ATOM_Q = BQ * 128;            // bytes of one 64-dim atom of the Q tile (128 rows x 128 B)
+constexpr int ATOM_K = BKEY * 128;          // ... of a K / V tile (64 rows x 128 B)
+
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor, version 1, SWIZZLE_128B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {          // rows = M/N index, 64 K-elements (128 B) per row
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t atom_bytes) {   // rows = K index (8-row groups 1024 B apart), 64 N-elements per row,
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((atom_bytes >> 4) & 0x3FFF) << 16) |   // next 64 N-elements `atom_bytes` further (LBO)
+           ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor: D fp32, A/B fp16, A K-major, M = 128
+__device__ __forceinline__ uint32_t idesc(int N, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t id, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(id), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+          "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+          "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Args {
+    __half* out; long long o_bs; int ldo;
+    int B, H, Nq, Nk, causal;
+    float scale_log2;        // softmax scale * log2(e)
+};
+
+template <int D>
+__global__ void __launch_bounds__(THREADS, 2)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                         const __grid_constant__ Args a) {
+    constexpr int NA = (D + 63) / 64;                  // 64-dim atoms per tile row
+    constexpr int KS1 = NA * 4;                        // k16 steps of Q K^T (head dim padded to NA * 64 with zeros)
+    constexpr int Q_BYTES = NA * ATOM_Q, K_BYTES = NA * ATOM_K;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long q_full, k_full, v_full, k_empty, v_empty, s_full, p_full, o_full;
+    __shared__ uint32_t tmem_base_s;
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+    unsigned char* sQ = base;                          // [NA][128 rows][128 B]
+    unsigned char* sK = sQ + Q_BYTES;                  // [NA][64 rows][128 B]
+    unsigned char* sV = sK + K_BYTES;                  // [NA][64 rows][128 B]
+    unsigned char* sP = sV + K_BYTES;                  // [128 rows][128 B]   (64 keys, K-major, swizzled)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+    int nblk = (a.Nk + BKEY - 1) / BKEY;
+    if (a.causal) nblk = min(nblk, (m0 + BQ + BKEY - 1) / BKEY);
+
+    if (threadIdx.x == 0) {
+        mbar_init(s_addr(&q_full), 1); mbar_init(s_addr(&k_full), 1); mbar_init(s_addr(&v_full), 1);
+        mbar_init(s_addr(&k_empty), 1); mbar_init(s_addr(&v_empty), 1);
+        mbar_init(s_addr(&s_full), 1); mbar_init(s_addr(&p_full), 4); mbar_init(s_addr(&o_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + BKEY;
+
+    if (warp == 0) {
+        if (lane == 0) {                                          // ===== TMA producer =====
+            mbar_expect_tx(s_addr(&q_full), Q_BYTES);
+#pragma unroll
+            for (int t = 0; t < NA; t++) tma_load_3d(s_addr(sQ + t * ATOM_Q), &map_q, t * 64, h, b * a.Nq + m0, s_addr(&q_full));
+            for (int j = 0; j < nblk; ++j) {
+                if (j > 0) mbar_wait(s_addr(&k_empty), (j - 1) & 1);          // Q K^T of block j-1 has read the K buffer
+                mbar_expect_tx(s_addr(&k_full), K_BYTES);
+#pragma unroll
+                for (int t = 0; t < NA; t++) tma_load_3d(s_addr(sK + t * ATOM_K), &map_k, t * 64, h, b * a.Nk + j * BKEY, s_addr(&k_full));
+                if (j > 0) mbar_wait(s_addr(&v_empty), (j - 1) & 1);          // P V of block j-1 has read the V buffer
+                mbar_expect_tx(s_addr(&v_full), K_BYTES);
+#pragma unroll
+                for (int t = 0; t < NA; t++) tma_load_3d(s_addr(sV + t * ATOM_K), &map_v, t * 64, h, b * a.Nk + j * BKEY, s_addr(&v_full));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                          // ===== MMA issuer =====
+            const uint32_t id1 = idesc(BKEY, 0), id2 = idesc(D, 1);
+            mbar_wait(s_addr(&q_full), 0);
+            for (int j = 0; j < nblk; ++j) {
+                // S = Q K^T.  S of block j-1 has been consumed: the softmax warps arrived on p_full(j-1) after reading it, and P V(j-1) below
+                // was issued after that wait.
+                mbar_wait(s_addr(&k_full), j & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int s = 0; s < KS1; ++s) {
+                    const uint64_t da = desc_kmajor(s_addr(sQ + (s >> 2) * ATOM_Q) + (s & 3) * 32);
+                    const uint64_t db = desc_kmajor(s_addr(sK + (s >> 2) * ATOM_K) + (s & 3) * 32);
+                    umma_f16(tmem_s, da, db, id1, s != 0);
+                }
+                umma_commit(s_addr(&k_empty));
+                umma_commit(s_addr(&s_full));
+                // O_blk = P V once the softmax warps have written P (and have finished reading O_blk of block j-1: program order on their side)
+                mbar_wait(s_addr(&p_full), j & 1);
+                mbar_wait(s_addr(&v_full), j & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int s = 0; s < BKEY / 16; ++s) {
+                    const uint64_t da = desc_kmajor(s_addr(sP) + s * 32);
+                    const uint64_t db = desc_mnmajor(s_addr(sV) + s * 2048, ATOM_K);      // 16 keys further = two 8-row groups
+                    umma_f16(tmem_o, da, db, id2, s != 0);
+                }
+                umma_commit(s_addr(&v_empty));
+                umma_commit(s_addr(&o_full));
+            }
+        }
+    } else {                                                      // ===== softmax / epilogue: thread = query row =====
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;                           // row inside the tile = TMEM lane
+        const int qi = m0 + r;
+        const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+        float o[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) o[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < nblk; ++j) {
+            const int k0 = j * BKEY;
+            const bool edge = (a.causal && k0 + BKEY - 1 > m0) || (k0 + BKEY > a.Nk);      // some (row, key) pairs of this block are masked
+            mbar_wait(s_addr(&s_full), j & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t v[32];
+            // pass 1: row maximum
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c0 = 0; c0 < BKEY; c0 += 32) {
+                tmem_ld32(tmem_s + lane_sel + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    float s = __uint_as_float(v[i]);
+                    if (edge && ((a.causal && k0 + c0 + i > qi) || k0 + c0 + i >= a.Nk)) s = -INFINITY;
+                    mx = fmaxf(mx, s);
+                }
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float msc = (m_new == -INFINITY) ? 0.f : m_new * a.scale_log2;
+            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * a.scale_log2 - msc);
+            // pass 2: p = exp2(s * scale - m * scale), fp16, into the swizzled K-major P tile (row r: 128 B, 16-byte chunk c at position c ^ (r & 7))
+            float lsum = 0.f;
+            const uint32_t prow = s_addr(sP) + (uint32_t)r * 128;
+#pragma unroll
+            for (int c0 = 0; c0 < BKEY; c0 += 32) {
+                tmem_ld32(tmem_s + lane_sel + c0, v);
+                uint32_t ph[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+                    if (edge) {
+                        if ((a.causal && k0 + c0 + i > qi) || k0 + c0 + i >= a.Nk) s0 = -INFINITY;
+                        if ((a.causal && k0 + c0 + i + 1 > qi) || k0 + c0 + i + 1 >= a.Nk) s1 = -INFINITY;
+                    }
+                    const float p0 = exp2f(s0 * a.scale_log2 - msc), p1 = exp2f(s1 * a.scale_log2 - msc);
+                    lsum += p0 + p1;
+                    const __half2 hh = __floats2half2_rn(p0, p1);
+                    ph[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int chunk = (c0 >> 3) + c;
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (uint32_t)((chunk ^ (r & 7)) * 16)), "r"(ph[4 * c]), "r"(ph[4 * c + 1]),
+                                 "r"(ph[4 * c + 2]), "r"(ph[4 * c + 3]) : "memory");
+                }
+            }
+            l_run = l_run * alpha + lsum;
+            m_run = m_new;
+            // P is read by the tensor core through the async proxy; S has been fully read
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_addr(&p_full));
+            // O = O * alpha + O_blk
+            mbar_wait(s_addr(&o_full), j & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < D; c0 += 32) {
+                tmem_ld32(tmem_o + lane_sel + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) o[c0 + i] = fmaf(o[c0 + i], alpha, __uint_as_float(v[i]));
+            }
+        }
+        if (qi < a.Nq) {
+            const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+            __half* op = a.out + (size_t)b * a.o_bs + (size_t)qi * a.ldo + (size_t)h * D;
+#pragma unroll
+            for (int c = 0; c < D / 8; c++) {
+                __align__(16) __half hh[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) hh[i] = __float2half_rn(o[8 * c + i] * inv);
+                *reinterpret_cast<uint4*>(op + 8 * c) = *reinterpret_cast<const uint4*>(hh);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiled encode_fn() {
+    static EncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiled)p;
+    }
+    return fn;
+}
+// view [rows][H][D] (row pitch ld elements, head h at h * D): dims {D, H, rows}; box {64, 1, box_rows}; 128-byte swizzle; OOB = zero
+static bool make_map(CUtensorMap* map, const __half* base, long long rows, int H, int D, int ld, int box_rows) {
+    EncodeTiled enc = encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)H, (cuuint64_t)rows};
+    const cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)ld * 2};
+    const cuuint32_t box[3] = {64, 1, (cuuint32_t)box_rows};
+    const cuuint32_t elem[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int D>
+static cudaError_t launch(const er::AttnArgs& a, cudaStream_t stream) {
+    CUtensorMap mq, mk, mv;
+    if (!make_map(&mq, a.q, (long long)a.B * a.Nq, a.H, D, a.ldq, BQ) || !make_map(&mk, a.k, (long long)a.B * a.Nk, a.H, D, a.ldk, BKEY) ||
+        !make_map(&mv, a.v, (long long)a.B * a.Nk, a.H, D, a.ldv, BKEY))
+        return cudaErrorNotSupported;
+    Args g{};
+    g.out = a.out; g.o_bs = a.o_bs; g.ldo = a.ldo; g.B = a.B; g.H = a.H; g.Nq = a.Nq; g.Nk = a.Nk; g.causal = a.causal;
+    g.scale_log2 = rsqrtf((float)D) * 1.4426950408889634f;
+    constexpr int NA = (D + 63) / 64;
+    const size_t smem = (size_t)NA * ATOM_Q + 2 * (size_t)NA * ATOM_K + (size_t)BQ * 128 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((a.Nq + BQ - 1) / BQ, a.H, a.B);
+    attention_tcgen05_kernel<D><<<grid, THREADS, smem, stream>>>(mq, mk, mv, g);
+    return cudaGetLastError();
+}
+
+}  // namespace fa
+}  // namespace er
+
+// -> cudaErrorNotSupported when the operand views do not meet the TMA rules (the caller then uses the mma.sync kernel)
+cudaError_t er_attention_tcgen05(const er::AttnArgs& a, cudaStream_t stream) {
+    // batches must be back to back in one row space, rows 16-byte aligned, head h at h * D inside a row
+    if ((a.ldq & 7) || (a.ldk & 7) || (a.ldv & 7) || (a.ldo & 7) || ((uintptr_t)a.q & 15) || ((uintptr_t)a.k & 15) || ((uintptr_t)a.v & 15) || ((uintptr_t)a.out & 15))
+        return cudaErrorNotSupported;
+    if (a.B > 1 && (a.q_bs != (long long)a.Nq * a.ldq || a.k_bs != (long long)a.Nk * a.ldk || a.v_bs != (long long)a.Nk * a.ldv)) return cudaErrorNotSupported;
+    if (a.H * a.D > a.ldq || a.H * a.D > a.ldk || a.H * a.D > a.ldv) return cudaErrorNotSupported;
+    if (a.D == 96) return er::fa::launch<96>(a, stream);
+    if (a.D == 64) return er::fa::launch<64>(a, stream);
+    return cudaErrorNotSupported;
+}

@@ -629,11 +629,10 @@ constexpr float kFixInv = 1.0f / 4294967296.0f;
 constexpr unsigned long long kFixBias = 1ull << 47;        // every addend is non-negative and < 2^48: 255 of them cannot carry into the count
 constexpr unsigned long long kFixOne = 1ull << 56;
 constexpr unsigned long long kFixMask = (1ull << 56) - 1;
-// One accumulator per 32-byte sector (element u lives at word u * kAccStride): measured with 16 accumulators per 128-byte line, the 2 368
-// atomics that land on each line serialise in ONE L2 slice and only 48 of the 184 slices work (lines 2k / 2k+1 share a slice) — 5.3 us per
-// fc2 reduction (profiles/r02_phase_timeline_tensor_parallel_v1.json).  At 8 accumulators per 256-byte chunk the 1536 elements cover 192
-// chunks, i.e. every slice, and a poller touches exactly one sector per element.
-constexpr int kAccStride = 4;
+// Element u lives at word u * kAccStride.  Measured: a fc2 reduction (148 x 1536 atomics) takes ~5.5 us whether the accumulators are
+// packed (stride 1) or spread one per 32-byte sector (stride 4: 7.9 us — more sectors per warp-wide RED, no gain from more L2 slices):
+// the cost is the NUMBER of atomic operations (~40 per ns chip-wide), not their placement.  Hence the groups of four below.
+constexpr int kAccStride = 1;
 __device__ __forceinline__ void fix_add_cnt(unsigned long long* acc, float v) {
     v = fminf(fmaxf(v, -32000.f), 32000.f);                 // also maps NaN to a number: the count must always arrive
     const long long q = __float2ll_rn(v * kFixScale);       // exact for |v| >= 2^-9, rounded to 2^-32 below
@@ -1468,9 +1467,24 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                         cur = fc2_job(ring, cur, nr, C, p.ustride, s_addr(h1s), part_s);
                         prof_stamp(p, pb + 13, prof_on);      // fc2 partial sums computed (atomics follow)
                         cbar();
-                        {   // every CTA starts at its own offset: the first wave of 148 x 256 atomics is spread over all slices
-                            const int rot = (int)((blockIdx.x * (unsigned)(C / 8 * 3 + 8)) % (unsigned)C);
-                            for (int i = tid; i < C; i += kConsumers) { int u = i + rot; if (u >= C) u -= C; fix_add_cnt(acc_y2 + (size_t)u * kAccStride, part[u]); }
+                        if (p.red_group == 4) {
+                            // pre-reduce among 4 CTAs through flagged words, then add: 148 x 1536 atomics took ~5.5 us of every layer; with groups of
+                            // four each CTA sends the three quarters it does not own to their owners, sums the three it receives with its own (fixed
+                            // order) and issues C/4 atomics: 4x fewer atomics per element (37 addends), one extra hop among 4 CTAs that finish together
+                            const int me = (int)(blockIdx.x & 3u), g4 = (int)(blockIdx.x >> 2), Q = C >> 2;
+                            for (int i = tid; i < 3 * Q; i += kConsumers) {
+                                const int q = (me + 1 + i / Q) & 3, e = i % Q;
+                                ll_store(p.xq + ((size_t)(4 * g4 + q) * 4 + me) * Q + e, __float_as_uint(part[q * Q + e]), flag);
+                            }
+                            for (int e0 = 0; e0 < Q; e0 += kConsumers) {
+                                const int e = e0 + tid;
+                                uint32_t w[3] = {0u, 0u, 0u};
+                                ll_poll<3>(w, (e < Q && !nosync) ? 7u : 0u, flag, p.poll_rounds,
+                                           [&](int j) { return p.xq + ((size_t)blockIdx.x * 4 + ((me + 1 + j) & 3)) * Q + e; });
+                                if (e < Q) fix_add_cnt(acc_y2 + (size_t)(me * Q + e) * kAccStride, ((part[me * Q + e] + __uint_as_float(w[0])) + __uint_as_float(w[1])) + __uint_as_float(w[2]));
+                            }
+                        } else {
+                            for (int u = tid; u < C; u += kConsumers) fix_add_cnt(acc_y2 + (size_t)u * kAccStride, part[u]);
                         }
                     }
                 }
@@ -1499,7 +1513,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                 if (!FUSE) grid_barrier(p.bar, epoch, nosync);
                 prof_stamp(p, pb + 14, prof_on); prof_all(p, 14, all_on);
                 // ---------------- x = LN2(x + y2) ------------------------------------------------------------------------------------------
-                residual_layer_norm(xres_s, xin_s, p.y2 + (size_t)xcopy * C, false, lp2, C, inv_c, red, acc_y2, (int)gridDim.x, FUSE ? p.b2 + (size_t)layer * C : nullptr, nosync);
+                residual_layer_norm(xres_s, xin_s, p.y2 + (size_t)xcopy * C, false, lp2, C, inv_c, red, acc_y2, (int)gridDim.x / p.red_group, FUSE ? p.b2 + (size_t)layer * C : nullptr, nosync);
                 if (FUSE && tid == 0) *(volatile int*)&s_red_done = 2 * gl + 2;
             }
             // ================= lm_head: logits_pre = fp16(x) @ W^T (fp32 value before the fp16 store) ================

@@ -55,6 +55,8 @@ struct DecodeParams {
     // tensor-parallel layer (use_fuse): per layer [H][C][HD+8] per-head out_proj units, then [F][ustride] transposed fc2 units;
     // acc: four copies of [C] u64 counting fixed-point accumulators (reduction k uses copy k & 3), zeroed by the host before each launch
     const __half *wfuse; unsigned long long *acc; int use_fuse;
+    // fc2 reduction: CTAs pre-reduce in groups of red_group (4 or 1) through the flagged words xq [grid][4][C/4] before the atomics
+    unsigned long long *xq; int red_group;
     // L2 run-ahead: a second streaming warp issues cp.async.bulk.prefetch.L2 for this CTA's future ring bytes, staying at most
     // pf_dist bytes ahead of the ring producer, so that HBM keeps streaming while the consumers sit in an exchange (0 = off)
     int pf_dist;

@@ -133,7 +133,7 @@ struct er_engine {
     bool cache_rows_stale = false;     // a decode ran since cache_rows was set: the exact row count lives in the device state
     unsigned long long* prof = nullptr; int prof_token = -1, prof_cta = 0;
     // decode-kernel knobs (defaults = the production configuration; changed only through er_debug_set)
-    int split_handicap = 4, split_handicap_fuse = 0, xrep = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
+    int red_group4 = 1, split_handicap = 4, split_handicap_fuse = 0, xrep = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
     int lat_batch_cap = 1;
 };
 
@@ -298,9 +298,9 @@ static int create_impl(er_engine* e, const er_config* cfg) {
     e->grid = sms;
     e->S = sms / H; if (e->S > 16) e->S = 16; if (e->S < 1) { return set_err(ER_ERR_INVALID, "need >= num_heads SMs"); }
     ALLOC(e->part, (size_t)H * 16 * 100);
-    e->ll_words = (size_t)3 * C / 2 + (size_t)H * 16 * 100;       // flagged words: q|k|v [3C/2], split partials [H][16][100]
+    e->ll_words = (size_t)3 * C / 2 + (size_t)H * 16 * 100 + (size_t)sms * C;       // flagged words: q|k|v [3C/2], split partials [H][16][100], group-of-4 exchange [grid][4][C/4]
     ALLOC(e->ll, e->ll_words);
-    ALLOC(e->acc, 4 * (size_t)C * 4);                               // four copies of C counting accumulators, one per 32-byte sector
+    ALLOC(e->acc, 4 * (size_t)C);                                   // four copies of C counting accumulators
     // tensor-parallel layer: S in {12, 9, 6} so that a CTA's 288 / S qkv rows stay inside one of q | k | v; needs the tensor-core
     // GEMV shapes (C % 256), <= 64 fc1 rows and <= 32 accumulator words per CTA
     e->S_fuse = 0;
@@ -561,6 +561,7 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     p.ll_q = e->ll; p.ll_part = p.ll_q + 3 * C / 2;
     p.poll_rounds = e->poll_rounds;
     p.use_fuse = fuse; p.wfuse = e->wfuse; p.acc = e->acc;
+    p.xq = p.ll_part + (size_t)e->H * 16 * 100; p.red_group = (G % 4 == 0 && C % 4 == 0 && e->red_group4) ? 4 : 1;
     p.xrep = e->xrep;
     p.pf_dist = e->pf_dist; p.dbg_nosync = e->dbg_nosync;
     p.st = e->st; p.bar = e->bar;
@@ -572,7 +573,7 @@ extern "C" int er_decode(er_engine* e, int32_t max_new_tokens, int32_t mode, int
     for (int done = 0; done < max_new_tokens; done += chunk) {
         p.steps = std::min(chunk, max_new_tokens - done);
         CK(cudaMemsetAsync(e->bar, 0, (64 + 64) * 4, st));
-        if (p.use_fuse) { CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st)); CK(cudaMemsetAsync(e->acc, 0, 4 * (size_t)C * 4 * 8, st)); }
+        if (p.use_fuse) { CK(cudaMemsetAsync(e->ll, 0, e->ll_words * 8, st)); CK(cudaMemsetAsync(e->acc, 0, 4 * (size_t)C * 8, st)); }
         CKL(e, er_decode_launch(p, G, e->dec_smem, st));
     }
     if (out_len_dev) {
@@ -683,6 +684,7 @@ extern "C" int er_debug_set(er_engine* e, const char* key, int64_t value) {
     if (!key) return set_err(ER_ERR_INVALID, "null key");
     const std::string k = key;
     if (k == "poison_alloc") { g_poison_alloc = (int)value; return ER_OK; }      // process-wide; e may be NULL
+    if (k == "dense_legacy") { extern int g_er_dense_legacy; g_er_dense_legacy = value != 0; return ER_OK; }   // process-wide: mma.sync GEMM / attention
     if (!e) return set_err(ER_ERR_INVALID, "null engine");
     const int v = (int)value;
     if (k == "decode_fuse") {
@@ -692,6 +694,7 @@ extern "C" int er_debug_set(er_engine* e, const char* key, int64_t value) {
     }
     else if (k == "gemv_cuda") { if (e->finalized) return set_err(ER_ERR_STATE, "gemv_cuda must be set before er_finalize_weights"); e->use_mma = (v == 0 && e->C % 256 == 0) ? 1 : 0; e->upstage = e->use_mma ? 8 : er_decode_stage_bytes() / (e->ustride * 2) / 8 * 8; }
     else if (k == "split_handicap") e->split_handicap = std::max(0, std::min(7, v));
+    else if (k == "red_group4") e->red_group4 = v != 0;
     else if (k == "split_handicap_fuse") e->split_handicap_fuse = std::max(0, std::min(7, v));
     else if (k == "xrep") e->xrep = std::max(1, std::min(8, v));
     else if (k == "poll_rounds") e->poll_rounds = std::max(0, v);

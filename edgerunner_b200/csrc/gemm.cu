@@ -148,7 +148,8 @@ cudaError_t er_gemm_tcgen05(const er::GemmArgs& a, cudaStream_t stream);   // ge
 cudaError_t er_gemm(const er::GemmArgs& g, cudaStream_t stream) {
     using namespace er;
     if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-    {   // tcgen05 + TMA kernel whenever the operands meet the TMA alignment rules (every shape of the ArAE / tiny presets does); the
+    extern int g_er_dense_legacy;
+    if (!g_er_dense_legacy) {   // tcgen05 + TMA kernel whenever the operands meet the TMA alignment rules (every shape of the ArAE / tiny presets does); the
         // mma.sync kernel below remains for odd strides
         const cudaError_t e = er_gemm_tcgen05(g, stream);
         if (e != cudaErrorNotSupported) return e;

@@ -125,7 +125,8 @@ int64_t er_kernel_launches(const er_engine* e);          /* kernels launched by 
  * "decode_fuse" (1: tensor-parallel decode layer, 0: five-exchange layer), "gemv_cuda" (CUDA-core GEMV consumers) — both before
  * er_finalize_weights —, "split_handicap", "xrep", "poll_rounds", "pf_dist" (bytes of L2 run-ahead per CTA), "nosync" (timing diagnostics: grid barriers skipped,
  * results are garbage), "cache_rows" (pretend the cache holds that many rows; timing at a chosen context length),
- * "poison_alloc" (process-wide, e may be NULL: fill later allocations with 0xFF).  Unknown key: ER_ERR_INVALID. */
+ * "poison_alloc" (process-wide, e may be NULL: fill later allocations with 0xFF), "dense_legacy" (process-wide: use the mma.sync GEMM /
+ * attention kernels instead of the tcgen05 ones; A/B timing).  Unknown key: ER_ERR_INVALID. */
 int er_debug_set(er_engine* e, const char* key, int64_t value);
 
 /* Profiling aid (profiles/): phase timeline of one CTA for one generated token of the next er_decode call. Slots (ns):

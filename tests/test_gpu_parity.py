@@ -421,8 +421,8 @@ def test_padded_batch_masked_forward(tiny_setup):
         ref = orc.forward_tf(conds[b:b + 1], tokens[b:b + 1, :n], labels[b:b + 1, :P + n], nf[b:b + 1])
         d = (logits[b, :P + n].cpu() - ref['logits_pre'][0]).abs().max().item()
         assert d <= 2 * LOGIT_TOL, (b, d)
-        ce_sum += float(ref['loss_ce']) * (n - 1)
-        n_tok += n - 1
+        ce_sum += float(ref['loss_ce']) * n          # n supervised positions: the labels at P .. P+n-1 (the first is predicted by the last condition row)
+        n_tok += n
     np.testing.assert_allclose(float(losses[1]), ce_sum / n_tok, rtol=3e-4)
     np.testing.assert_allclose(float(sums[0]) / float(sums[1]), float(losses[1]), rtol=1e-6)
     assert int(sums[1]) == n_tok
