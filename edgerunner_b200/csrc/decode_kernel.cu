@@ -629,9 +629,9 @@ constexpr float kFixInv = 1.0f / 4294967296.0f;
 constexpr unsigned long long kFixBias = 1ull << 47;        // every addend is non-negative and < 2^48: 255 of them cannot carry into the count
 constexpr unsigned long long kFixOne = 1ull << 56;
 constexpr unsigned long long kFixMask = (1ull << 56) - 1;
-// Element u lives at word u * kAccStride.  Measured: a fc2 reduction (148 x 1536 atomics) takes ~5.5 us whether the accumulators are
-// packed (stride 1) or spread one per 32-byte sector (stride 4: 7.9 us — more sectors per warp-wide RED, no gain from more L2 slices):
-// the cost is the NUMBER of atomic operations (~40 per ns chip-wide), not their placement.  Hence the groups of four below.
+// Element u lives at word u * kAccStride.  Measured: a fc2 reduction (148 x 1536 atomics) is observed complete ~5.5 us after a CTA has
+// issued its own adds whether the accumulators are packed (stride 1) or spread one per 32-byte sector (stride 4: 7.9 us — more sectors per
+// warp-wide RED), and ~3.5 us later with 4x fewer atomics (groups of four, below): the cost is the all-to-all hop itself.
 constexpr int kAccStride = 1;
 __device__ __forceinline__ void fix_add_cnt(unsigned long long* acc, float v) {
     v = fminf(fmaxf(v, -32000.f), 32000.f);                 // also maps NaN to a number: the count must always arrive
@@ -1468,9 +1468,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
                         prof_stamp(p, pb + 13, prof_on);      // fc2 partial sums computed (atomics follow)
                         cbar();
                         if (p.red_group == 4) {
-                            // pre-reduce among 4 CTAs through flagged words, then add: 148 x 1536 atomics took ~5.5 us of every layer; with groups of
-                            // four each CTA sends the three quarters it does not own to their owners, sums the three it receives with its own (fixed
-                            // order) and issues C/4 atomics: 4x fewer atomics per element (37 addends), one extra hop among 4 CTAs that finish together
+                            // (experiment, er_debug_set red_group4 = 1; off by default) pre-reduce among 4 CTAs through flagged words, then add: each CTA
+                            // sends the three quarters it does not own to their owners, sums the three it receives with its own (fixed order) and issues
+                            // C/4 atomics: 4x fewer atomics per element (37 addends).  Measured: the extra hop costs 3 us and the wait for the completed
+                            // reduction shrinks by only 2 us — what a reduction costs is the all-to-all hop (skew of 148 CTAs + atomics in flight + poll),
+                            // not the atomic count (profiles/r02_phase_timeline_tensor_parallel_v4_group4.json)
                             const int me = (int)(blockIdx.x & 3u), g4 = (int)(blockIdx.x >> 2), Q = C >> 2;
                             for (int i = tid; i < 3 * Q; i += kConsumers) {
                                 const int q = (me + 1 + i / Q) & 3, e = i % Q;

@@ -133,7 +133,7 @@ struct er_engine {
     bool cache_rows_stale = false;     // a decode ran since cache_rows was set: the exact row count lives in the device state
     unsigned long long* prof = nullptr; int prof_token = -1, prof_cta = 0;
     // decode-kernel knobs (defaults = the production configuration; changed only through er_debug_set)
-    int red_group4 = 1, split_handicap = 4, split_handicap_fuse = 0, xrep = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
+    int red_group4 = 0, split_handicap = 4, split_handicap_fuse = 0, xrep = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
     int lat_batch_cap = 1;
 };
 
