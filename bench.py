@@ -204,6 +204,87 @@ def run_reference_arm(args):
     }), flush=True)
 
 
+def run_teacher_forced(args):
+    """BASELINE configs[3]: ArAE teacher-forced forward, seq_len 8192 (+ 2049 condition rows + BOS/EOS = 10 243 rows), batch 4 per GPU, data
+    parallel: every rank runs the forward on its own batch through LMM.forward, ONE NCCL all-reduce of the fp64 {ce_sum, n_tokens, kl}.  Forward
+    only (no backward exists: DESIGN.md §6).  value = supervised tokens/s over all ranks; roofline: tensor-bound, algorithmic FLOPs
+    against MEASURED_PEAKS bf16_tflops_sustained."""
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from dataclasses import replace
+    from core.models import LMM
+    from core.options import config_defaults
+    from edgerunner_b200 import synth
+    opt = replace(config_defaults['ArAE'], generate_mode='greedy') if not args.tiny else synth.tiny_options()
+    B, T = 4, (8194 if not args.tiny else 48)
+    P, C, NL = opt.num_cond_tokens, opt.hidden_dim, opt.num_layers
+    N = P + T
+    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
+    with torch.device('meta'):
+        model = LMM(opt)
+    model.load_state_dict(sd, strict=True, assign=True)
+    del sd
+    model = model.half().eval().to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    tokens = torch.randint(6, model.vocab_size, (B, T), generator=g)
+    tokens[:, 0] = opt.bos_token_id
+    data = {'conds': torch.cat([synth.synth_point_cloud(rank * B + b, opt.point_num) for b in range(B)]).to(dev), 'tokens': tokens,
+            'labels': torch.cat([torch.full((B, P), -100, dtype=torch.long), tokens.long()], dim=1), 'masks': torch.ones((B, N), dtype=torch.bool),
+            'num_faces': torch.tensor([4000] * B), 'num_tokens': torch.full((B,), T)}
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 1)):
+        out = model(data)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    l0 = model._engine.kernel_launches()
+    ev[0].record()
+    for _ in range(args.steps):
+        out = model(data)
+        loss = float(out['loss'])                          # D2H of the step's result
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.destroy_process_group()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    ms_step = ms / args.steps
+    flops = (2 * 680_752_128 * B * N + 2 * N * N * C * NL * B + 0.16e12 * B) if not args.tiny else float('nan')
+    peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    peak = float(json.load(open(peaks_path)).get('bf16_tflops_sustained', 1400.0)) if os.path.exists(peaks_path) else 1400.0
+    tf = flops / (ms_step * 1e-3) / 1e12
+    print(json.dumps({
+        'metric': 'teacher-forced tokens/sec, ArAE forward seq_len 8192 batch 4/GPU (BASELINE configs[3], forward only)', 'value': world * B * T / (ms_step * 1e-3),
+        'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic', 'loss': loss,
+        'config': {'workload': f'ArAE teacher-forced forward B={B}/GPU N={N} (P={P} + T={T}), data parallel x{world}, one NCCL all-reduce of 3 fp64 numbers per step',
+                   'backward': 'none (forward only)', 'l2': f'activations of {B * N} rows x 1536 exceed L2'},
+        'clocks': clocks, 'gpu_launches': int(model._engine.kernel_launches() - l0),
+        'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'traffic': None,
+                     'kernel': 'er::tc::gemm_tcgen05_kernel + er::fa::attention_tcgen05_kernel', 'algorithmic_flops_per_step_per_gpu': flops,
+                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)'},
+        'e2e': {'value': world * B * T / (ms_step * 1e-3), 'unit': 'tokens/s', 'h2d_bytes_per_step': int(tokens.numel() * 4 + data['labels'].numel() * 8),
+                'd2h_bytes_per_step': 4, 'note': 'LMM.forward(data): tokens / labels uploaded and the loss read back every step inside the timed region'},
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -217,10 +298,15 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-reference-gpu', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3, help='timed LMM.generate calls of the e2e leg (bounded: each is a full 16k request)')
+    ap.add_argument('--workload', default='decode', choices=['decode', 'tf'],
+                    help="decode = BASELINE configs[1] (the metric); tf = configs[3]: teacher-forced forward seq 8192 batch 4/GPU, loss all-reduced over NCCL")
     args = ap.parse_args()
 
     if args.impl == 'reference':
         run_reference_arm(args)
+        return
+    if args.workload == 'tf':
+        run_teacher_forced(args)
         return
 
     rank = int(os.environ.get('RANK', '0'))

@@ -35,13 +35,22 @@ def run(kind, steps, warmup, tokens, threads=None, tiny=False):
     from edgerunner_b200 import synth
     opt = synth.tiny_options() if tiny else replace(cfgs['ArAE'], generate_mode='greedy')
     windows = (80, 200, 400) if tiny else WINDOWS
-    if not gpu:
-        n_host = os.cpu_count() or 1
-        torch.set_num_threads(threads or n_host)
     sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0)
     model = rr.build_model(opt, sd, dev, half=gpu)
     del sd
     pasts = {L: rr.make_past(model, L, randn=gpu) for L in windows}
+    if not gpu:
+        # a chain of small GEMVs + a torch.cat of the whole cache per layer: more threads is not faster (128 threads on this box: 16 s per
+        # token; 16 threads: tens of ms).  Time one cached step per candidate at the shortest window and keep the best.
+        n_host = os.cpu_count() or 1
+        cands = [threads] if threads else sorted({c for c in (8, 16, 32, 64) if c <= n_host} | ({n_host} if n_host <= 16 else set()))
+        best, best_t = cands[0], float('inf')
+        for c in cands:
+            torch.set_num_threads(c)
+            t = rr.decode_window(model, windows[0], 2, warm=1, past=pasts[windows[0]])
+            if t < best_t:
+                best, best_t = c, t
+        torch.set_num_threads(best)
     per_step = []
     last = None
     for i in range(warmup + steps):
