@@ -2,16 +2,19 @@
 // fp16 operands, fp32 scores / statistics / accumulation, probabilities rounded to fp16 before P V — the arithmetic of the flash kernel the
 // reference calls (core/transformer/attention.py:44-46).  Replaces the mma.sync kernel of attention.cu where the operands meet the TMA rules.
 //
-// One CTA = one (batch, head, 128-query tile); key blocks of 64; 192 threads; two CTAs per SM (80 KB of shared memory and 256 TMEM columns
-// each), so one CTA's softmax overlaps the other's MMAs:
+// One CTA = one (batch, head, 128-query tile); key blocks of 64; 320 threads; two CTAs per SM (80 KB of shared memory and 256 TMEM columns
+// each).  S is double-buffered in TMEM: Q K^T of block j+1 is issued before the softmax of block j has finished, so the tensor core works
+// under the softmax; the second CTA of the SM fills what is left:
 //   warp 0      TMA producer: Q once, then per key block K and V as 3-D bulk tensor copies {64 dims, 1 head, 64|128 rows} with 128-byte swizzle.
 //               D = 96 is two 64-dim atoms, the second half-filled: the tensor's innermost extent IS the head dim, so the copy engine
 //               zero-fills dims 96..127 (K = 128 for Q K^T costs 33 % more MMA time there and nothing anywhere else)
 //   warp 1      MMA issuer (one elected lane): S[128 x 64] = Q K^T (tcgen05.mma M 128, N 64, K-major x K-major) into TMEM columns 0..63;
 //               O_blk[128 x D] = P V (A = P from shared memory, K-major; B = the V tile AS LOADED, i.e. MN-major: dims contiguous) into
 //               TMEM columns 64..64+D; tcgen05.commit publishes S / O_blk and frees the K / V buffers for the next copies
-//   warps 2..5  softmax: thread = query row (TMEM lane).  Pass 1 reads S for the row maximum, pass 2 re-reads it (TMEM reads are cheap,
-//               registers are not), exponentiates, rounds to fp16 and stores P in the K-major swizzled layout the MMA wants; then
+//   warps 2..9  softmax: TWO threads per query row (TMEM lane): warps 2..5 take keys 0..31 and output dims [0, D/2), warps 6..9 keys 32..63
+//               and dims [D/2, D) (a warp may touch TMEM lanes 32 (warp % 4) .. +31 only, any columns).  Pass 1 reads S for the row maximum
+//               (the two halves meet through shared memory and one named barrier), pass 2 re-reads it (TMEM reads are cheap, registers
+//               are not), exponentiates, rounds to fp16 and stores P in the K-major swizzled layout the MMA wants; then
 //               O = O * alpha + O_blk from TMEM.  K(j+1) streams in under softmax(j) / P V(j), V(j+1) under Q K^T(j+1) / softmax(j+1).
 // SASS: UTCHMMA, UTMALDG.3D, LDTM, UTCBAR.
 #include <cuda.h>
@@ -25,7 +28,7 @@
 namespace er {
 namespace fa {
 
-constexpr int BQ = 128, BKEY = 64, THREADS = 192;
+constexpr int BQ = 128, BKEY = 64, THREADS = 320;
 constexpr uint32_t TMEM_COLS = 256;
 constexpr int ATOM_Q = BQ * 128;            // bytes of one 64-dim atom of the Q tile (128 rows x 128 B)
 constexpr int ATOM_K = BKEY * 128;          // ... of a K / V tile (64 rows x 128 B)
@@ -79,6 +82,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+          "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 struct Args {
     __half* out; long long o_bs; int ldo;
     int B, H, Nq, Nk, causal;
@@ -92,9 +104,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     constexpr int NA = (D + 63) / 64;                  // 64-dim atoms per tile row
     constexpr int KS1 = NA * 4;                        // k16 steps of Q K^T (head dim padded to NA * 64 with zeros)
     constexpr int Q_BYTES = NA * ATOM_Q, K_BYTES = NA * ATOM_K;
+    constexpr int DH = D / 2;                          // output dims per softmax thread
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long q_full, k_full, v_full, k_empty, v_empty, s_full, p_full, o_full;
+    __shared__ __align__(8) unsigned long long q_full, k_full, v_full, k_empty, v_empty, s_full[2], p_full, o_full;
     __shared__ uint32_t tmem_base_s;
+    __shared__ float xmax[2][BQ];                      // row maxima of the two key halves
+    __shared__ float xsum[BQ];                         // final: denominator of the upper half
     unsigned char* base = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
     unsigned char* sQ = base;                          // [NA][128 rows][128 B]
     unsigned char* sK = sQ + Q_BYTES;                  // [NA][64 rows][128 B]
@@ -108,7 +123,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     if (threadIdx.x == 0) {
         mbar_init(s_addr(&q_full), 1); mbar_init(s_addr(&k_full), 1); mbar_init(s_addr(&v_full), 1);
         mbar_init(s_addr(&k_empty), 1); mbar_init(s_addr(&v_empty), 1);
-        mbar_init(s_addr(&s_full), 1); mbar_init(s_addr(&p_full), 4); mbar_init(s_addr(&o_full), 1);
+        mbar_init(s_addr(&s_full[0]), 1); mbar_init(s_addr(&s_full[1]), 1); mbar_init(s_addr(&p_full), 8); mbar_init(s_addr(&o_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -119,7 +134,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + BKEY;
+    const uint32_t tmem_o = tmem_base + 2 * BKEY;      // S0: columns 0..63, S1: 64..127, O_blk: 128..128+D
 
     if (warp == 0) {
         if (lane == 0) {                                          // ===== TMA producer =====
@@ -140,12 +155,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     } else if (warp == 1) {
         if (lane == 0) {                                          // ===== MMA issuer =====
             const uint32_t id1 = idesc(BKEY, 0), id2 = idesc(D, 1);
-            mbar_wait(s_addr(&q_full), 0);
-            for (int j = 0; j < nblk; ++j) {
-                // S = Q K^T.  S of block j-1 has been consumed: the softmax warps arrived on p_full(j-1) after reading it, and P V(j-1) below
-                // was issued after that wait.
+            auto qk = [&](int j) {                                // S[j & 1] = Q K_j^T
                 mbar_wait(s_addr(&k_full), j & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_s = tmem_base + (uint32_t)(j & 1) * BKEY;
 #pragma unroll
                 for (int s = 0; s < KS1; ++s) {
                     const uint64_t da = desc_kmajor(s_addr(sQ + (s >> 2) * ATOM_Q) + (s & 3) * 32);
@@ -153,7 +166,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                     umma_f16(tmem_s, da, db, id1, s != 0);
                 }
                 umma_commit(s_addr(&k_empty));
-                umma_commit(s_addr(&s_full));
+                umma_commit(s_addr(&s_full[j & 1]));
+            };
+            mbar_wait(s_addr(&q_full), 0);
+            qk(0);
+            for (int j = 0; j < nblk; ++j) {
+                // S[(j+1) & 1] was last read by the softmax of block j-1, which arrived on p_full(j-1) after reading it — waited for below, one
+                // iteration ago — so Q K^T of block j+1 can run under the softmax of block j
+                if (j + 1 < nblk) qk(j + 1);
                 // O_blk = P V once the softmax warps have written P (and have finished reading O_blk of block j-1: program order on their side)
                 mbar_wait(s_addr(&p_full), j & 1);
                 mbar_wait(s_addr(&v_full), j & 1);
@@ -168,45 +188,46 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                 umma_commit(s_addr(&o_full));
             }
         }
-    } else {                                                      // ===== softmax / epilogue: thread = query row =====
+    } else {                                                      // ===== softmax / epilogue: two threads per query row =====
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;                         // 0: keys 0..31, dims [0, DH); 1: keys 32..63, dims [DH, D)
         const int r = quad * 32 + lane;                           // row inside the tile = TMEM lane
         const int qi = m0 + r;
         const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-        float o[D];
+        float o[DH];
 #pragma unroll
-        for (int i = 0; i < D; i++) o[i] = 0.f;
+        for (int i = 0; i < DH; i++) o[i] = 0.f;
         float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < nblk; ++j) {
-            const int k0 = j * BKEY;
-            const bool edge = (a.causal && k0 + BKEY - 1 > m0) || (k0 + BKEY > a.Nk);      // some (row, key) pairs of this block are masked
-            mbar_wait(s_addr(&s_full), j & 1);
+            const int k0 = j * BKEY + half * 32;                  // first key of this thread's 32
+            const bool edge = (a.causal && j * BKEY + BKEY - 1 > m0) || (j * BKEY + BKEY > a.Nk);   // some (row, key) pairs of this block are masked
+            const uint32_t tmem_s = tmem_base + (uint32_t)(j & 1) * BKEY + (uint32_t)half * 32;
+            mbar_wait(s_addr(&s_full[j & 1]), (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t v[32];
-            // pass 1: row maximum
+            // pass 1: maximum over this thread's 32 keys, then over the row (other half through shared memory)
             float mx = -INFINITY;
+            tmem_ld32(tmem_s + lane_sel, v);
 #pragma unroll
-            for (int c0 = 0; c0 < BKEY; c0 += 32) {
-                tmem_ld32(tmem_s + lane_sel + c0, v);
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    float s = __uint_as_float(v[i]);
-                    if (edge && ((a.causal && k0 + c0 + i > qi) || k0 + c0 + i >= a.Nk)) s = -INFINITY;
-                    mx = fmaxf(mx, s);
-                }
+            for (int i = 0; i < 32; i++) {
+                float s = __uint_as_float(v[i]);
+                if (edge && ((a.causal && k0 + i > qi) || k0 + i >= a.Nk)) s = -INFINITY;
+                mx = fmaxf(mx, s);
             }
-            const float m_new = fmaxf(m_run, mx);
+            xmax[half][r] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 softmax warps
+            const float m_new = fmaxf(m_run, fmaxf(mx, xmax[half ^ 1][r]));
             const float msc = (m_new == -INFINITY) ? 0.f : m_new * a.scale_log2;
             const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * a.scale_log2 - msc);
             // pass 2: p = exp2(s * scale - m * scale), fp16, into the swizzled K-major P tile (row r: 128 B, 16-byte chunk c at position c ^ (r & 7))
             float lsum = 0.f;
             const uint32_t prow = s_addr(sP) + (uint32_t)r * 128;
 #pragma unroll
-            for (int c0 = 0; c0 < BKEY; c0 += 32) {
-                tmem_ld32(tmem_s + lane_sel + c0, v);
-                uint32_t ph[16];
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                tmem_ld16(tmem_s + lane_sel + c0, v);
+                uint32_t ph[8];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
+                for (int i = 0; i < 16; i += 2) {
                     float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
                     if (edge) {
                         if ((a.causal && k0 + c0 + i > qi) || k0 + c0 + i >= a.Nk) s0 = -INFINITY;
@@ -218,8 +239,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                     ph[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
                 }
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int chunk = (c0 >> 3) + c;
+                for (int c = 0; c < 2; c++) {
+                    const int chunk = half * 4 + (c0 >> 3) + c;
                     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (uint32_t)((chunk ^ (r & 7)) * 16)), "r"(ph[4 * c]), "r"(ph[4 * c + 1]),
                                  "r"(ph[4 * c + 2]), "r"(ph[4 * c + 3]) : "memory");
                 }
@@ -231,21 +252,27 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(s_addr(&p_full));
-            // O = O * alpha + O_blk
+            // O = O * alpha + O_blk (this thread's DH dims)
             mbar_wait(s_addr(&o_full), j & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int c0 = 0; c0 < D; c0 += 32) {
-                tmem_ld32(tmem_o + lane_sel + c0, v);
+            for (int c0 = 0; c0 < DH; c0 += 16) {
+                tmem_ld16(tmem_o + lane_sel + (uint32_t)(half * DH + c0), v);
 #pragma unroll
-                for (int i = 0; i < 32; i++) o[c0 + i] = fmaf(o[c0 + i], alpha, __uint_as_float(v[i]));
+                for (int i = 0; i < 16; i++) o[c0 + i] = fmaf(o[c0 + i], alpha, __uint_as_float(v[i]));
             }
         }
+        // the two halves of a row share the denominator
+        if (half == 1) xsum[r] = l_run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) xsum[r] += l_run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (qi < a.Nq) {
-            const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-            __half* op = a.out + (size_t)b * a.o_bs + (size_t)qi * a.ldo + (size_t)h * D;
+            const float l = xsum[r];
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            __half* op = a.out + (size_t)b * a.o_bs + (size_t)qi * a.ldo + (size_t)h * D + half * DH;
 #pragma unroll
-            for (int c = 0; c < D / 8; c++) {
+            for (int c = 0; c < DH / 8; c++) {
                 __align__(16) __half hh[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) hh[i] = __float2half_rn(o[8 * c + i] * inv);
