@@ -14,8 +14,10 @@
 //   warps 2..9  softmax: TWO threads per query row (TMEM lane): warps 2..5 take keys 0..31 and output dims [0, D/2), warps 6..9 keys 32..63
 //               and dims [D/2, D) (a warp may touch TMEM lanes 32 (warp % 4) .. +31 only, any columns).  Pass 1 reads S for the row maximum
 //               (the two halves meet through shared memory and one named barrier), pass 2 re-reads it (TMEM reads are cheap, registers
-//               are not), exponentiates, rounds to fp16 and stores P in the K-major swizzled layout the MMA wants; then
-//               O = O * alpha + O_blk from TMEM.  K(j+1) streams in under softmax(j) / P V(j), V(j+1) under Q K^T(j+1) / softmax(j+1).
+//               are not), exponentiates, rounds to fp16 and stores P in the K-major swizzled layout the MMA wants.  O ACCUMULATES IN TMEM
+//               across key blocks (the MMA's accumulate flag); the reference maximum of a row is only raised when the block maximum exceeds
+//               it by more than 2^8 in the exponent (P stays <= 256, exact in the final O / l), and only then are the row's O (tcgen05.ld /
+//               .st) and l rescaled — rare after the first blocks.  K(j+1) streams in under softmax(j) / P V(j), V(j+1) under Q K^T(j+1).
 // SASS: UTCHMMA, UTMALDG.3D, LDTM, UTCBAR.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -89,6 +91,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
           "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+          "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 struct Args {
@@ -182,7 +192,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                 for (int s = 0; s < BKEY / 16; ++s) {
                     const uint64_t da = desc_kmajor(s_addr(sP) + s * 32);
                     const uint64_t db = desc_mnmajor(s_addr(sV) + s * 2048, ATOM_K);      // 16 keys further = two 8-row groups
-                    umma_f16(tmem_o, da, db, id2, s != 0);
+                    umma_f16(tmem_o, da, db, id2, (j | s) != 0);          // O accumulates in TMEM over all key blocks
                 }
                 umma_commit(s_addr(&v_empty));
                 umma_commit(s_addr(&o_full));
@@ -194,10 +204,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         const int r = quad * 32 + lane;                           // row inside the tile = TMEM lane
         const int qi = m0 + r;
         const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-        float o[DH];
-#pragma unroll
-        for (int i = 0; i < DH; i++) o[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;
+        float m_ref = -INFINITY, l_run = 0.f;              // m_ref: the (possibly stale) maximum the exponentials of this row are taken against
         for (int j = 0; j < nblk; ++j) {
             const int k0 = j * BKEY + half * 32;                  // first key of this thread's 32
             const bool edge = (a.causal && j * BKEY + BKEY - 1 > m0) || (j * BKEY + BKEY > a.Nk);   // some (row, key) pairs of this block are masked
@@ -216,10 +223,29 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             }
             xmax[half][r] = mx;
             asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 softmax warps
-            const float m_new = fmaxf(m_run, fmaxf(mx, xmax[half ^ 1][r]));
-            const float msc = (m_new == -INFINITY) ? 0.f : m_new * a.scale_log2;
-            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * a.scale_log2 - msc);
-            // pass 2: p = exp2(s * scale - m * scale), fp16, into the swizzled K-major P tile (row r: 128 B, 16-byte chunk c at position c ^ (r & 7))
+            mx = fmaxf(mx, xmax[half ^ 1][r]);
+            // P V of block j-1 must have completed before P is overwritten (and before O may be rescaled); every phase is consumed in order
+            if (j > 0) { mbar_wait(s_addr(&o_full), (j - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+            // raise the reference maximum only when the block exceeds it by more than 2^8 (or it is still -inf)
+            const bool raise = mx > m_ref && (m_ref == -INFINITY || (mx - m_ref) * a.scale_log2 > 8.f);
+            float factor = 1.f;
+            if (raise) {
+                factor = (m_ref == -INFINITY) ? 0.f : exp2f((m_ref - mx) * a.scale_log2);
+                m_ref = mx;
+                l_run *= factor;
+            }
+            if (j > 0 && __any_sync(0xffffffffu, raise)) {        // warp-uniform: tcgen05.ld / .st are warp-wide
+#pragma unroll
+                for (int c0 = 0; c0 < DH; c0 += 16) {
+                    uint32_t w[16];
+                    tmem_ld16(tmem_o + lane_sel + (uint32_t)(half * DH + c0), w);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) w[i] = __float_as_uint(__uint_as_float(w[i]) * factor);
+                    tmem_st16(tmem_o + lane_sel + (uint32_t)(half * DH + c0), w);
+                }
+            }
+            const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * a.scale_log2;
+            // pass 2: p = exp2(s * scale - m_ref * scale), fp16, into the swizzled K-major P tile (row r: 128 B, 16-byte chunk c at position c ^ (r & 7))
             float lsum = 0.f;
             const uint32_t prow = s_addr(sP) + (uint32_t)r * 128;
 #pragma unroll
@@ -245,38 +271,36 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                                  "r"(ph[4 * c + 2]), "r"(ph[4 * c + 3]) : "memory");
                 }
             }
-            l_run = l_run * alpha + lsum;
-            m_run = m_new;
-            // P is read by the tensor core through the async proxy; S has been fully read
+            l_run += lsum;
+            // P is read by the tensor core through the async proxy; S has been fully read; a rescaled O is in place
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(s_addr(&p_full));
-            // O = O * alpha + O_blk (this thread's DH dims)
-            mbar_wait(s_addr(&o_full), j & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int c0 = 0; c0 < DH; c0 += 16) {
-                tmem_ld16(tmem_o + lane_sel + (uint32_t)(half * DH + c0), v);
-#pragma unroll
-                for (int i = 0; i < 16; i++) o[c0 + i] = fmaf(o[c0 + i], alpha, __uint_as_float(v[i]));
-            }
         }
+        // the last P V
+        mbar_wait(s_addr(&o_full), (nblk - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // the two halves of a row share the denominator
         if (half == 1) xsum[r] = l_run;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (half == 0) xsum[r] += l_run;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (qi < a.Nq) {
+        {   // every lane takes part in the TMEM loads; only rows inside the tile store
             const float l = xsum[r];
             const float inv = l > 0.f ? 1.f / l : 0.f;
             __half* op = a.out + (size_t)b * a.o_bs + (size_t)qi * a.ldo + (size_t)h * D + half * DH;
 #pragma unroll
-            for (int c = 0; c < DH / 8; c++) {
-                __align__(16) __half hh[8];
+            for (int c0 = 0; c0 < DH; c0 += 16) {
+                uint32_t w[16];
+                tmem_ld16(tmem_o + lane_sel + (uint32_t)(half * DH + c0), w);
+                __align__(16) __half hh[16];
 #pragma unroll
-                for (int i = 0; i < 8; i++) hh[i] = __float2half_rn(o[8 * c + i] * inv);
-                *reinterpret_cast<uint4*>(op + 8 * c) = *reinterpret_cast<const uint4*>(hh);
+                for (int i = 0; i < 16; i++) hh[i] = __float2half_rn(__uint_as_float(w[i]) * inv);
+                if (qi < a.Nq) {
+                    *reinterpret_cast<uint4*>(op + c0) = *reinterpret_cast<const uint4*>(hh);
+                    *reinterpret_cast<uint4*>(op + c0 + 8) = *reinterpret_cast<const uint4*>(hh + 8);
+                }
             }
         }
     }

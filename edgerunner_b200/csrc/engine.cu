@@ -55,9 +55,9 @@ __global__ void init_state_kernel(er::DecodeState* st, int L) {
 __global__ void finish_decode_kernel(const er::DecodeState* st, int32_t* out_len) { *out_len = st->t; }
 // losses[0..2] = {loss, mean CE, KL}; sums[0..2] (optional) = {sum of token CEs, supervised tokens, KL}: what a data-parallel run all-reduces
 __global__ void tf_losses_kernel(const double* loss_sum, const int* count, const double* sq_sum, float kl_weight, int has_kl, float* losses, double* sums) {
-    const float ce = (float)(*loss_sum / (double)max(*count, 1));
-    const float kl = has_kl ? (float)(0.5 * *sq_sum) : 0.f;
-    losses[1] = ce; losses[2] = kl; losses[0] = ce + (has_kl ? kl_weight * kl : 0.f);
+    const double ce = *loss_sum / (double)max(*count, 1);                    // all in fp64, rounded once: the data-parallel path (dist.py) does the same
+    const double kl = has_kl ? 0.5 * *sq_sum : 0.0;
+    losses[1] = (float)ce; losses[2] = (float)kl; losses[0] = (float)(ce + (has_kl ? (double)kl_weight * kl : 0.0));
     if (sums) { sums[0] = *loss_sum; sums[1] = (double)*count; sums[2] = has_kl ? 0.5 * *sq_sum : 0.0; }
 }
 

@@ -68,4 +68,5 @@ def dp_reduce_losses(ce_sum: torch.Tensor, n_tokens: torch.Tensor, kl_sum: torch
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     loss_ce = buf[0] / buf[1].clamp(min=1)
     loss_kl = buf[2]
-    return (loss_ce + kl_weight * loss_kl).float(), loss_ce.float(), loss_kl.float()
+    w = float(np.float32(kl_weight))          # the C ABI takes kl_weight as fp32: same constant as the single-process kernel
+    return (loss_ce + w * loss_kl).float(), loss_ce.float(), loss_kl.float()
