@@ -435,3 +435,35 @@ def test_padded_batch_masked_forward(tiny_setup):
     holed = masks.clone(); holed[0, P + 3] = False
     with pytest.raises(NotImplementedError):
         eng.forward_tf(conds.cuda(), tokens, labels, nf, opt.kl_weight, masks=holed)
+
+
+@pytest.mark.parametrize('variant', ['five_exchange', 'tensor_parallel'])
+def test_eos_stops_the_persistent_kernel(variant):
+    """The EOS path of the persistent kernel (HF EosTokenCriteria): with an EOS logit of +30 the first op position after BOM + 9 coordinates
+    emits EOS (token 11): the consumers break, the producer drains its in-flight copies, the run-ahead / janitor warps exit, the device state
+    is written, `out_len` and `er_cache_rows` are exact.  Also with chunked launches (EOS inside a later launch) and with a forced EOS as
+    the FIRST token of a launch (every CTA must take the same `done` snapshot)."""
+    from edgerunner_b200.engine import Engine
+    opt = synth.tiny_options(hidden_dim=768, num_heads=8, num_layers=3)
+    sd = synth.synth_state_dict(opt, seed=3, eos_logit=30.0)
+    cond = synth.synth_point_cloud(1, opt.point_num)[0].cuda()
+    eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=64, max_points=opt.point_num, debug={'decode_fuse': int(variant == 'tensor_parallel')})
+    eng.load_state_dict(sd)
+    P = opt.num_cond_tokens
+    runs = []
+    for chunk in (0, 4, 11):
+        eng.encode_cond(cond, 1000); eng.prefill([1])
+        toks = eng.decode(64, mode='greedy', tokens_per_launch=chunk)['tokens']
+        runs.append(toks)
+        assert len(toks) == 11 and toks[0] == 5 and toks[-1] == opt.eos_token_id and (toks[1:10] >= 6).all(), toks
+        assert eng.lib.er_cache_rows(eng.h) == P + 1 + 10          # BOS + the ten tokens that were fed; EOS is never fed
+    np.testing.assert_array_equal(runs[0], runs[1]); np.testing.assert_array_equal(runs[0], runs[2])
+    # forced stream with EOS at index 8 and launches of 4 tokens: EOS is the first token of the third launch
+    forced = [5] + [100 + i for i in range(7)] + [opt.eos_token_id] + [7] * 8
+    eng.encode_cond(cond, 1000); eng.prefill([1])
+    out = eng.decode(17, mode='greedy', forced=forced, tokens_per_launch=4)
+    assert len(out['tokens']) == 9
+    assert eng.lib.er_cache_rows(eng.h) == P + 1 + 8
+    # the engine is reusable afterwards
+    eng.encode_cond(cond, 1000); eng.prefill([1])
+    np.testing.assert_array_equal(eng.decode(64, mode='greedy')['tokens'], runs[0])
