@@ -1,9 +1,11 @@
 """The attention op seam.  Mirrors ``/root/reference/core/transformer/attention.py:27-95``:
 ``attention(q, k, v, mask_q=None, mask_kv=None, dropout=0, causal=False)`` with ``[B, N, H, D]`` tensors.
 
-Unmasked fp16 CUDA inputs run on the sm_100a flash-style kernel of ``edgerunner_b200`` (head_dim 64 or 96) instead of
-flash-attn; like the reference without flash-attn, padding masks raise ``NotImplementedError``.  There is no eager /
-CPU fallback: non-CUDA inputs raise.
+fp16 CUDA inputs run on the sm_100a tcgen05 flash kernel of ``edgerunner_b200`` (head_dim 64 or 96) instead of flash-attn.
+Padding masks (the varlen branch, reference ``:65-93``: unpad -> ``flash_attn_varlen_func`` -> ``pad_input``) are supported when they
+are RIGHT-padded, which is what ``collate_fn`` produces: sample b then attends over its first ``len_kv[b]`` keys with its first
+``len_q[b]`` queries, and the padded query rows come back as zeros (``pad_input``).  Masks with holes raise ``NotImplementedError``.
+There is no eager / CPU fallback: non-CUDA inputs raise.
 """
 
 import torch
@@ -18,16 +20,34 @@ def attention(q, k, v, mask_q=None, mask_kv=None, dropout=0, causal=False):
     M = k.shape[1]
     if causal:
         assert N == 1 or N == M, 'Causal mask only supports self-attention'
-    if mask_q is not None or mask_kv is not None:
-        raise NotImplementedError('masked (varlen) attention is not part of the B200 decode path')
     if dropout:
         raise NotImplementedError('attention dropout is a training-time op; not part of the B200 decode path')
     if not q.is_cuda:
         raise RuntimeError('edgerunner_b200 attention needs CUDA tensors (no CPU fallback)')
     in_dtype = q.dtype
     q16, k16, v16 = (t.to(torch.float16).contiguous() for t in (q, k, v))
-    out = torch.empty_like(q16)
     lib = _lib.load()
-    _lib.check(lib.er_attention_bnhd(q16.data_ptr(), k16.data_ptr(), v16.data_ptr(), out.data_ptr(), B, N, M, H, D,
-                                     1 if (causal and N > 1) else 0, torch.cuda.current_stream().cuda_stream))
+    stream = torch.cuda.current_stream().cuda_stream
+    if mask_q is None and mask_kv is None:
+        out = torch.empty_like(q16)
+        _lib.check(lib.er_attention_bnhd(q16.data_ptr(), k16.data_ptr(), v16.data_ptr(), out.data_ptr(), B, N, M, H, D,
+                                         1 if (causal and N > 1) else 0, stream))
+        return out.to(in_dtype)
+    # varlen branch for right-padded masks (reference :65-93: a missing mask counts as all-True)
+    mq = torch.ones(B, N, dtype=torch.bool, device=q.device) if mask_q is None else mask_q.bool()
+    mk = torch.ones(B, M, dtype=torch.bool, device=q.device) if mask_kv is None else mask_kv.bool()
+    for m in (mq, mk):
+        if bool((m[:, 1:] & ~m[:, :-1]).any()):
+            raise NotImplementedError('only right-padded attention masks are supported (collate_fn pads at the end)')
+    len_q, len_k = mq.sum(1).tolist(), mk.sum(1).tolist()
+    out = torch.zeros_like(q16)                                   # pad_input: masked query rows are zero
+    row = H * D * 2                                              # bytes per (batch, position) row
+    for b in range(B):
+        nq, nk = int(len_q[b]), int(len_k[b])
+        if nq == 0 or nk == 0:
+            continue
+        if causal and nq > 1 and nq != nk:
+            raise NotImplementedError('causal varlen attention needs equal query / key lengths per sample')
+        _lib.check(lib.er_attention_bnhd(q16.data_ptr() + b * N * row, k16.data_ptr() + b * M * row, v16.data_ptr() + b * M * row,
+                                         out.data_ptr() + b * N * row, 1, nq, nk, H, D, 1 if (causal and nq > 1) else 0, stream))
     return out.to(in_dtype)

@@ -8,23 +8,23 @@
 //   OptFlashAttention2.forward             modeling_opt.py:185-232   (q/k/v GEMV, KV append, 1 x L attention)
 //   lm_head                                modeling_opt.py:497
 //
-// One cooperative launch generates up to `steps` tokens: one CTA per SM (8 consumer warps + 1 producer warp).  All CTAs
-// walk the same phase list and meet at a grid barrier between dependent phases (5 per layer).  The token loop, the FSM
-// and the sampler live on the device, so there is no host round trip per token (the reference has >= 5).
+// One cooperative launch generates up to `steps` tokens: one CTA per SM (8 consumer warps + producer warp + L2 run-ahead warp +
+// accumulator janitor warp).  The token loop, the FSM and the sampler live on the device, so there is no host round trip per token
+// (the reference has >= 5).  Two layer variants (template FUSE): the tensor-parallel layer (default; two head-local flagged-word
+// exchanges + two counting-atomic all-reduces, zero grid barriers — see the block comment above fix_add_cnt) and the five-exchange layer
+// of round 1 (a grid barrier between dependent phases).  One grid barrier per token remains in both (after lm_head).
 //
 // HBM-bound by construction (B = 1 GEMV + single-query attention, ~1 flop/byte).  Every weight byte and every cached
-// K/V byte is read exactly once per token.  The producer warp streams this CTA's slice of every phase — weight rows,
-// K blocks, V rows, in consumption order — from HBM into a shared-memory ring with TMA bulk copies
-// (cp.async.bulk.shared.global + mbarrier complete_tx; SASS UBLKCP).  Weights and old K/V rows do not depend on the
-// activations, so the stream runs AHEAD of the consumers across grid barriers (7 x 24 KB per SM).
-// What bounds a token at short context is not bandwidth but the chain of dependent steps (ncu: 50 % of warp samples at
-// CTA barriers, 21 % on long scoreboards), so the consumer side is organised to keep that chain short: one weight unit per
-// warp per stage with the input vector in registers, no shuffle reductions inside a phase (lane partials go to shared
-// memory, one short sum per output row at the end), fused residual+LayerNorm with one block reduction, per-warp softmax
-// maxima merged with one barrier, biases / LayerNorm parameters fetched into registers before the grid barrier they
-// follow, and the split-KV merge done once per head by the last split to finish instead of by every CTA.
+// K/V byte is read exactly once per token.  The producer warp streams this CTA's slice of every phase — weight units,
+// K blocks, V blocks, in consumption order — from HBM into a shared-memory ring with TMA bulk copies
+// (cp.async.bulk.shared.global + mbarrier complete_tx; SASS UBLKCP); the run-ahead warp walks the same ranges further ahead with
+// cp.async.bulk.prefetch.L2 (UBLKPF).  Weights and old K/V rows do not depend on the activations, so both streams run AHEAD of the
+// consumers across every wait (7 x 24 KB of ring + 128 KB of L2 per SM).
+// What bounds a token is not bandwidth but the chain of dependent steps, so the consumer side keeps that chain short: GEMV, q.K and P.V
+// on mma.sync with the operands in registers / ldmatrix, no shuffle reductions inside a phase, fused residual + LayerNorm with one block
+// reduction, per-warp softmax maxima merged with one barrier, biases / LayerNorm parameters fetched before the wait they follow.
 // The new K/V row is appended in place with plain stores (the reference re-allocates and copies the whole cache per
-// layer per step, modeling_opt.py:191-192) and is the only key read straight from global memory.
+// layer per step, modeling_opt.py:191-192).
 //
 // dtype ledger (mirrored by oracle/er_oracle.py mode='ledger'): fp16 weights and KV,
 // fp32 accumulation everywhere, activations rounded to fp16 exactly where model.half()+autocast(fp16) does.
@@ -149,14 +149,13 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch,
 
 // ---- flagged exchange between CTAs ("LL" words) -----------------------------------------------------------------------------------
 // A grid barrier costs ~2.5 us here (drain the CTA's stores for the release, one atomic, one polled acquire) and the data it
-// guards is then fetched with one more L2 round trip.  Every vector that crosses CTAs inside a token is instead published as
-// 8-byte words {payload, flag} with single-copy-atomic 64-bit stores; a reader polls the words it needs until each carries the
-// flag of the current (token, layer).  Arrival of the data IS the synchronisation: one store + one load on the critical path,
-// no fences.  Reuse is safe without further handshakes: a vector written in phase k is read by every CTA before that CTA writes
-// its phase k+1 output, and nobody can complete the poll of phase k+1 (hence reach phase k+2, let alone phase k of the next
-// layer) before all of those outputs exist.  Flags are unique per request (t * layers + layer + 1); the host zeroes the words
-// before each launch.  One real grid barrier per token remains (after lm_head): it also orders the K/V rows appended with
-// plain stores before the next token's bulk copies.
+// guards is then fetched with one more L2 round trip.  The small vectors that cross the S CTAs of a head (q / new k / new v, the
+// split partials) are instead published as 8-byte words {payload, flag} with single-copy-atomic 64-bit stores; a reader polls the
+// words it needs until each carries the flag of the current (token, layer).  Arrival of the data IS the synchronisation: one store +
+// one load on the critical path, no fences.  (Round 1 published EVERY exchanged vector this way, all 148 CTAs polling 24 KB of fc1
+// output: a polling storm, slower than barriers.  With S = 9 pollers per word there is none.)  Reuse is safe without handshakes: a
+// word is rewritten for layer l+1 only by a CTA that has seen an all-reduce of layer l complete, i.e. after every reader of layer l is
+// done.  Flags are unique per request (t * layers + layer + 1); the host zeroes the words before each launch.
 constexpr int kSpinLimit = 1 << 22;   // ~ seconds; a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void ll_store(unsigned long long* ptr, uint32_t data, uint32_t flag) {
     const unsigned long long v = ((unsigned long long)flag << 32) | data;

@@ -18,7 +18,7 @@ struct DecodeState {   // lives in device memory; carries the token loop across 
 struct DecodeParams {
     // dimensions
     int C, H, F, V, layers;
-    int S;            // KV splits per head in the attention phase (H*S <= grid)
+    int S;            // KV splits per head in the attention phase (H*S <= grid); tensor-parallel layer: S in {12, 9, 6}, also the qkv row split of a head
     int Lmax;         // V-cache rows per head
     int nkb;          // K-cache 32-key blocks per head (ceil(Lmax/32))
     int nstage;       // shared-memory ring stages (24 KB each)
@@ -29,7 +29,7 @@ struct DecodeParams {
     // the same decoder weights re-packed for the decode stream: units of C fp16 padded to `ustride` (see decode_kernel.cu)
     const __half *wdec; int ustride, upstage, use_mma;
     int split_handicap;   // K blocks the last KV split gives up (it also owns the new key and usually merges the head)
-    // KV cache: K blocked [layer][head][key/32][d/8][key%32][8], V natural [layer][head][key][96]
+    // KV cache: K and V both blocked [layer][head][key/32][d/8][key%32][8]
     __half *kc, *vc;
     // cross-CTA scratch (global, read back with ld.cg)
     int xrep;   // replicas of attn16 / y1 / h1 / y2 (writers store all, CTA b reads replica b % xrep): spreads 148 readers over L2 slices

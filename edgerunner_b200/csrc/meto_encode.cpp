@@ -1,4 +1,4 @@
-// Native meto tokenizer, LR_ABSCO and LR backends, ENCODE side (mesh -> token stream) behind the C ABI.
+// Native meto tokenizer, LR_ABSCO, LR and CLERS backends, ENCODE side (mesh -> token stream) behind the C ABI.
 //
 // Stands in for the pybind module `_meto` of the reference on the training-data side:
 //   Mesh::Mesh                 meto/include/meto/mesh.h:172-278     (quantise, half-edges, twins, boundary marks, ordering heuristics)
@@ -153,12 +153,65 @@ struct Emitter {
     void rel3(int dx, int dy, int dz) { tok.push_back(rel(dx)); tok.push_back(rel(dy)); tok.push_back(rel(dz)); }
 };
 
+// Engine_CLERS::encode (meto/include/meto/engine_clers.h:66-183): the classic EdgeBreaker walk.  Per face: (residual of the parallelogram
+// prediction, 3 tokens — not for the first face of a sub-mesh) then the op: C (tip unseen: mark it, go right), E (both neighbours seen: the
+// strip ends), L (left seen: go right), R (right seen: go left), S (neither: go right, then left).  The reference recurses per face; here an
+// explicit LIFO of gates gives the same depth-first order (S pushes left, then right).  Like Engine_LR it re-enters a gate even when its face
+// was reached another way in the meantime, so faces can repeat.
+void clers_encode(Builder& m, int bins, int64_t n_faces, std::vector<int32_t>& tok, std::vector<int32_t>& ord, std::vector<int32_t>& typ) {
+    enum : int32_t { C_ = 0, L_ = 1, E_ = 2, R_ = 3, S_ = 4, BOM_ = 5, EOM_ = 6, NUM_ = 7 };
+    const int off = 2 * bins + NUM_;
+    auto visited_face = [&](int h) { return m.F[m.H[h].face].mark != 0; };
+    std::vector<int> gates;
+    for (int64_t i = 0; i < n_faces; ++i) {
+        if (m.F[m.order[i]].mark) continue;
+        int c = m.F[m.order[i]].he[0];
+        tok.push_back(BOM_);
+        {
+            const QVert &qv = m.V[m.H[c].v], &qs = m.V[m.H[c].s], &qe = m.V[m.H[c].e];
+            tok.push_back(qv.x + off); tok.push_back(qv.y + off); tok.push_back(qv.z + off);
+            tok.push_back(qs.x - qv.x + off); tok.push_back(qs.y - qv.y + off); tok.push_back(qs.z - qv.z + off);
+            tok.push_back(qe.x - qs.x + off); tok.push_back(qe.y - qs.y + off); tok.push_back(qe.z - qs.z + off);
+        }
+        m.V[m.H[c].s].mark = 1; m.V[m.H[c].e].mark = 1;
+        gates.clear();
+        gates.push_back(c);
+        bool init = true;
+        while (!gates.empty()) {
+            c = gates.back();
+            gates.pop_back();
+            if (c < 0) { init = false; continue; }          // no face across that edge (the reference would dereference NULL)
+            m.F[m.H[c].face].mark = 1;
+            ord.push_back(m.F[m.H[c].face].index);
+            if (!init) {
+                const HalfEdge& tw = m.H[m.H[c].twin];
+                if (!(m.H[c].s == tw.e && m.H[c].e == tw.s)) m.flip(m.H[c].face);
+                const HalfEdge& hf = m.H[c];
+                const QVert &qv = m.V[hf.v], &qo = m.V[m.H[hf.twin].v], &qn = m.V[m.H[hf.next].v], &qp = m.V[m.H[hf.prev].v];
+                tok.push_back(qv.x + qo.x - qn.x - qp.x + off); tok.push_back(qv.y + qo.y - qn.y - qp.y + off); tok.push_back(qv.z + qo.z - qn.z - qp.z + off);
+            }
+            init = false;
+            const HalfEdge& h = m.H[c];
+            const bool tip_seen = m.V[h.v].mark != 0;
+            const int left_gate = m.H[h.prev].twin, right_gate = m.H[h.next].twin;
+            const bool left_seen = left_gate < 0 || visited_face(left_gate);
+            const bool right_seen = right_gate < 0 || visited_face(right_gate);
+            if (!tip_seen) { tok.push_back(C_); typ.push_back(C_); m.V[h.v].mark = 1; gates.push_back(right_gate); }
+            else if (left_seen && right_seen) { tok.push_back(E_); typ.push_back(E_); }
+            else if (left_seen) { tok.push_back(L_); typ.push_back(L_); gates.push_back(right_gate); }
+            else if (right_seen) { tok.push_back(R_); typ.push_back(R_); gates.push_back(left_gate); }
+            else { tok.push_back(S_); typ.push_back(S_); gates.push_back(left_gate); gates.push_back(right_gate); }
+        }
+        tok.push_back(EOM_);
+    }
+}
+
 }  // namespace
 
 extern "C" int er_meto_encode(int32_t backend, int32_t discrete_bins, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces,
                               int32_t* tokens, int64_t tokens_cap, int32_t* face_order, int32_t* face_type, int64_t faces_cap,
                               int64_t* n_tokens, int64_t* n_faces_out) {
-    if ((backend != ER_METO_LR_ABSCO && backend != ER_METO_LR) || discrete_bins <= 0 || n_verts < 0 || n_faces < 0 ||
+    if ((backend != ER_METO_LR_ABSCO && backend != ER_METO_LR && backend != ER_METO_CLERS) || discrete_bins <= 0 || n_verts < 0 || n_faces < 0 ||
         (n_faces > 0 && (!verts || !faces)) || !tokens || !face_order || !face_type || !n_tokens || !n_faces_out)
         return ER_ERR_INVALID;
     for (int64_t i = 0; i < 3 * n_faces; ++i)
@@ -169,6 +222,16 @@ extern "C" int er_meto_encode(int32_t backend, int32_t discrete_bins, const floa
     Emitter out;
     out.bins = discrete_bins; out.lr = lr;
     out.tok.reserve(10 * n_faces + 16); out.ord.reserve(n_faces + 16); out.typ.reserve(n_faces + 16);
+    if (backend == ER_METO_CLERS) {
+        clers_encode(m, discrete_bins, n_faces, out.tok, out.ord, out.typ);
+        *n_tokens = (int64_t)out.tok.size();
+        *n_faces_out = (int64_t)out.ord.size();
+        if ((int64_t)out.tok.size() > tokens_cap || (int64_t)out.ord.size() > faces_cap) return ER_ERR_CAPACITY;
+        std::copy(out.tok.begin(), out.tok.end(), tokens);
+        std::copy(out.ord.begin(), out.ord.end(), face_order);
+        std::copy(out.typ.begin(), out.typ.end(), face_type);
+        return ER_OK;
+    }
     std::vector<int> pending;   // sub-meshes still to be opened (LIFO == the reference's recursion order)
     auto visited_face = [&](int h) { return m.F[m.H[h].face].mark != 0; };
     for (int64_t i = 0; i < n_faces; ++i) {

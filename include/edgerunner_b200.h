@@ -135,13 +135,14 @@ int er_debug_set(er_engine* e, const char* key, int64_t value);
 int er_debug_phase_timeline(er_engine* e, int32_t token, int32_t cta);
 int er_debug_read_timeline(er_engine* e, uint64_t* out_host, int32_t n);
 
-/* meto tokenizer backends of the reference's pybind module `_meto` (meto/src/bindings.cpp:11-28; CLERS is not reachable from
- * core.options.Options and is not provided) */
+/* meto tokenizer backends of the reference's pybind module `_meto` (meto/src/bindings.cpp:11-28) */
 #define ER_METO_LR_ABSCO 0   /* Engine_LR_ABSCO: absolute coordinates, vocabulary bins + 3 (the ArAE / DiT presets) */
 #define ER_METO_LR 1         /* Engine_LR: parallelogram residuals, vocabulary 2 * bins + 3 (Options.meto_backend = 'LR') */
+#define ER_METO_CLERS 2      /* Engine_CLERS: classic EdgeBreaker C/L/E/R/S + BOM/EOM, parallelogram residuals offset by 2 * bins + 7
+                                (meto/include/meto/engine_clers.h; the reference's python wrapper reports 2 * bins + 7 tokens) */
 
-/* Detokenizer (CPU, native): replaces `_meto.Engine_{LR_ABSCO,LR}.decode`
- * (meto/include/meto/engine_lr_absco.h:223-295, engine_lr.h:171-254).  tokens are already -3 shifted (provider.py:115).
+/* Detokenizer (CPU, native): replaces `_meto.Engine_{LR_ABSCO,LR,CLERS}.decode`
+ * (meto/include/meto/engine_lr_absco.h:223-295, engine_lr.h:171-254, engine_clers.h:186-283).  tokens are already -3 shifted (provider.py:115).
  * Capacities: verts >= 3*(n/4+3) floats*3, faces >= (n/4+3)*3, face_type >= n/4+3.  Counts are returned through
  * n_verts/n_faces/n_types. */
 int er_meto_decode(int32_t backend, int32_t discrete_bins, const int32_t* tokens, int64_t n, float* verts, int32_t* faces,

@@ -1,6 +1,6 @@
 """``meto`` — mesh tokenizer package, drop-in for ``/root/reference/meto/meto/__init__.py``.
 
-``Engine(discrete_bins, verbose=False, backend='LR_ABSCO' | 'LR')`` keeps the reference's surface (:21-50):
+``Engine(discrete_bins, verbose=False, backend='LR_ABSCO' | 'LR' | 'CLERS')`` keeps the reference's surface (:21-50):
 ``encode(vertices [V,3], faces [F,3]) -> (tokens, face_order, face_type)``,
 ``decode(tokens[N] int) -> (vertices float64 [V,3], faces int [F,3], face_type)`` and the ``num_tokens`` /
 ``num_base_tokens`` / ``num_special_tokens`` attributes.  The implementation is the pair of native C-ABI functions
@@ -17,14 +17,14 @@ from edgerunner_b200 import _lib
 
 class Engine:
     def __init__(self, discrete_bins, verbose=False, backend: Literal['CLERS', 'LR', 'LR_ABSCO'] = 'LR_ABSCO'):
-        if backend not in ('LR_ABSCO', 'LR'):
-            raise NotImplementedError(f"meto backend '{backend}': LR_ABSCO and LR (the two values of Options.meto_backend) are provided")
+        if backend not in ('LR_ABSCO', 'LR', 'CLERS'):
+            raise NotImplementedError(f"meto backend '{backend}': LR_ABSCO, LR and CLERS are provided")
         self.discrete_bins = int(discrete_bins)
         self.verbose = verbose
         self.backend = backend
-        self._backend_id = 0 if backend == 'LR_ABSCO' else 1          # ER_METO_LR_ABSCO / ER_METO_LR
+        self._backend_id = {'LR_ABSCO': 0, 'LR': 1, 'CLERS': 2}[backend]          # ER_METO_LR_ABSCO / ER_METO_LR / ER_METO_CLERS
         self.num_base_tokens = self.discrete_bins * (1 if backend == 'LR_ABSCO' else 2)
-        self.num_special_tokens = 3
+        self.num_special_tokens = 7 if backend == 'CLERS' else 3                   # reference meto/meto/__init__.py:26-37
         self.num_tokens = self.num_base_tokens + self.num_special_tokens
         self._lib = _lib.load()
 
@@ -51,7 +51,7 @@ class Engine:
         if nf and (f.min() < 0 or f.max() >= nv):
             raise ValueError('meto.encode: face index out of range')
         p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-        tcap, fcap = max(10 * nf, 1), max(nf, 1)                       # always enough for LR_ABSCO; LR may repeat faces: retry once
+        tcap, fcap = max(12 * nf, 1), max(nf, 1)                       # always enough for LR_ABSCO; LR / CLERS may repeat faces: retry once
         for _ in range(2):
             tok = np.empty(tcap, dtype=np.int32)
             order = np.empty(fcap, dtype=np.int32)

@@ -316,6 +316,73 @@ def gen_meto_goldens():
     print('[gen] wrote meto.npz', flush=True)
 
 
+def clers_op_positions(tok):
+    """Indices of the operator tokens of a well-formed Engine_CLERS stream (BOM + 9 coordinates, op, (3 coordinates, op)*, EOM)."""
+    pos, i = [], 0
+    while i < len(tok):
+        if tok[i] == 5:
+            i += 10
+        elif tok[i] == 6:
+            i += 1
+        else:
+            pos.append(i)
+            i += 1 if (i + 1 < len(tok) and tok[i + 1] in (5, 6)) or tok[i] == 2 and i + 1 < len(tok) and tok[i + 1] == 6 else 4
+    return pos
+
+
+def gen_meto_clers_goldens():
+    """Engine_CLERS (meto/include/meto/engine_clers.h): encode + decode of the fixtures and stress meshes, and truncated / corrupted streams.
+    Streams on which the reference itself reads out of bounds (an E as the very last token, an E that pops an empty stack) are left out."""
+    import _meto
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    import meshes
+    out, names = {}, []
+    fx = dict(fixture_meshes())
+    cases = [(n, b) for n in fx for b in (512,)] + [(n, b) for n in meshes.stress_meshes() for b in (8, 512)]
+    fx.update(meshes.stress_meshes())
+    for name, bins in cases:
+        v, f = fx[name]
+        eng = _meto.Engine_CLERS(bins, False)
+        tok, order, ftype = eng.encode(v.astype(np.float32).tolist(), f.astype(np.int32).tolist())
+        dv, df, dt = eng.decode(tok)
+        key = f'clers_{name}_{bins}'
+        names.append(key)
+        out[key + '_tokens'] = np.asarray(tok, dtype=np.int16 if 4 * bins + 7 < 32768 else np.int32)
+        out[key + '_order'] = np.asarray(order, dtype=np.int32)
+        out[key + '_ftype'] = np.asarray(ftype, dtype=np.int8)
+        out[key + '_dv'] = np.asarray(dv, dtype=np.float32).reshape(-1, 3)
+        out[key + '_df'] = np.asarray(df, dtype=np.int32).reshape(-1, 3)
+        out[key + '_dt'] = np.asarray(dt, dtype=np.int8)
+    # truncations of one stream at every length (minus the out-of-bounds ones), and coordinates where an operator is expected
+    v, f = fx['two_components']
+    eng = _meto.Engine_CLERS(64, False)
+    tok = list(eng.encode(v.astype(np.float32).tolist(), f.astype(np.int32).tolist())[0])
+    ops = set(clers_op_positions(tok))
+    streams = [[]]
+    for n in range(1, min(len(tok), 160)):
+        if (n - 1) in ops and tok[n - 1] == 2:
+            continue
+        streams.append(tok[:n])
+    rng = np.random.RandomState(13)
+    for _ in range(6):
+        bad = list(tok)
+        k = sorted(ops)[rng.randint(1, len(ops) - 1)]
+        if bad[k] == 2:
+            continue
+        bad[k] = 7 + rng.randint(0, 4 * 64)
+        streams.append(bad)
+    for i, s in enumerate(streams):
+        dv, df, dt = eng.decode([int(x) for x in s])
+        out[f'clers_stream{i}_tokens'] = np.asarray(s, dtype=np.int16)
+        out[f'clers_stream{i}_dv'] = np.asarray(dv, dtype=np.float32).reshape(-1, 3)
+        out[f'clers_stream{i}_df'] = np.asarray(df, dtype=np.int16).reshape(-1, 3)
+        out[f'clers_stream{i}_dt'] = np.asarray(dt, dtype=np.int8)
+    out['names'] = np.asarray(names)
+    out['n_streams'] = np.asarray(len(streams))
+    np.savez_compressed(os.path.join(GOLD, 'meto_clers.npz'), **out)
+    print('[gen] wrote meto_clers.npz', len(names), 'meshes', len(streams), 'streams', flush=True)
+
+
 def gen_meta(synth):
     from core.options import config_defaults
     from core.models import LMM
@@ -386,6 +453,8 @@ def main():
         gen_meta(synth)
     if args.only in ('all', 'meto'):
         gen_meto_goldens()
+    if args.only in ('all', 'meto_clers'):
+        gen_meto_clers_goldens()
     if args.only in ('all', 'provider'):
         gen_provider_goldens(synth)
     if args.only in ('all', 'tiny'):

@@ -467,3 +467,29 @@ def test_eos_stops_the_persistent_kernel(variant):
     # the engine is reusable afterwards
     eng.encode_cond(cond, 1000); eng.prefill([1])
     np.testing.assert_array_equal(eng.decode(64, mode='greedy')['tokens'], runs[0])
+
+
+def test_attention_seam_right_padded_masks():
+    """attention(q, k, v, mask_q, mask_kv, causal): the varlen branch (reference attention.py:65-93) for right-padded masks against a masked
+    fp32 torch softmax; padded query rows are zero (pad_input); masks with holes raise."""
+    from core.transformer.attention import attention
+    torch.manual_seed(1)
+    for (B, N, M, H, D, causal) in [(3, 150, 150, 2, 96, True), (2, 70, 200, 2, 64, False)]:
+        q = torch.randn(B, N, H, D, device='cuda', dtype=torch.float16)
+        k = torch.randn(B, M, H, D, device='cuda', dtype=torch.float16)
+        v = torch.randn(B, M, H, D, device='cuda', dtype=torch.float16)
+        lq = torch.tensor([N, N - 37, 5][:B]); lk = lq if causal else torch.tensor([M, M - 90, 9][:B])
+        mq = (torch.arange(N)[None] < lq[:, None]).cuda(); mk = (torch.arange(M)[None] < lk[:, None]).cuda()
+        out = attention(q, k, v, mask_q=mq, mask_kv=mk, causal=causal)
+        qf, kf, vf = (t.float().transpose(1, 2) for t in (q, k, v))
+        w = qf @ kf.transpose(-1, -2) / D ** 0.5
+        w = w.masked_fill(~mk[:, None, None, :], float('-inf'))
+        if causal:
+            w = w + torch.triu(torch.full((N, M), float('-inf'), device='cuda'), diagonal=1)
+        ref = (torch.softmax(w, -1) @ vf).transpose(1, 2)
+        ref = ref * mq[:, :, None, None]
+        assert (out.float() - ref).abs().max().item() < 4e-3
+        assert (out[~mq] == 0).all()
+    holed = mq.clone(); holed[0, 3] = False
+    with pytest.raises(NotImplementedError):
+        attention(q, k, v, mask_q=holed, mask_kv=mk, causal=False)

@@ -269,10 +269,50 @@ def test_lr_backend_matches_reference_goldens(golden_dir):
         np.testing.assert_array_equal(dt, g[f'lr_stream{i}_dt'], err_msg=f'stream {i}')
 
 
+def test_clers_backend_matches_reference_goldens(golden_dir):
+    """Engine(backend='CLERS'): encode + decode against the compiled reference's Engine_CLERS (EdgeBreaker C/L/E/R/S ops, S-stack, offset
+    residuals), every truncation of a two-component stream, and coordinates where an operator is expected."""
+    import meshes
+    from meto import Engine
+    g = np.load(os.path.join(golden_dir, 'meto_clers.npz'))
+    fixtures = dict(meshes.all_meshes())
+    fixtures.update(meshes.stress_meshes())
+    ops = set()
+    for key in g['names']:
+        key = str(key)
+        name, bins = key[len('clers_'):].rsplit('_', 1)
+        v, f = fixtures[name]
+        eng = Engine(int(bins), backend='CLERS')
+        assert eng.num_tokens == 2 * int(bins) + 7
+        tok, order, ftype = eng.encode(v, f)
+        np.testing.assert_array_equal(tok, g[key + '_tokens'], err_msg=key)
+        np.testing.assert_array_equal(order, g[key + '_order'], err_msg=key)
+        np.testing.assert_array_equal(ftype, g[key + '_ftype'], err_msg=key)
+        dv, df, dt = eng.decode(tok)
+        np.testing.assert_array_equal(dv.astype(np.float32), g[key + '_dv'].reshape(-1, 3), err_msg=key)
+        np.testing.assert_array_equal(df, g[key + '_df'].reshape(-1, 3), err_msg=key)
+        np.testing.assert_array_equal(dt, g[key + '_dt'], err_msg=key)
+        ops |= set(np.asarray(ftype).tolist())
+    assert len(g['names']) >= 40 and ops == {0, 1, 2, 3, 4}     # every EdgeBreaker op occurs
+    eng = Engine(64, backend='CLERS')
+    for i in range(int(g['n_streams'])):
+        dv, df, dt = eng.decode(g[f'clers_stream{i}_tokens'].astype(np.int64))
+        np.testing.assert_array_equal(dv.astype(np.float32), g[f'clers_stream{i}_dv'].reshape(-1, 3), err_msg=f'stream {i}')
+        np.testing.assert_array_equal(df, g[f'clers_stream{i}_df'].reshape(-1, 3), err_msg=f'stream {i}')
+        np.testing.assert_array_equal(dt, g[f'clers_stream{i}_dt'], err_msg=f'stream {i}')
+    # where the reference reads out of bounds this implementation stops: an E as the very last token, an E with nothing to pop
+    tok = g['clers_two_components_512_tokens'].astype(np.int64)
+    first_e = int(np.flatnonzero(tok == 2)[0])
+    dv, df, dt = Engine(512, backend='CLERS').decode(tok[:first_e + 1])
+    assert len(df) >= 1 and dt[-1] == 2
+    dv, df, dt = Engine(512, backend='CLERS').decode(np.array([5] + [1100] * 9 + [2, 1100, 1100, 1100, 0]))
+    assert len(df) == 1
+
+
 def test_unknown_backend_is_refused():
     from meto import Engine
     with pytest.raises(NotImplementedError):
-        Engine(512, backend='CLERS')
+        Engine(512, backend='EDGEBREAKER')
 
 
 def test_native_mesh_clean_matches_python_steps():
