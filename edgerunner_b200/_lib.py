@@ -17,6 +17,10 @@ class ErConfig(C.Structure):
         'point_num_heads', 'point_latent_size', 'point_latent_dim', 'max_seq_rows', 'max_points', 'max_tf_rows')]
 
 
+class ErDitConfig(C.Structure):
+    _fields_ = [(n, c_i32) for n in ('device', 'hidden_dim', 'num_heads', 'num_layers', 'latent_size', 'latent_dim', 'cond_tokens', 'cond_dim')]
+
+
 # name -> (restype, argtypes); must list every symbol the header declares (tests/test_abi_cpu.py checks this)
 SIGNATURES = {
     'er_last_error': (C.c_char_p, []),
@@ -39,6 +43,17 @@ SIGNATURES = {
     'er_debug_set': (C.c_int, [c_vp, C.c_char_p, c_i64]),
     'er_debug_phase_timeline': (C.c_int, [c_vp, c_i32, c_i32]),
     'er_debug_read_timeline': (C.c_int, [c_vp, C.POINTER(c_u64), c_i32]),
+    'er_dit_create': (C.c_int, [C.POINTER(ErDitConfig), C.POINTER(c_vp)]),
+    'er_dit_destroy': (None, [c_vp]),
+    'er_dit_load_weight': (C.c_int, [c_vp, C.c_char_p, c_vp, c_i32, c_i64, c_vp]),
+    'er_dit_finalize_weights': (C.c_int, [c_vp, c_vp]),
+    'er_dit_cond': (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'er_dit_forward': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'er_dit_run': (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, C.POINTER(c_f32), C.POINTER(c_f32), c_f32, c_i32, c_i32, c_vp]),
+    'er_dit_run_host': (C.c_int, [c_vp, C.POINTER(c_f32), C.POINTER(c_f32), c_i32, c_i32, C.POINTER(c_f32), C.POINTER(c_f32), c_f32, c_i32, c_i32]),
+    'er_dit_kernel_launches': (c_i64, [c_vp]),
+    'er_dit_flops_per_forward': (C.c_double, [c_vp, c_i32]),
+    'er_dit_debug_set': (C.c_int, [c_vp, C.c_char_p, c_i64]),
     'er_meto_decode': (C.c_int, [c_i32, c_i32, C.POINTER(c_i32), c_i64, C.POINTER(c_f32), C.POINTER(c_i32), C.POINTER(c_i32),
                                  C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]),
     'er_meto_encode': (C.c_int, [c_i32, c_i32, C.POINTER(c_f32), c_i64, C.POINTER(c_i32), c_i64, C.POINTER(c_i32), c_i64,

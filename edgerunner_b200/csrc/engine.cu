@@ -32,6 +32,13 @@ static int set_err(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+int er_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
 #define CK(call)                                                                                              \
     do {                                                                                                      \
         cudaError_t _e = (call);                                                                              \

@@ -33,6 +33,9 @@ struct AttnArgs {   // softmax(q k^T / sqrt(D)) v ; q [B][Nq][H][D], k/v [B][Nk]
 
 }  // namespace er
 
+// sets the thread-local message behind er_last_error() and returns `code` (engine.cu)
+int er_set_error(int code, const char* fmt, ...);
+
 cudaError_t er_gemm(const er::GemmArgs& g, cudaStream_t stream);
 cudaError_t er_attention(const er::AttnArgs& a, cudaStream_t stream);
 

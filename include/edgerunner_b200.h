@@ -135,6 +135,51 @@ int er_debug_set(er_engine* e, const char* key, int64_t value);
 int er_debug_phase_timeline(er_engine* e, int32_t token, int32_t cta);
 int er_debug_read_timeline(er_engine* e, uint64_t* out_host, int32_t n);
 
+/* ---- DiT denoiser: the latent generator of the image-conditioned path (infer_dit.py:104-113) ---------------------------------------------
+ * Replaces core/transformer/dit.py (DiT, DiTLayer, Timesteps, TimestepEmbedding) and the device work of core/models_dit.py MDiT.get_cond /
+ * MDiT.run.  The CLIP vision tower stays a library model on the Python side (as in the reference); the scheduler's per-step scalars are
+ * computed by the Python mirror of diffusers' DDIMScheduler and handed in as a table, the update itself runs in the fused kernel. */
+typedef struct er_dit er_dit;
+typedef struct er_dit_config {
+    int32_t device;
+    int32_t hidden_dim, num_heads, num_layers;   /* Options.dit_hidden_dim / dit_num_heads / dit_num_layers (core/options.py:55-59) */
+    int32_t latent_size, latent_dim;             /* Options.point_latent_size / point_latent_dim: the denoised tensor is [latent_size][latent_dim] */
+    int32_t cond_tokens, cond_dim;               /* CLIP ViT-H/14 @ 224: 257 tokens of 1280 (core/models_dit.py:52-54) */
+} er_dit_config;
+#define ER_DIT_PRED_EPSILON 0
+#define ER_DIT_PRED_V 1                          /* Options.noise_scheduler_predtype (core/options.py:63) */
+
+/* MDiT.__init__ + load_state_dict + .half().to(device) for the keys `dit.*`, `proj_cond.*`, `norm_cond.*` (core/models_dit.py:33-76,
+ * infer_dit.py:58-70); data fp16 or fp32 on the device, rounded to fp16.  Unknown names / wrong sizes: ER_ERR_INVALID. */
+int er_dit_create(const er_dit_config* cfg, er_dit** out);
+void er_dit_destroy(er_dit* e);
+int er_dit_load_weight(er_dit* e, const char* name, const void* data_dev, int32_t dtype, int64_t numel, void* stream);
+int er_dit_finalize_weights(er_dit* e, void* stream);
+
+/* MDiT.get_cond after the image encoder (core/models_dit.py:116): norm_cond(proj_cond(h)); clip_hidden_dev fp16 [B][cond_tokens][cond_dim]
+ * -> cond_out_dev fp32 [B][cond_tokens][hidden_dim]. */
+int er_dit_cond(er_dit* e, const void* clip_hidden_dev, int32_t B, float* cond_out_dev, void* stream);
+
+/* DiT.forward(x, c, t) (core/transformer/dit.py:165-196) under autocast(fp16): x_dev fp32 [B][latent_size][latent_dim], cond_dev fp32
+ * [B][cond_tokens][hidden_dim], t_dev fp32 [B] -> out_dev fp16 [B][latent_size][latent_dim]. */
+int er_dit_forward(er_dit* e, const float* x_dev, const float* cond_dev, const float* t_dev, int32_t B, void* out_dev, void* stream);
+
+/* MDiT.run's loop (core/models_dit.py:209-227): for each of n_steps timesteps: [latents] * 2 -> DiT -> classifier-free guidance ->
+ * scheduler.step; latents_dev fp32 [R][latent_size][latent_dim] is updated in place (in: the initial noise, or the re-noised latents).
+ * cond_dev fp32 [R][cond_tokens][hidden_dim] is the conditional half (the unconditional half is zeros, as in the reference); guided = 0
+ * runs without guidance (one prediction per sample).  timesteps_host [n_steps] fp32; coef_host [n_steps][4] fp32 = {sqrt(alpha_t),
+ * sqrt(1 - alpha_t), sqrt(alpha_prev), sqrt(1 - alpha_prev - sigma_t^2)} (DDIM, eta = 0: sigma = 0).  Asynchronous on `stream` after the tables
+ * are uploaded; one CUDA graph per step. */
+int er_dit_run(er_dit* e, const float* cond_dev, float* latents_dev, int32_t R, int32_t n_steps, const float* timesteps_host,
+               const float* coef_host, float guidance_scale, int32_t guided, int32_t prediction_type, void* stream);
+/* the same with HOST buffers, synchronous (bench.py's e2e leg of the DiT workload) */
+int er_dit_run_host(er_dit* e, const float* cond_host, float* latents_host, int32_t R, int32_t n_steps, const float* timesteps_host,
+                    const float* coef_host, float guidance_scale, int32_t guided, int32_t prediction_type);
+
+int64_t er_dit_kernel_launches(const er_dit* e);
+double er_dit_flops_per_forward(const er_dit* e, int32_t batch);   /* GEMM + attention FLOPs of one denoiser forward over `batch` samples */
+int er_dit_debug_set(er_dit* e, const char* key, int64_t value);   /* "graph": 0 = launch every step's kernels directly (A/B timing) */
+
 /* meto tokenizer backends of the reference's pybind module `_meto` (meto/src/bindings.cpp:11-28) */
 #define ER_METO_LR_ABSCO 0   /* Engine_LR_ABSCO: absolute coordinates, vocabulary bins + 3 (the ArAE / DiT presets) */
 #define ER_METO_LR 1         /* Engine_LR: parallelogram residuals, vocabulary 2 * bins + 3 (Options.meto_backend = 'LR') */

@@ -383,6 +383,27 @@ def gen_meto_clers_goldens():
     print('[gen] wrote meto_clers.npz', len(names), 'meshes', len(streams), 'streams', flush=True)
 
 
+def gen_dit_goldens():
+    """The reference DiT module itself (core/transformer/dit.py), CPU fp32, naive attention, on the seeded weights of oracle/dit_oracle.py."""
+    from core.transformer.dit import DiT
+    sys.path.insert(0, HERE)
+    from dit_oracle import synth_dit_state
+    cfg = dict(hidden_dim=128, num_heads=2, latent_size=40, latent_dim=16, num_layers=2)
+    sd = synth_dit_state(**cfg, seed=3)
+    m = DiT(**cfg, gradient_checkpointing=False).eval()
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, cfg['latent_size'], cfg['latent_dim'], generator=g)
+    c = torch.randn(2, 9, cfg['hidden_dim'], generator=g)
+    t = torch.tensor([991.0, 3.0])
+    with torch.no_grad():
+        out = m(x, c, t)
+    keys = sorted(m.state_dict().keys())
+    np.savez_compressed(os.path.join(GOLD, 'dit.npz'), x=x.numpy(), c=c.numpy(), t=t.numpy(), out=out.numpy(), keys=np.asarray(keys),
+                        shapes=np.asarray([','.join(map(str, m.state_dict()[k].shape)) for k in keys]), cfg=json.dumps(cfg))
+    print('[gen] wrote dit.npz', float(out.abs().mean()), flush=True)
+
+
 def gen_meta(synth):
     from core.options import config_defaults
     from core.models import LMM
@@ -455,6 +476,8 @@ def main():
         gen_meto_goldens()
     if args.only in ('all', 'meto_clers'):
         gen_meto_clers_goldens()
+    if args.only in ('all', 'dit'):
+        gen_dit_goldens()
     if args.only in ('all', 'provider'):
         gen_provider_goldens(synth)
     if args.only in ('all', 'tiny'):
