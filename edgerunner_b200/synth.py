@@ -156,3 +156,39 @@ def tiny_options(**over):
                 max_seq_length=512, generate_mode='greedy')
     base.update(over)
     return replace(config_defaults['ArAE'], **base)
+
+
+def synth_dit_state_dict(hidden_dim, num_heads, latent_size, latent_dim, num_layers, cond_dim=None, seed=0, gain=1.0):
+    """Seeded synthetic weights with the reference DiT's state-dict schema (+ proj_cond / norm_cond when cond_dim is given), scaled so
+    that activations stay O(1) through the stack (there is no pretrained checkpoint offline)."""
+    g = torch.Generator().manual_seed(seed)
+    C = hidden_dim
+    sd = {}
+
+    def lin(name, out_f, in_f, s=1.0):
+        sd[name + '.weight'] = torch.randn(out_f, in_f, generator=g) * (s * gain / math.sqrt(in_f))
+        sd[name + '.bias'] = torch.randn(out_f, generator=g) * 0.02
+
+    lin('proj_in', C, latent_dim)
+    sd['pos_embed'] = torch.randn(1, latent_size, C, generator=g) / math.sqrt(C)
+    lin('timestep_proj.linear_1', C, 256)
+    lin('timestep_proj.linear_2', C, C)
+    lin('adaln_linear', 6 * C, C, 0.5)
+    for l in range(num_layers):
+        p = f'layers.{l}.'
+        lin(p + 'attn1.qkv_proj', 3 * C, C)
+        lin(p + 'attn1.out_proj', C, C)
+        for n in ('q_proj', 'k_proj', 'v_proj', 'out_proj'):
+            lin(p + 'attn2.' + n, C, C)
+        lin(p + 'ff.net.0', 8 * C, C)
+        lin(p + 'ff.net.2', C, 4 * C)
+        sd[p + 'scale_shift_table'] = torch.randn(6, C, generator=g) / math.sqrt(C)
+    sd['scale_shift_table'] = torch.randn(2, C, generator=g) / math.sqrt(C)
+    lin('proj_out', latent_dim, C)
+    if cond_dim is not None:
+        out = {'dit.' + k: v for k, v in sd.items()}
+        w = torch.randn(C, cond_dim, generator=g) / math.sqrt(cond_dim)
+        out.update({'proj_cond.weight': w, 'proj_cond.bias': torch.randn(C, generator=g) * 0.02,
+                    'norm_cond.weight': 1 + 0.1 * torch.randn(C, generator=g), 'norm_cond.bias': 0.05 * torch.randn(C, generator=g)})
+        return out
+    return sd
