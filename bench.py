@@ -285,6 +285,154 @@ def run_teacher_forced(args):
     }), flush=True)
 
 
+def ref_dit_leg(kind, images, steps, warmup, layers=24, timeout=900):
+    """oracle/ref_dit_leg.py in its own process -> dict (reference DiT module when oracle/_ref/py travelled, else the oracle port)."""
+    cmd = [sys.executable, os.path.join(REPO, 'oracle', 'ref_dit_leg.py'), kind, '--images', str(images), '--steps', str(steps), '--warmup', str(warmup),
+           '--layers', str(layers)]
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'TORCHELASTIC_RUN_ID'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        return {'error': f'reference DiT {kind} leg timed out after {timeout}s'}
+    for line in out.stdout.splitlines():
+        if line.startswith('REF_DIT_LEG '):
+            return json.loads(line[12:])
+    return {'error': (out.stderr or out.stdout)[-400:]}
+
+
+DIT_METRIC = 'DiT denoiser steps/sec, guided DDIM sampling of 4 images (denoiser batch 8 x 2048 latents, 24 layers; BASELINE configs[4] denoise stage)'
+
+
+def run_dit(args):
+    """BASELINE configs[4], the stage this repository adds to the image-conditioned path: MDiT.run — 100 guided DDIM steps for a batch of 4
+    images (denoiser batch 8) at the DiT preset size.  A bench step = one whole sampling run.  value = denoiser steps/s over all ranks
+    (replicas: every rank samples its own 4 images); roofline: tensor-bound, GEMM + attention FLOPs of the denoiser forward against
+    MEASURED_PEAKS bf16_tflops_sustained; e2e: er_dit_run_host (condition + noise uploaded, latents read back every step)."""
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    import numpy as np
+    from core.models_dit import DDIMScheduler
+    from edgerunner_b200 import synth
+    from edgerunner_b200.dit_engine import DiTEngine
+    R, S, M = 4, 100, 257
+    cfg = dict(hidden_dim=1024, num_heads=16, latent_size=2048, latent_dim=64, num_layers=24) if not args.tiny else \
+        dict(hidden_dim=128, num_heads=2, latent_size=64, latent_dim=16, num_layers=2)
+    eng = DiTEngine(dev, cfg['hidden_dim'], cfg['num_heads'], cfg['num_layers'], cfg['latent_size'], cfg['latent_dim'], M, 1280)
+    eng.load_state_dict(synth.synth_dit_state_dict(**cfg, cond_dim=1280, seed=0))
+    sched = DDIMScheduler(prediction_type='v_prediction')
+    sched.set_timesteps(S)
+    ts = sched.timesteps.numpy().astype(np.float32)
+    coef = sched.step_coefficients(sched.timesteps).numpy()
+    g = torch.Generator().manual_seed(200 + rank)
+    cond_h = torch.randn(R, M, cfg['hidden_dim'], generator=g).pin_memory()
+    noise_h = torch.randn(R, cfg['latent_size'], cfg['latent_dim'], generator=g).pin_memory()
+    cond_d, noise_d = cond_h.to(dev), noise_h.to(dev)
+    lat = torch.empty_like(noise_d)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one():
+        lat.copy_(noise_d)
+        eng.run(cond_d, lat, ts, coef, 7.5, True, 'v_prediction')
+    for _ in range(max(args.warmup, 1)):
+        one()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    l0 = eng.kernel_launches()
+    ev[0].record()
+    for _ in range(args.steps):
+        one()
+    ev[1].record()
+    barrier()
+    launches = eng.kernel_launches() - l0
+    ms = ev[0].elapsed_time(ev[1])
+    # e2e: host buffers through the C ABI
+    lat_h = np.empty_like(noise_h.numpy())
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    np.copyto(lat_h, noise_h.numpy()); eng.run_host(cond_h.numpy(), lat_h, ts, coef, 7.5, True, 'v_prediction')
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        np.copyto(lat_h, noise_h.numpy())
+        eng.run_host(cond_h.numpy(), lat_h, ts, coef, 7.5, True, 'v_prediction')
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    finite = bool(np.isfinite(lat_h).all())
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0].item()), float(t[1].item())
+        dist.destroy_process_group()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    ms_step = ms / args.steps
+    flops = eng.flops_per_forward(2 * R) * S
+    peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    peak = float(json.load(open(peaks_path)).get('bf16_tflops_sustained', 1400.0)) if os.path.exists(peaks_path) else 1400.0
+    tf = flops / (ms_step * 1e-3) / 1e12
+    line = {
+        'metric': DIT_METRIC, 'value': world * S / (ms_step * 1e-3), 'unit': 'denoiser steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+        'config': {'workload': f'MDiT.run: {S} guided DDIM steps (v_prediction, guidance 7.5), {R} images/GPU -> denoiser batch {2 * R} x {cfg["latent_size"]} latents, '
+                               f'{cfg["num_layers"]} layers x {cfg["hidden_dim"]}, {M} condition tokens; replicas x{world}',
+                   'l2': 'activations (16384 rows x 1024..8192 fp16, 33..268 MB per tensor) exceed L2', 'latents_finite': finite},
+        'clocks': clocks, 'gpu_launches': int(launches),
+        'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'traffic': None,
+                     'kernel': 'er::tc::gemm_tcgen05_kernel + er::fa::attention_tcgen05_kernel (inside one CUDA graph per step)',
+                     'algorithmic_flops_per_step_per_gpu': flops, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)'},
+        'e2e': {'value': world * S / e2e_s, 'unit': 'denoiser steps/s', 'h2d_bytes_per_step': int(cond_h.numel() * 4 + noise_h.numel() * 4),
+                'd2h_bytes_per_step': int(noise_h.numel() * 4), 'note': 'er_dit_run_host: condition + noise uploaded, latents read back, synchronous'},
+    }
+    if not args.no_reference_gpu and not args.tiny:
+        rg = ref_dit_leg('gpu', R, 3, 2)
+        if rg and 's_per_forward' in rg:
+            line['reference_gpu'] = {'value': 1.0 / rg['s_per_forward'], 'unit': 'denoiser steps/s', 'impl': rg.get('impl'), 'flash_attn': rg.get('flash_attn'),
+                                     'sample': f"{rg['impl']} DiT module, .half() + autocast(fp16), denoiser batch {rg['batch']}, forward only (no scheduler / guidance)"}
+        else:
+            line['reference_gpu'] = rg
+    if not args.no_cpu_baseline and not args.tiny:
+        rc = ref_dit_leg('cpu', 1, 1, 1)
+        if rc and 's_per_forward' in rc:
+            line['cpu_baseline'] = {'value': 1.0 / (rc['s_per_forward'] * R), 'unit': 'denoiser steps/s', 'cores': rc.get('cores'), 'kind': rc.get('impl'),
+                                    'sample': f"1 denoiser forward of 1 image (batch 2), fp32 torch CPU ops, scaled x{R} to the 4-image step"}
+        else:
+            line['cpu_baseline'] = rc
+    print(json.dumps(line), flush=True)
+
+
+def run_dit_reference_arm(args):
+    """`--impl reference --workload dit`: the reference's DiT module on the host cores (fp32, naive attention), bounded sample = one denoiser
+    forward of one image (batch 2) per step, scaled to the 4-image step."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    R = 4
+    rc = ref_dit_leg('cpu', 1, max(args.steps, 1), min(args.warmup, 1), timeout=1500)
+    if not rc or 's_per_forward' not in rc:
+        print(json.dumps({'impl': 'reference', 'unavailable': str(rc)[:200]}), flush=True)
+        return
+    v = 1.0 / (rc['s_per_forward'] * R)
+    cb = {'value': v, 'unit': 'denoiser steps/s', 'cores': rc.get('cores'), 'kind': rc.get('impl'),
+          'sample': f"{args.steps} x one denoiser forward of 1 image (batch 2), fp32 torch CPU ops, scaled x{R} to the 4-image step"}
+    print(json.dumps({'impl': 'reference', 'metric': DIT_METRIC, 'value': v, 'unit': 'denoiser steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+                      'warmup': args.warmup, 'ms_per_step': rc['s_per_forward'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                      'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': 'reference DiT module forward, CPU', 'sample': cb['sample']},
+                      'cpu_baseline': cb, 'e2e': {'value': v, 'unit': 'denoiser steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -298,12 +446,15 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-reference-gpu', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3, help='timed LMM.generate calls of the e2e leg (bounded: each is a full 16k request)')
-    ap.add_argument('--workload', default='decode', choices=['decode', 'tf'],
+    ap.add_argument('--workload', default='decode', choices=['decode', 'tf', 'dit'],
                     help="decode = BASELINE configs[1] (the metric); tf = configs[3]: teacher-forced forward seq 8192 batch 4/GPU, loss all-reduced over NCCL")
     args = ap.parse_args()
 
     if args.impl == 'reference':
-        run_reference_arm(args)
+        (run_dit_reference_arm if args.workload == 'dit' else run_reference_arm)(args)
+        return
+    if args.workload == 'dit':
+        run_dit(args)
         return
     if args.workload == 'tf':
         run_teacher_forced(args)

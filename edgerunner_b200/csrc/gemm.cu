@@ -154,6 +154,7 @@ cudaError_t er_gemm(const er::GemmArgs& g, cudaStream_t stream) {
         const cudaError_t e = er_gemm_tcgen05(g, stream);
         if (e != cudaErrorNotSupported) return e;
     }
+    if (g.mode == er::GEMM_F16_GEGLU || g.mode == er::GEMM_GATE_RES32) return cudaErrorNotSupported;   // fused DiT epilogues exist in the tcgen05 kernel only
     if ((g.K & 7) || (g.lda & 7) || (g.ldw & 7)) return cudaErrorInvalidValue;
     static bool attr[64] = {};                 // per DEVICE: the attribute belongs to the function on the current device's context
     const int smem = STAGES * (BM + BN) * 64;

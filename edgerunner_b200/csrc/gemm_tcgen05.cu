@@ -9,8 +9,10 @@
 //   warp 1      MMA issuer (one elected lane): 4 x tcgen05.mma.cta_group::1.kind::f16 (M 128, N 256, K 16) per stage from shared-memory
 //               matrix descriptors; the accumulator lives in 256 TMEM columns and there are TWO of them (all 512 columns), so the next
 //               tile's main loop runs while the epilogue drains the previous one; tcgen05.commit releases smem stages / publishes a tile
-//   warps 2..5  epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (one output row per thread), tcgen05.ld 16 columns at a time, bias,
-//               rounding / ReLU / residual of the mode, 32- / 64-byte row segments stored straight from registers
+//   warps 2..9  epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (one output row per thread) and one 128-column half of the tile,
+//               tcgen05.ld 32 columns at a time, bias, rounding / ReLU / residual / GEGLU / gated residual of the mode, 32- / 64-byte row
+//               segments stored straight from registers.  Eight warps because with K = 1024 a tile's main loop is only ~8k cycles: four
+//               warps could not drain an fp32-residual epilogue (16 dependent global round trips per row) in that time
 // SASS: UTCHMMA, UTMALDG.2D, LDTM, UTCBAR, SYNCS.  The descriptors follow cute::UMMA (SmemDescriptor / InstrDescriptor of the CUTLASS
 // headers vendored under flashinfer/data/cutlass); scripts/microbench/gemm_tcgen05.cu is the single-tile self-checking precursor
 // (profiles/r02_microbench_gemm_tcgen05_draft.txt).
@@ -27,7 +29,7 @@ namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 64, UK = 16, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 16 KB + 32 KB
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;
 constexpr uint32_t TMEM_COLS = 512;     // two 256-column accumulators
 
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,8 +77,54 @@ struct EpiArgs {
     const __half* bias; int mode;
     __half* out16; float* out32; int ldo;
     const __half* res16; const float* res32; int ldr;
+    const __half *gate_tab, *gate_t; long long gate_bs; int n_per;
     int M, N, K;
 };
+
+__device__ __forceinline__ void load16h(const __half* p, float* f) {      // 16 fp16 (32-byte aligned run) -> fp32
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 8);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) { const float2 t = h2f2(w[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ void store16h(__half* p, const float* f) {
+    __align__(16) __half h[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) h[j] = __float2half_rn(f[j]);
+    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(p + 8) = *reinterpret_cast<const uint4*>(h + 8);
+}
+// GEMM_F16_GEGLU: columns [col, col+16) are the value half, [col+16, col+32) the gate half of output columns [col/2, col/2+16)
+__device__ __forceinline__ void epilogue_geglu32(const EpiArgs& g, const int row, const int col, const uint32_t* v) {
+    float ba[16], bg[16], o[16];
+    load16h(g.bias + col, ba); load16h(g.bias + col + 16, bg);
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const float a = round_f16(__uint_as_float(v[j]) + ba[j]);
+        const float x = round_f16(__uint_as_float(v[16 + j]) + bg[j]);
+        o[j] = a * round_f16(0.5f * x * (1.f + erff(x * 0.70710678118654752440f)));
+    }
+    store16h(g.out16 + (size_t)row * g.ldo + (col >> 1), o);
+}
+// GEMM_GATE_RES32 over 16 columns
+__device__ __forceinline__ void epilogue_gate16(const EpiArgs& g, const int row, const int col, const uint32_t* v) {
+    float b[16], gt[16], tv[16], o[16];
+    const float* rp = g.res32 + (size_t)row * g.ldr + col;
+    float4 r[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) r[j] = *reinterpret_cast<const float4*>(rp + 4 * j);
+    load16h(g.bias + col, b); load16h(g.gate_tab + col, gt); load16h(g.gate_t + (size_t)(row / g.n_per) * g.gate_bs + col, tv);
+    const float* rf = reinterpret_cast<const float*>(r);
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const float y = round_f16(__uint_as_float(v[j]) + b[j]);
+        o[j] = rf[j] + round_f16(round_f16(gt[j] + tv[j]) * y);
+    }
+    float* op = g.out32 + (size_t)row * g.ldo + col;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    if (g.out16) store16h(g.out16 + (size_t)row * g.ldo + col, o);
+}
 
 // 16 consecutive columns [col, col+16) of output row `row`: v = fp32 accumulators
 __device__ __forceinline__ void epilogue_16(const EpiArgs& g, const int row, const int col, const uint32_t* v) {
@@ -154,7 +202,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; i++) { mbar_init(s_addr(&full_bar[i]), 1); mbar_init(s_addr(&empty_bar[i]), 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(s_addr(&acc_full[i]), 1); mbar_init(s_addr(&acc_empty[i]), 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(s_addr(&acc_full[i]), 1); mbar_init(s_addr(&acc_empty[i]), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {       // one warp allocates all 512 TMEM columns (1 CTA per SM: the shared-memory ring alone guarantees it)
@@ -204,30 +252,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 umma_commit(s_addr(&acc_full[buf]));              // accumulator of this tile complete
             }
         }
-    } else {                                                      // ===== epilogue (warps 2..5) =====
+    } else {                                                      // ===== epilogue (warps 2..9) =====
         const int quad = warp & 3;                                // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;                         // which 128 columns of the tile
         uint32_t local = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++local) {
             const uint32_t buf = local & 1;
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN + half * (BN / 2);
             mbar_wait(s_addr(&acc_full[buf]), (local >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + quad * 32 + lane;
-            const int ncols = min(BN, g.N - n0);
+            const int ncols = min(BN / 2, g.N - n0);
 #pragma unroll 1
-            for (int c0 = 0; c0 < ncols; c0 += 16) {
-                uint32_t v[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN + (uint32_t)c0;
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                             : "r"(taddr));
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN + (uint32_t)(half * (BN / 2) + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                      "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                      "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < g.M) epilogue_16(g, row, n0 + c0, v);
+                if (row < g.M) {
+                    if (g.mode == GEMM_F16_GEGLU) {
+                        epilogue_geglu32(g, row, n0 + c0, v);
+                    } else if (g.mode == GEMM_GATE_RES32) {
+                        epilogue_gate16(g, row, n0 + c0, v);
+                        epilogue_gate16(g, row, n0 + c0 + 16, v + 16);
+                    } else {
+                        epilogue_16(g, row, n0 + c0, v);
+                        if (c0 + 16 < ncols) epilogue_16(g, row, n0 + c0 + 16, v + 16);
+                    }
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(s_addr(&acc_empty[buf]));  // 4 arrivals (one per epilogue warp) free the accumulator
+            if (lane == 0) mbar_arrive(s_addr(&acc_empty[buf]));  // 8 arrivals (one per epilogue warp) free the accumulator
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -267,10 +328,16 @@ cudaError_t er_gemm_tcgen05(const er::GemmArgs& a, cudaStream_t stream) {
     using namespace er::tc;
     if ((a.lda & 7) || (a.ldw & 7) || ((uintptr_t)a.A & 15) || ((uintptr_t)a.W & 15) || a.K < 8) return cudaErrorNotSupported;
     if (a.bias && ((uintptr_t)a.bias & 15)) return cudaErrorNotSupported;
+    if (a.mode == er::GEMM_F16_GEGLU || a.mode == er::GEMM_GATE_RES32) {        // fused DiT epilogues: vector accesses only, no ragged N
+        if ((a.N & 31) || !a.bias || (a.ldo & 7)) return cudaErrorInvalidValue;
+        if (a.mode == er::GEMM_GATE_RES32 && (!a.res32 || !a.out32 || !a.gate_tab || !a.gate_t || a.n_per <= 0 || (a.ldr & 3) || (a.gate_bs & 7)))
+            return cudaErrorInvalidValue;
+    }
     CUtensorMap ma, mw;
     if (!make_map(&ma, a.A, a.M, a.K, a.lda, BM) || !make_map(&mw, a.W, a.N, a.K, a.ldw, BN)) return cudaErrorNotSupported;
     EpiArgs g{};
     g.bias = a.bias; g.mode = a.mode; g.out16 = a.out16; g.out32 = a.out32; g.ldo = a.ldo; g.res16 = a.res16; g.res32 = a.res32; g.ldr = a.ldr;
+    g.gate_tab = a.gate_tab; g.gate_t = a.gate_t; g.gate_bs = a.gate_bs; g.n_per = a.n_per;
     g.M = a.M; g.N = a.N; g.K = a.K;
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

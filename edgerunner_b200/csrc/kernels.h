@@ -12,6 +12,11 @@ enum GemmMode {
     GEMM_F16_RES16 = 2,  // out16 = f16( f16(acc + bias) + res16 )        (fp16 + fp16 residual, encoder)
     GEMM_F32_RES32 = 3,  // out32 = res32 + f16(acc + bias)               (fp32 + fp16 residual, decoder)
     GEMM_F32 = 4,        // out32 = acc (+ bias)                          (logits before the fp16 store)
+    // tcgen05 kernel only (DiT denoiser, dit.cu); N must be a multiple of 32:
+    GEMM_F16_GEGLU = 5,  // W rows interleaved in groups of 16 (16 value rows, then their 16 gate rows): out16[row][n / 2 ..] =
+                         // f16( f16(acc_a + bias) * f16(gelu_erf(f16(acc_g + bias))) ), ldo = row pitch of the N / 2 wide output
+    GEMM_GATE_RES32 = 6, // y = f16(acc + bias); gate = f16(gate_tab[n] + gate_t[(row / n_per) * gate_bs + n]);
+                         // out32 = res32 + f16(gate * y); out16 (optional) = f16(out32)
 };
 
 struct GemmArgs {
@@ -22,6 +27,7 @@ struct GemmArgs {
     int mode;
     __half* out16; float* out32; int ldo;
     const __half* res16; const float* res32; int ldr;
+    const __half *gate_tab, *gate_t; long long gate_bs; int n_per;     // GEMM_GATE_RES32
 };
 
 struct AttnArgs {   // softmax(q k^T / sqrt(D)) v ; q [B][Nq][H][D], k/v [B][Nk][H][D] with element strides
