@@ -62,7 +62,10 @@ def test_dit_forward_matches_oracle_preset_shape():
     """the preset's layer shape (1024 wide, 16 heads, 2048 latents, 257 CLIP tokens), 3 layers, batch 2."""
     cfg = dict(hidden_dim=1024, num_heads=16, latent_size=2048, latent_dim=64, num_layers=3)
     sd, x, c, t, orc, eng = _case(cfg, 257, 2, cond_dim=1280)
-XX, float(d.max()), 'mean', float(d.mean()), 'ref mean abs', float(ref.abs().mean()))
+    y = eng.forward(x, c, t).float()
+    ref = orc.forward(x, c, t)
+    d = (y - ref).abs()
+    print('preset shape: max', float(d.max()), 'mean', float(d.mean()), 'ref mean abs', float(ref.abs().mean()))
     assert float(ref.abs().mean()) > 0.1 and float(d.max()) <= 3e-2 and float(d.mean()) <= 2e-3
 
 
