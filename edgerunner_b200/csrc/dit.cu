@@ -45,16 +45,18 @@ __device__ __forceinline__ float mod_val(const __half* tab, const __half* tv, in
 // LayerNorm(eps 1e-6, no affine) in fp32, then x * (1 + scale) + shift (dit.py:127-128,134-135,191-192).
 // in: in32 [M][C], or in16 [M][C] (+ add16 [(row % n_per)][C]: the learned positions, summed in fp16 first — dit.py:176).
 // shift = f16(tab_shift + t_shift[b]), scale = f16(tab_scale + t_scale[b]), b = row / n_per.  One block (128 threads) per row.
+// Rows below `split` read alt32 + cadd instead of in32 (the unconditional half of a guided step, see denoiser()).
 __global__ void __launch_bounds__(128) dit_ln_mod_kernel(const float* __restrict__ in32, const __half* __restrict__ in16, const __half* __restrict__ add16,
                                                          const __half* tab_shift, const __half* tab_scale, const __half* t_shift, const __half* t_scale,
-                                                         long long t_bs, int n_per, float* __restrict__ out32, __half* __restrict__ out16, int C) {
+                                                         long long t_bs, int n_per, float* __restrict__ out32, __half* __restrict__ out16, int C,
+                                                         const float* __restrict__ alt32, const __half* __restrict__ cadd, int split) {
     const int row = blockIdx.x, tid = threadIdx.x;
     const int b = row / n_per;
     __shared__ float red[4];
     __shared__ float srow[2048];
     const int Cs = C <= 2048 ? C : 0;      // rows up to 2048 wide are staged in shared memory; wider ones are re-read
     auto load = [&](int c) -> float {
-        if (in32) return in32[(size_t)row * C + c];
+        if (in32) return row < split ? __fadd_rn(alt32[(size_t)row * C + c], h2f(cadd[c])) : in32[(size_t)row * C + c];
         float v = h2f(in16[(size_t)row * C + c]);
         if (add16) v = rh(v + h2f(add16[(size_t)(row % n_per) * C + c]));
         return v;
@@ -232,6 +234,8 @@ struct er_dit {
     __half *x16 = nullptr, *qkv16 = nullptr, *a16 = nullptr, *y16 = nullptr, *h16 = nullptr, *g16 = nullptr, *in16 = nullptr, *pred16 = nullptr;
     __half *c16 = nullptr, *kv16 = nullptr;        // condition fp16 [batch][M][C]; per layer K|V [NL][batch * M][2C]
     __half *pc16 = nullptr;                        // proj_cond output
+    __half *cconst16 = nullptr;                    // [NL][C] cross-attention branch of a zero-condition sample
+    int uncond_shortcut = 1;
     // timestep path: capacity max_steps rows
     int max_steps = 0;
     float* t_dev = nullptr; __half *te256 = nullptr, *te1 = nullptr, *te1s = nullptr, *temb = nullptr, *tembs = nullptr, *ada = nullptr;
@@ -316,6 +320,7 @@ extern "C" int er_dit_create(const er_dit_config* cfg, er_dit** out) {
     if (!rc) rc = dalloc(e, &e->temb_cur, C);
     if (!rc) rc = dalloc(e, &e->coef_cur, 1);
     if (!rc) rc = dalloc(e, &e->counter, 1);
+    if (!rc) rc = dalloc(e, &e->cconst16, (size_t)e->NL * C + 64);
     if (rc) { er_dit_destroy(e); return rc; }
     *out = e;
     return ER_OK;
@@ -414,17 +419,27 @@ static int timestep_path(er_dit* e, int n, cudaStream_t st) {
     return ER_OK;
 }
 // K | V of the condition rows for every layer (CrossAttention.k_proj / v_proj, attention.py:147-148): kv16 [NL][batch * M][2C]
-static int cond_kv(er_dit* e, int batch, cudaStream_t st) {
-    const int C = e->C, rows = batch * e->M;
-    for (int l = 0; l < e->NL; l++)
-        CKL(e, gemm(e->c16, C, e->L[l].kv_w, e->L[l].kv_b, rows, 2 * C, C, er::GEMM_F16, e->kv16 + (size_t)l * rows * 2 * C, nullptr, 2 * C, nullptr, st));
+// Samples [0, uncond) have an all-zero condition: no K / V rows are needed for them (see denoiser()); their cross-attention branch is the
+// constant row cconst16[l] = out_proj(value bias).
+static int cond_kv(er_dit* e, int batch, int uncond, cudaStream_t st) {
+    const int C = e->C, rows = batch * e->M, skip = uncond * e->M;
+    for (int l = 0; l < e->NL; l++) {
+        CKL(e, gemm(e->c16 + (size_t)skip * C, C, e->L[l].kv_w, e->L[l].kv_b, rows - skip, 2 * C, C, er::GEMM_F16,
+                    e->kv16 + ((size_t)l * rows + skip) * 2 * C, nullptr, 2 * C, nullptr, st));
+        if (uncond) CKL(e, gemm(e->L[l].kv_b + C, C, e->L[l].o2_w, e->L[l].o2_b, 1, C, C, er::GEMM_F16, e->cconst16 + (size_t)l * C, nullptr, C, nullptr, st));
+    }
     return ER_OK;
 }
 
 // One denoiser forward over `batch` samples: in16 [batch][N][DL] -> pred16 [batch][N][DL].  adaLN vectors at ada / temb with sample stride
 // (ada_bs, temb_bs) (0: all samples share one timestep).  Needs cond_kv() for this batch.
-static int denoiser(er_dit* e, int batch, const __half* ada, long long ada_bs, const __half* temb, long long temb_bs, cudaStream_t st) {
+// uncond > 0 (a guided step: samples [0, uncond) carry the all-zero condition): their cross-attention is skipped.  With a zero condition every
+// key / value row of such a sample equals the projection bias, so softmax weights are uniform and the attention output is the value bias
+// exactly (k * v_fp16 is exact in fp32 for k <= 257); out_proj of identical rows is one row, computed once per run by the same GEMM kernel
+// (cconst16, bit-identical to any row of the full product).  The branch then is `x += const` and is folded into the next LayerNorm's load.
+static int denoiser(er_dit* e, int batch, const __half* ada, long long ada_bs, const __half* temb, long long temb_bs, int uncond, cudaStream_t st) {
     const int C = e->C, N = e->N, H = e->H, D = e->D, rows = batch * N, crows = batch * e->M;
+    const int urows = uncond * N, ucrows = uncond * e->M;
     const unsigned ew4 = (unsigned)(((size_t)rows * C / 4 + 255) / 256);
     const bool fuse = e->fuse && !(C & 31);      // GEGLU and the two gated residuals in the GEMM epilogues (3 kernels and ~0.9 GB of traffic less per layer)
     CKL(e, gemm(e->in16, e->DL, e->pin_w, e->pin_b, rows, C, e->DL, er::GEMM_F16, e->x16, nullptr, C, nullptr, st));
@@ -433,7 +448,7 @@ static int denoiser(er_dit* e, int batch, const __half* ada, long long ada_bs, c
         const er_dit::Layer& y = e->L[l];
         // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = rows 0..5 (dit.py:125)
         CKL(e, (dit_ln_mod_kernel<<<rows, 128, 0, st>>>(xin32, xin32 ? nullptr : e->x16, xin32 ? nullptr : e->pos, y.table, y.table + C, ada, ada + C, ada_bs, N,
-                                                       e->xa32, e->x16, C), cudaGetLastError()));
+                                                       e->xa32, e->x16, C, nullptr, nullptr, 0), cudaGetLastError()));
         CKL(e, gemm(e->x16, C, y.qkv_w, y.qkv_b, rows, 3 * C, C, er::GEMM_F16, e->qkv16, nullptr, 3 * C, nullptr, st));
         er::AttnArgs a{};
         a.q = e->qkv16; a.k = e->qkv16 + C; a.v = e->qkv16 + 2 * C; a.out = e->a16;
@@ -447,17 +462,18 @@ static int denoiser(er_dit* e, int batch, const __half* ada, long long ada_bs, c
             CKL(e, (dit_gate_res_kernel<<<ew4, 256, 0, st>>>(e->xa32, e->y16, y.table + 2 * C, ada + 2 * C, ada_bs, N, e->xb32, e->x16, (size_t)rows, C), cudaGetLastError()));
         }
         // cross-attention to the condition (dit.py:131): x = x + attn2(x, c)
-        CKL(e, gemm(e->x16, C, y.q_w, y.q_b, rows, C, C, er::GEMM_F16, e->qkv16, nullptr, C, nullptr, st));
-        const __half* kv = e->kv16 + (size_t)l * crows * 2 * C;
+        const size_t uo = (size_t)urows * C;
+        CKL(e, gemm(e->x16 + uo, C, y.q_w, y.q_b, rows - urows, C, C, er::GEMM_F16, e->qkv16 + uo, nullptr, C, nullptr, st));
+        const __half* kv = e->kv16 + ((size_t)l * crows + ucrows) * 2 * C;
         er::AttnArgs x{};
-        x.q = e->qkv16; x.k = kv; x.v = kv + C; x.out = e->a16;
+        x.q = e->qkv16 + uo; x.k = kv; x.v = kv + C; x.out = e->a16 + uo;
         x.ldq = C; x.ldk = x.ldv = 2 * C; x.ldo = C; x.q_bs = x.o_bs = (long long)N * C; x.k_bs = x.v_bs = (long long)e->M * 2 * C;
-        x.B = batch; x.H = H; x.Nq = N; x.Nk = e->M; x.D = D; x.causal = 0;
+        x.B = batch - uncond; x.H = H; x.Nq = N; x.Nk = e->M; x.D = D; x.causal = 0;
         CKL(e, er_attention(x, st));
-        CKL(e, gemm(e->a16, C, y.o2_w, y.o2_b, rows, C, C, er::GEMM_F32_RES32, nullptr, e->xa32, C, e->xb32, st));
+        CKL(e, gemm(e->a16 + uo, C, y.o2_w, y.o2_b, rows - urows, C, C, er::GEMM_F32_RES32, nullptr, e->xa32 + uo, C, e->xb32 + uo, st));
         // feed-forward (dit.py:133-136)
         CKL(e, (dit_ln_mod_kernel<<<rows, 128, 0, st>>>(e->xa32, nullptr, nullptr, y.table + 3 * C, y.table + 4 * C, ada + 3 * C, ada + 4 * C, ada_bs, N, e->xb32,
-                                                       e->x16, C), cudaGetLastError()));
+                                                       e->x16, C, e->xb32, e->cconst16 + (size_t)l * C, urows), cudaGetLastError()));
         if (fuse) {
             CKL(e, gemm(e->x16, C, y.ff1_wi, y.ff1_bi, rows, 8 * C, C, er::GEMM_F16_GEGLU, e->g16, nullptr, 4 * C, nullptr, st));
             CKL(e, gemm_gate(e->g16, 4 * C, y.ff2_w, y.ff2_b, rows, C, 4 * C, e->xb32, e->xa32, nullptr, y.table + 5 * C, ada + 5 * C, ada_bs, N, st));
@@ -470,7 +486,7 @@ static int denoiser(er_dit* e, int batch, const __half* ada, long long ada_bs, c
         xin32 = e->xa32;
     }
     // shift, scale = (table2 + t_emb).chunk(2) ; norm_out ; modulate ; proj_out  (dit.py:189-194)
-    CKL(e, (dit_ln_mod_kernel<<<rows, 128, 0, st>>>(xin32, nullptr, nullptr, e->table2, e->table2 + C, temb, temb, temb_bs, N, nullptr, e->x16, C), cudaGetLastError()));
+    CKL(e, (dit_ln_mod_kernel<<<rows, 128, 0, st>>>(xin32, nullptr, nullptr, e->table2, e->table2 + C, temb, temb, temb_bs, N, nullptr, e->x16, C, nullptr, nullptr, 0), cudaGetLastError()));
     CKL(e, gemm(e->x16, C, e->pout_w, e->pout_b, rows, e->DL, C, er::GEMM_F16, e->pred16, nullptr, e->DL, nullptr, st));
     return ER_OK;
 }
@@ -502,8 +518,8 @@ extern "C" int er_dit_forward(er_dit* e, const float* x_dev, const float* cond_d
     CKL(e, er_f32_to_f16(cond_dev, e->c16, nc, st));
     CK(cudaMemcpyAsync(e->t_dev, t_dev, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
     if ((rc = timestep_path(e, B, st))) return rc;
-    if ((rc = cond_kv(e, B, st))) return rc;
-    if ((rc = denoiser(e, B, e->ada, 6LL * e->C, e->temb, e->C, st))) return rc;
+    if ((rc = cond_kv(e, B, 0, st))) return rc;
+    if ((rc = denoiser(e, B, e->ada, 6LL * e->C, e->temb, e->C, 0, st))) return rc;
     CK(cudaMemcpyAsync(out_dev, e->pred16, nx * sizeof(__half), cudaMemcpyDeviceToDevice, st));
     return ER_OK;
 }
@@ -515,7 +531,7 @@ static int one_step(er_dit* e, float* lat, int R, int guided, float gscale, int 
     CKL(e, (dit_select_step_kernel<<<8, 256, 0, st>>>(e->counter, e->ada, e->temb, e->coef_dev, e->ada_cur, e->temb_cur, e->coef_cur, e->C), cudaGetLastError()));
     if (guided) CKL(e, (dit_dup_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lat, e->in16, n), cudaGetLastError()));
     else CKL(e, er_f32_to_f16(lat, e->in16, n, st));
-    int rc = denoiser(e, batch, e->ada_cur, 0, e->temb_cur, 0, st);
+    int rc = denoiser(e, batch, e->ada_cur, 0, e->temb_cur, 0, guided && e->uncond_shortcut ? R : 0, st);
     if (rc) return rc;
     CKL(e, (dit_guide_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->pred16, lat, n, gscale, guided, v_pred, e->coef_cur, e->counter), cudaGetLastError()));
     return ER_OK;
@@ -538,7 +554,7 @@ extern "C" int er_dit_run(er_dit* e, const float* cond_dev, float* latents_dev, 
     // hoisted out of the loop: condition K / V of every layer, timestep MLP + adaLN vectors of every step, scheduler coefficients
     if (guided) CKL(e, (dit_cfg_cond_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cond_dev, e->c16, nc), cudaGetLastError()));
     else CKL(e, er_f32_to_f16(cond_dev, e->c16, nc, st));
-    if ((rc = cond_kv(e, batch, st))) return rc;
+    if ((rc = cond_kv(e, batch, guided && e->uncond_shortcut ? R : 0, st))) return rc;
     CK(cudaMemcpyAsync(e->t_dev, timesteps_host, sizeof(float) * n_steps, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(e->coef_dev, coef_host, sizeof(StepCoef) * n_steps, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));        // the host arrays may be pageable / reused by the caller
@@ -595,6 +611,7 @@ extern "C" int er_dit_debug_set(er_dit* e, const char* key, int64_t value) {
     if (!e || !key) return er_set_error(ER_ERR_INVALID, "null argument");
     if (!strcmp(key, "graph")) { e->use_graph = value != 0; return ER_OK; }
     if (!strcmp(key, "fuse")) { e->fuse = value != 0; return ER_OK; }
+    if (!strcmp(key, "uncond_shortcut")) { e->uncond_shortcut = value != 0; if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; } return ER_OK; }
     return er_set_error(ER_ERR_INVALID, "unknown key '%s'", key);
 }
 // algorithmic FLOPs of one denoiser forward over `batch` samples (GEMMs + attention; bench.py roofline)

@@ -106,26 +106,6 @@ __device__ __forceinline__ void epilogue_geglu32(const EpiArgs& g, const int row
     }
     store16h(g.out16 + (size_t)row * g.ldo + (col >> 1), o);
 }
-// GEMM_GATE_RES32 over 16 columns
-__device__ __forceinline__ void epilogue_gate16(const EpiArgs& g, const int row, const int col, const uint32_t* v) {
-    float b[16], gt[16], tv[16], o[16];
-    const float* rp = g.res32 + (size_t)row * g.ldr + col;
-    float4 r[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) r[j] = *reinterpret_cast<const float4*>(rp + 4 * j);
-    load16h(g.bias + col, b); load16h(g.gate_tab + col, gt); load16h(g.gate_t + (size_t)(row / g.n_per) * g.gate_bs + col, tv);
-    const float* rf = reinterpret_cast<const float*>(r);
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const float y = round_f16(__uint_as_float(v[j]) + b[j]);
-        o[j] = rf[j] + round_f16(round_f16(gt[j] + tv[j]) * y);
-    }
-    float* op = g.out32 + (size_t)row * g.ldo + col;
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-    if (g.out16) store16h(g.out16 + (size_t)row * g.ldo + col, o);
-}
-
 // 16 consecutive columns [col, col+16) of output row `row`: v = fp32 accumulators
 __device__ __forceinline__ void epilogue_16(const EpiArgs& g, const int row, const int col, const uint32_t* v) {
     float x[16];
@@ -199,6 +179,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int nk = (g.K + BK - 1) / BK;
     const int tiles_n = (g.N + BN - 1) / BN, tiles_m = (g.M + BM - 1) / BM, ntiles = tiles_n * tiles_m;
     unsigned char* tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+    float* scratch = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES);      // 8 x 4 KB transpose scratch of the epilogue warps
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; i++) { mbar_init(s_addr(&full_bar[i]), 1); mbar_init(s_addr(&empty_bar[i]), 1); }
@@ -274,12 +255,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                       "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < g.M) {
+                if (g.mode == GEMM_GATE_RES32 || g.mode == GEMM_F32_RES32) {
+                    // fp32 residual stream: one row per thread would make every 128-bit access touch 32 different rows (32 L1 wavefronts
+                    // per instruction; ~20k wavefronts per tile against an ~8k-cycle main loop).  Transpose the warp's 32 x 32 block through a
+                    // private, XOR-swizzled shared-memory scratch instead, so that each global access is one 128-byte row segment.
+                    float* sc = scratch + (warp - 2) * 1024;
+                    const int col = n0 + c0;
+                    const bool two = col + 32 <= g.N;                 // (N is a multiple of 16 for these modes' callers; ragged N handled per element)
+                    float b[32];
+                    if (g.bias && two) { load16h(g.bias + col, b); load16h(g.bias + col + 16, b + 16); }
+                    else { for (int j = 0; j < 32; j++) b[j] = (g.bias && col + j < g.N) ? __half2float(g.bias[col + j]) : 0.f; }
+                    if (g.mode == GEMM_GATE_RES32) {
+                        float gt[32], tv[32];
+                        const __half* tp = g.gate_t + (size_t)(min(row, g.M - 1) / g.n_per) * g.gate_bs + col;
+                        load16h(g.gate_tab + col, gt); load16h(g.gate_tab + col + 16, gt + 16); load16h(tp, tv); load16h(tp + 16, tv + 16);
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            sc[lane * 32 + (j ^ lane)] = round_f16(round_f16(gt[j] + tv[j]) * round_f16(__uint_as_float(v[j]) + b[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) sc[lane * 32 + (j ^ lane)] = round_f16(__uint_as_float(v[j]) + b[j]);
+                    }
+                    __syncwarp();
+                    const int rbase = m0 + quad * 32;
+                    const int nrow = min(32, g.M - rbase);
+                    const int cc = col + lane;
+                    if (cc < g.N) {
+#pragma unroll 4
+                        for (int rr = 0; rr < nrow; rr++) {
+                            const size_t grow = (size_t)(rbase + rr);
+                            const float o = g.res32[grow * g.ldr + cc] + sc[rr * 32 + (lane ^ rr)];
+                            g.out32[grow * g.ldo + cc] = o;
+                            if (g.out16) g.out16[grow * g.ldo + cc] = __float2half_rn(o);
+                        }
+                    }
+                    __syncwarp();
+                } else if (row < g.M) {
                     if (g.mode == GEMM_F16_GEGLU) {
                         epilogue_geglu32(g, row, n0 + c0, v);
-                    } else if (g.mode == GEMM_GATE_RES32) {
-                        epilogue_gate16(g, row, n0 + c0, v);
-                        epilogue_gate16(g, row, n0 + c0 + 16, v + 16);
                     } else {
                         epilogue_16(g, row, n0 + c0, v);
                         if (c0 + 16 < ncols) epilogue_16(g, row, n0 + c0 + 16, v + 16);
@@ -339,7 +352,7 @@ cudaError_t er_gemm_tcgen05(const er::GemmArgs& a, cudaStream_t stream) {
     g.bias = a.bias; g.mode = a.mode; g.out16 = a.out16; g.out32 = a.out32; g.ldo = a.ldo; g.res16 = a.res16; g.res32 = a.res32; g.ldr = a.ldr;
     g.gate_tab = a.gate_tab; g.gate_t = a.gate_t; g.gate_bs = a.gate_bs; g.n_per = a.n_per;
     g.M = a.M; g.N = a.N; g.K = a.K;
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 8 * 4096;
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;

@@ -179,7 +179,8 @@ int er_dit_run_host(er_dit* e, const float* cond_host, float* latents_host, int3
 int64_t er_dit_kernel_launches(const er_dit* e);
 double er_dit_flops_per_forward(const er_dit* e, int32_t batch);   /* GEMM + attention FLOPs of one denoiser forward over `batch` samples */
 int er_dit_debug_set(er_dit* e, const char* key, int64_t value);   /* "graph": 0 = launch every step's kernels directly; "fuse": 0 = GEGLU / gated
-                                                                      residuals as separate kernels instead of GEMM epilogues (A/B timing, bit-identical) */
+                                                                      residuals as separate kernels instead of GEMM epilogues; "uncond_shortcut": 0 = run the
+                                                                      cross-attention of the zero-condition half in full (all A/B timing, bit-identical) */
 
 /* meto tokenizer backends of the reference's pybind module `_meto` (meto/src/bindings.cpp:11-28) */
 #define ER_METO_LR_ABSCO 0   /* Engine_LR_ABSCO: absolute coordinates, vocabulary bins + 3 (the ArAE / DiT presets) */

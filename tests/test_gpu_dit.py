@@ -94,6 +94,10 @@ def test_sampling_loop_matches_oracle(ptype):
     direct = eng.run(c, lat0.clone(), ts.astype(np.float32), coef.numpy(), 7.5, True, ptype)
     assert torch.equal(out, direct)
     eng.debug_set('graph', 1)
+    # the zero-condition half's cross-attention replaced by its closed form (default) == computing it in full, bit for bit
+    eng.debug_set('uncond_shortcut', 0)
+    assert torch.equal(out, eng.run(c, lat0.clone(), ts.astype(np.float32), coef.numpy(), 7.5, True, ptype))
+    eng.debug_set('uncond_shortcut', 1)
     # strength path: start in the middle of a longer schedule; unguided variant runs too
     ts2, coef2 = ddim_tables(10)
     part = eng.run(c, lat0.clone(), ts2[4:].astype(np.float32), coef2[4:].numpy(), 3.0, True, ptype)
