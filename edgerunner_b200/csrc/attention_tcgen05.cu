@@ -2,7 +2,7 @@
 // fp16 operands, fp32 scores / statistics / accumulation, probabilities rounded to fp16 before P V — the arithmetic of the flash kernel the
 // reference calls (core/transformer/attention.py:44-46).  Replaces the mma.sync kernel of attention.cu where the operands meet the TMA rules.
 //
-// One CTA = one (batch, head, 128-query tile); key blocks of 64; 320 threads; two CTAs per SM (80 KB of shared memory and 256 TMEM columns
+// One CTA = one (batch, head, 128-query tile); key blocks of 64; 320 threads; two CTAs per SM (<= 96 KB of shared memory and 256 TMEM columns
 // each).  S is double-buffered in TMEM: Q K^T of block j+1 is issued before the softmax of block j has finished, so the tensor core works
 // under the softmax; the second CTA of the SM fills what is left:
 //   warp 0      TMA producer: Q once, then per key block K and V as 3-D bulk tensor copies {64 dims, 1 head, 64|128 rows} with 128-byte swizzle.
@@ -124,25 +124,28 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     constexpr int KS1 = NA * 4;                        // k16 steps of Q K^T (head dim padded to NA * 64 with zeros)
     constexpr int Q_BYTES = NA * ATOM_Q, K_BYTES = NA * ATOM_K;
     constexpr int DH = D / 2;                          // output dims per softmax thread
+    constexpr int NB = (D <= 64) ? 2 : 1;              // K and V shared-memory buffers (two where two CTAs still fit an SM: the copy of block
+                                                       // j+2 then starts as soon as the MMA of block j has read its buffer, a whole iteration early)
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long q_full, k_full, v_full, k_empty, v_empty, s_full[2], p_full, o_full;
+    __shared__ __align__(8) unsigned long long q_full, k_full[2], v_full[2], k_empty[2], v_empty[2], s_full[2], p_full, o_full[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float xmax[2][BQ];                      // row maxima of the two key halves
     __shared__ float xsum[BQ];                         // final: denominator of the upper half
     unsigned char* base = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
     unsigned char* sQ = base;                          // [NA][128 rows][128 B]
     unsigned char* sK = sQ + Q_BYTES;                  // [NA][64 rows][128 B]
-    unsigned char* sV = sK + K_BYTES;                  // [NA][64 rows][128 B]
-    unsigned char* sP = sV + K_BYTES;                  // [128 rows][128 B]   (64 keys, K-major, swizzled)
+    unsigned char* sV = sK + NB * K_BYTES;             // [NA][64 rows][128 B]
+    unsigned char* sP = sV + NB * K_BYTES;                  // 2 x [128 rows][128 B]   (64 keys, K-major, swizzled); block j uses buffer j & 1
+    constexpr int P_BYTES = BQ * 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
     int nblk = (a.Nk + BKEY - 1) / BKEY;
     if (a.causal) nblk = min(nblk, (m0 + BQ + BKEY - 1) / BKEY);
 
     if (threadIdx.x == 0) {
-        mbar_init(s_addr(&q_full), 1); mbar_init(s_addr(&k_full), 1); mbar_init(s_addr(&v_full), 1);
-        mbar_init(s_addr(&k_empty), 1); mbar_init(s_addr(&v_empty), 1);
-        mbar_init(s_addr(&s_full[0]), 1); mbar_init(s_addr(&s_full[1]), 1); mbar_init(s_addr(&p_full), 8); mbar_init(s_addr(&o_full), 1);
+        mbar_init(s_addr(&q_full), 1);
+        for (int i = 0; i < 2; i++) { mbar_init(s_addr(&k_full[i]), 1); mbar_init(s_addr(&v_full[i]), 1); mbar_init(s_addr(&k_empty[i]), 1); mbar_init(s_addr(&v_empty[i]), 1); }
+        mbar_init(s_addr(&s_full[0]), 1); mbar_init(s_addr(&s_full[1]), 1); mbar_init(s_addr(&p_full), 8); mbar_init(s_addr(&o_full[0]), 1); mbar_init(s_addr(&o_full[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -160,31 +163,33 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             mbar_expect_tx(s_addr(&q_full), Q_BYTES);
 #pragma unroll
             for (int t = 0; t < NA; t++) tma_load_3d(s_addr(sQ + t * ATOM_Q), &map_q, t * 64, h, b * a.Nq + m0, s_addr(&q_full));
-            for (int j = 0; j < nblk; ++j) {
-                if (j > 0) mbar_wait(s_addr(&k_empty), (j - 1) & 1);          // Q K^T of block j-1 has read the K buffer
-                mbar_expect_tx(s_addr(&k_full), K_BYTES);
+            for (int j = 0; j < nblk; ++j) {                      // block j uses buffer j % NB; its barriers are in phase j / NB
+                const int bf = j % NB, ph = j / NB;
+                if (j >= NB) mbar_wait(s_addr(&k_empty[bf]), (ph - 1) & 1);   // Q K^T of block j-NB has read this K buffer
+                mbar_expect_tx(s_addr(&k_full[bf]), K_BYTES);
 #pragma unroll
-                for (int t = 0; t < NA; t++) tma_load_3d(s_addr(sK + t * ATOM_K), &map_k, t * 64, h, b * a.Nk + j * BKEY, s_addr(&k_full));
-                if (j > 0) mbar_wait(s_addr(&v_empty), (j - 1) & 1);          // P V of block j-1 has read the V buffer
-                mbar_expect_tx(s_addr(&v_full), K_BYTES);
+                for (int t = 0; t < NA; t++) tma_load_3d(s_addr(sK + bf * K_BYTES + t * ATOM_K), &map_k, t * 64, h, b * a.Nk + j * BKEY, s_addr(&k_full[bf]));
+                if (j >= NB) mbar_wait(s_addr(&v_empty[bf]), (ph - 1) & 1);   // P V of block j-NB has read this V buffer
+                mbar_expect_tx(s_addr(&v_full[bf]), K_BYTES);
 #pragma unroll
-                for (int t = 0; t < NA; t++) tma_load_3d(s_addr(sV + t * ATOM_K), &map_v, t * 64, h, b * a.Nk + j * BKEY, s_addr(&v_full));
+                for (int t = 0; t < NA; t++) tma_load_3d(s_addr(sV + bf * K_BYTES + t * ATOM_K), &map_v, t * 64, h, b * a.Nk + j * BKEY, s_addr(&v_full[bf]));
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                          // ===== MMA issuer =====
             const uint32_t id1 = idesc(BKEY, 0), id2 = idesc(D, 1);
             auto qk = [&](int j) {                                // S[j & 1] = Q K_j^T
-                mbar_wait(s_addr(&k_full), j & 1);
+                const int bf = j % NB;
+                mbar_wait(s_addr(&k_full[bf]), (j / NB) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_s = tmem_base + (uint32_t)(j & 1) * BKEY;
 #pragma unroll
                 for (int s = 0; s < KS1; ++s) {
                     const uint64_t da = desc_kmajor(s_addr(sQ + (s >> 2) * ATOM_Q) + (s & 3) * 32);
-                    const uint64_t db = desc_kmajor(s_addr(sK + (s >> 2) * ATOM_K) + (s & 3) * 32);
+                    const uint64_t db = desc_kmajor(s_addr(sK + bf * K_BYTES + (s >> 2) * ATOM_K) + (s & 3) * 32);
                     umma_f16(tmem_s, da, db, id1, s != 0);
                 }
-                umma_commit(s_addr(&k_empty));
+                umma_commit(s_addr(&k_empty[bf]));
                 umma_commit(s_addr(&s_full[j & 1]));
             };
             mbar_wait(s_addr(&q_full), 0);
@@ -195,16 +200,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                 if (j + 1 < nblk) qk(j + 1);
                 // O_blk = P V once the softmax warps have written P (and have finished reading O_blk of block j-1: program order on their side)
                 mbar_wait(s_addr(&p_full), j & 1);
-                mbar_wait(s_addr(&v_full), j & 1);
+                const int bf = j % NB;
+                mbar_wait(s_addr(&v_full[bf]), (j / NB) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int s = 0; s < BKEY / 16; ++s) {
-                    const uint64_t da = desc_kmajor(s_addr(sP) + s * 32);
-                    const uint64_t db = desc_mnmajor(s_addr(sV) + s * 2048, ATOM_K);      // 16 keys further = two 8-row groups
+                    const uint64_t da = desc_kmajor(s_addr(sP + (j & 1) * P_BYTES) + s * 32);
+                    const uint64_t db = desc_mnmajor(s_addr(sV + bf * K_BYTES) + s * 2048, ATOM_K);      // 16 keys further = two 8-row groups
                     umma_f16(tmem_o, da, db, id2, (j | s) != 0);          // O accumulates in TMEM over all key blocks
                 }
-                umma_commit(s_addr(&v_empty));
-                umma_commit(s_addr(&o_full));
+                umma_commit(s_addr(&v_empty[bf]));
+                umma_commit(s_addr(&o_full[j & 1]));              // P V of blocks j, j+2, ... complete on barrier j & 1
             }
         }
     } else {                                                      // ===== softmax / epilogue: two threads per query row =====
@@ -237,8 +243,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             xmax[half][r] = mx;
             asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 softmax warps
             mx = fmaxf(mx, xmax[half ^ 1][r]);
-            // P V of block j-1 must have completed before P is overwritten (and before O may be rescaled); every phase is consumed in order
-            if (j > 0) { mbar_wait(s_addr(&o_full), (j - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+            // P is double-buffered: this block's buffer was last read by P V of block j-2, so the softmax of block j runs UNDER P V of block j-1
+            // (the exponentials never wait for the tensor core in the steady state).  Two barriers, one per buffer, so that no wait can fall two
+            // phases behind (parity waits only tell adjacent phases apart).
+            if (j > 1) { mbar_wait(s_addr(&o_full[j & 1]), ((j >> 1) - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
             // raise the reference maximum only when the block exceeds it by more than 2^8 (or it is still -inf)
             const bool raise = mx > m_ref && (m_ref == -INFINITY || (mx - m_ref) * a.scale_log2 > 8.f);
             float factor = 1.f;
@@ -248,6 +256,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                 l_run *= factor;
             }
             if (j > 0 && __any_sync(0xffffffffu, raise)) {        // warp-uniform: tcgen05.ld / .st are warp-wide
+                // O is about to be rescaled in place: P V of block j-1 must have finished accumulating into it (rare after the first blocks)
+                mbar_wait(s_addr(&o_full[(j - 1) & 1]), ((j - 1) >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int c0 = 0; c0 < DH; c0 += 16) {
                     uint32_t w[16];
@@ -260,7 +271,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * a.scale_log2;
             // pass 2: p = exp2(s * scale - m_ref * scale), fp16, into the swizzled K-major P tile (row r: 128 B, 16-byte chunk c at position c ^ (r & 7))
             float lsum = 0.f;
-            const uint32_t prow = s_addr(sP) + (uint32_t)r * 128;
+            const uint32_t prow = s_addr(sP + (j & 1) * P_BYTES) + (uint32_t)r * 128;
             auto pass2 = [&](const bool masked) {
 #pragma unroll
                 for (int c0 = 0; c0 < 32; c0 += 16) {
@@ -294,8 +305,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(s_addr(&p_full));
         }
-        // the last P V
-        mbar_wait(s_addr(&o_full), (nblk - 1) & 1);
+        // the last P V (the tensor core completes in order: every earlier one is done too)
+        mbar_wait(s_addr(&o_full[(nblk - 1) & 1]), ((nblk - 1) >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // the two halves of a row share the denominator
         if (half == 1) xsum[r] = l_run;
@@ -358,7 +369,8 @@ static cudaError_t launch(const er::AttnArgs& a, cudaStream_t stream) {
     g.out = a.out; g.o_bs = a.o_bs; g.ldo = a.ldo; g.B = a.B; g.H = a.H; g.Nq = a.Nq; g.Nk = a.Nk; g.causal = a.causal;
     g.scale_log2 = rsqrtf((float)D) * 1.4426950408889634f;
     constexpr int NA = (D + 63) / 64;
-    const size_t smem = (size_t)NA * ATOM_Q + 2 * (size_t)NA * ATOM_K + (size_t)BQ * 128 + 1024;
+    constexpr int NB = (D <= 64) ? 2 : 1;
+    const size_t smem = (size_t)NA * ATOM_Q + 2 * (size_t)NB * NA * ATOM_K + 2 * (size_t)BQ * 128 + 1024;
     cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((a.Nq + BQ - 1) / BQ, a.H, a.B);

@@ -281,12 +281,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const int nrow = min(32, g.M - rbase);
                     const int cc = col + lane;
                     if (cc < g.N) {
-#pragma unroll 4
-                        for (int rr = 0; rr < nrow; rr++) {
-                            const size_t grow = (size_t)(rbase + rr);
-                            const float o = g.res32[grow * g.ldr + cc] + sc[rr * 32 + (lane ^ rr)];
-                            g.out32[grow * g.ldo + cc] = o;
-                            if (g.out16) g.out16[grow * g.ldo + cc] = __float2half_rn(o);
+                        const float* rp = g.res32 + (size_t)rbase * g.ldr + cc;
+                        float* op = g.out32 + (size_t)rbase * g.ldo + cc;
+                        if (nrow == 32) {             // all 32 residual loads in flight before the first use (one memory latency per block, not 32)
+                            float r[32];
+#pragma unroll
+                            for (int rr = 0; rr < 32; rr++) r[rr] = rp[(size_t)rr * g.ldr];
+#pragma unroll
+                            for (int rr = 0; rr < 32; rr++) {
+                                r[rr] += sc[rr * 32 + (lane ^ rr)];
+                                op[(size_t)rr * g.ldo] = r[rr];
+                            }
+                            if (g.out16) {
+                                __half* hp = g.out16 + (size_t)rbase * g.ldo + cc;
+#pragma unroll
+                                for (int rr = 0; rr < 32; rr++) hp[(size_t)rr * g.ldo] = __float2half_rn(r[rr]);
+                            }
+                        } else {
+                            for (int rr = 0; rr < nrow; rr++) {
+                                const float o = rp[(size_t)rr * g.ldr] + sc[rr * 32 + (lane ^ rr)];
+                                op[(size_t)rr * g.ldo] = o;
+                                if (g.out16) g.out16[(size_t)(rbase + rr) * g.ldo + cc] = __float2half_rn(o);
+                            }
                         }
                     }
                     __syncwarp();

@@ -58,6 +58,19 @@ def test_dit_forward_matches_oracle_tiny_ragged():
     eng.debug_set('fuse', 1)
 
 
+def test_dit_forward_head_dim_96_generic_width():
+    """hidden 192 = 2 heads of 96: the D = 96 attention kernel (non-causal, ragged), the generic-width LayerNorm kernel."""
+    cfg = dict(hidden_dim=192, num_heads=2, latent_size=72, latent_dim=8, num_layers=2)
+    sd, x, c, t, orc, eng = _case(cfg, 5, 2, seed=2)
+    y = eng.forward(x, c, t).float()
+    ref = orc.forward(x, c, t)
+    d = (y - ref).abs()
+    print('d96: max', float(d.max()), 'mean', float(d.mean()))
+    assert float(ref.abs().mean()) > 0.1 and float(d.max()) <= 2e-2 and float(d.mean()) <= 1.5e-3
+    eng.debug_set('fuse', 0)
+    assert torch.equal(y, eng.forward(x, c, t).float())
+
+
 def test_dit_forward_matches_oracle_preset_shape():
     """the preset's layer shape (1024 wide, 16 heads, 2048 latents, 257 CLIP tokens), 3 layers, batch 2."""
     cfg = dict(hidden_dim=1024, num_heads=16, latent_size=2048, latent_dim=64, num_layers=3)
