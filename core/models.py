@@ -85,7 +85,9 @@ class LMM(nn.Module):
             e = Engine(self.opt, p0.device, max_new_tokens=cap, max_points=max(self.opt.point_num, 8192), max_tf_rows=max_tf_rows)
             self._engine_key = None
         if self._engine_key != key:
-            e.load_state_dict(self.state_dict())
+            # infer_dit.py builds LMM with cond_mode='point' and then flips the shared Options to 'point_latent' (infer_dit.py:38-55): the engine
+            # is then created without a point encoder and the module's point_encoder.* tensors are not its business
+            e.load_state_dict({k: v for k, v in self.state_dict().items() if e.cfg.has_point_encoder or not k.startswith('point_encoder.')})
             self._engine_key = key
         self._engine = e
         return e

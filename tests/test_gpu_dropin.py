@@ -72,3 +72,31 @@ def test_reference_infer_py_runs_unmodified(tmp_path):
         meshes, tokens = model.generate(cond, num_faces=1000, max_new_tokens=96, tokenizer=tokenizer, clean=True)
     np.testing.assert_array_equal(tokens[0] - 3, toks_file)
     assert len(meshes[0].faces) > 0
+
+
+INFER_DIT = os.path.join(REPO, 'oracle', '_ref', 'drop_in', 'infer_dit.py')
+
+
+@pytest.mark.skipif(not os.path.exists(INFER_DIT), reason='oracle/_ref/drop_in/infer_dit.py missing: run `make -C oracle refpy` in the build container')
+def test_reference_infer_dit_py_runs_unmodified(tmp_path):
+    """The image-conditioned script (infer_dit.py:34-144), unmodified, against this repository's core/ (LMM, MDiT, DiT) + meto/: RGBA image ->
+    CLIP tower (random ViT-H/14: no network) -> MDiT.run (100 guided DDIM steps on the device) -> LMM.generate(point_latent) -> .obj + tokens.
+    Small LMM / DiT dimensions through the script's own tyro flags; rembg / kiui image I/O are tests/stubs."""
+    from PIL import Image
+    rng = np.random.RandomState(0)
+    img = np.zeros((96, 96, 4), dtype=np.uint8)
+    img[24:72, 30:66, :3] = rng.randint(0, 255, (48, 36, 3))
+    img[24:72, 30:66, 3] = 255
+    path = str(tmp_path / 'blob.png')
+    Image.fromarray(img, 'RGBA').save(path)
+    ws = str(tmp_path / 'ws')
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([REPO, os.path.join(REPO, 'tests', 'stubs')]))
+    cmd = [sys.executable, INFER_DIT, 'DiT', '--test_path', path, '--workspace', ws, '--test_num_face', '1000', '--test_max_seq_length', '64',
+           '--test_repeat', '1', '--dit_hidden_dim', '128', '--dit_num_heads', '2', '--dit_num_layers', '2'] + DIMS
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=str(tmp_path))
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    obj, npy = os.path.join(ws, 'blob_0_1000f.obj'), os.path.join(ws, 'blob_0_1000f_tokens.npy')
+    assert os.path.exists(obj) and os.path.exists(npy) and os.path.exists(os.path.join(ws, 'blob.jpg')), os.listdir(ws)
+    toks = np.load(npy)
+    assert len(toks) == 64 and toks[0] == 2                        # BOM (5) - 3; the random LMM never emits EOS within 64 tokens... or stops early
+    assert open(obj).read(2) == 'v '
