@@ -404,6 +404,8 @@ def run_dit(args):
                                      'sample': f"{rg['impl']} DiT module, .half() + autocast(fp16), denoiser batch {rg['batch']}, forward only (no scheduler / guidance)"}
         else:
             line['reference_gpu'] = rg
+    if args.dit_pipeline and not args.tiny:
+        line['pipeline'] = dit_pipeline_leg(dev)
     if not args.no_cpu_baseline and not args.tiny:
         rc = ref_dit_leg('cpu', 1, 1, 1)
         if rc and 's_per_forward' in rc:
@@ -412,6 +414,43 @@ def run_dit(args):
         else:
             line['cpu_baseline'] = rc
     print(json.dumps(line), flush=True)
+
+
+def dit_pipeline_leg(dev):
+    """BASELINE configs[4] end to end for ONE image at the preset sizes, through the public classes exactly as infer_dit.py:104-113 drives them:
+    MDiT.run(image) [CLIP ViT-H/14 tower (library model, random weights) -> adaptor -> 100 guided DDIM steps] -> LMM.generate(latents,
+    num_faces=4000, 16 000 new tokens, greedy) -> detokenise + clean.  Wall-clock seconds per stage (host-timed, synchronised)."""
+    from dataclasses import replace
+    from core.models import LMM
+    from core.models_dit import MDiT
+    from core.options import config_defaults
+    from core.utils import get_tokenizer
+    from edgerunner_b200 import synth
+    opt = replace(config_defaults['DiT'], generate_mode='greedy')
+    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
+    with torch.device('meta'):
+        lmm = LMM(opt)
+    lmm.load_state_dict(sd, strict=True, assign=True)
+    del sd
+    lmm = lmm.half().eval().to(dev)
+    opt.cond_mode = 'point_latent'                                   # infer_dit.py:55
+    torch.manual_seed(0)
+    mdit = MDiT(opt)
+    mdit.load_state_dict(synth.synth_dit_state_dict(opt.dit_hidden_dim, opt.dit_num_heads, opt.point_latent_size, opt.point_latent_dim, opt.dit_num_layers,
+                                                    cond_dim=1280, seed=0), strict=False)
+    mdit = mdit.half().eval().to(dev)
+    tok, _ = get_tokenizer(opt)
+    img = torch.rand(1, 3, 512, 512, generator=torch.Generator().manual_seed(3)).to(dev)
+    out = {}
+    for rep in range(2):                                             # first pass warms up (engine creation, graph capture)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        lat = mdit.run(img)
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        meshes, tokens = lmm.generate(lat, num_faces=4000, max_new_tokens=16000, tokenizer=tok, clean=True)
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        out = {'image_to_latents_s': t1 - t0, 'latents_to_mesh_s': t2 - t1, 'total_s': t2 - t0, 'new_tokens': int(len(tokens[0])), 'faces': int(len(meshes[0].faces)),
+               'stages': 'MDiT.run (CLIP ViT-H/14 + adaptor + 100 guided DDIM steps, 1 image) | LMM.generate(point_latent, 4000 faces, 16000 tokens, greedy) + detokenise + clean'}
+    return out
 
 
 def run_dit_reference_arm(args):
@@ -446,6 +485,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-reference-gpu', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3, help='timed LMM.generate calls of the e2e leg (bounded: each is a full 16k request)')
+    ap.add_argument('--dit-pipeline', action='store_true', help='--workload dit: also time one image end to end (MDiT.run -> LMM.generate) at the preset sizes')
     ap.add_argument('--workload', default='decode', choices=['decode', 'tf', 'dit'],
                     help="decode = BASELINE configs[1] (the metric); tf = configs[3]: teacher-forced forward seq 8192 batch 4/GPU, loss all-reduced over NCCL")
     args = ap.parse_args()
