@@ -2,9 +2,9 @@
 ``attention(q, k, v, mask_q=None, mask_kv=None, dropout=0, causal=False)`` with ``[B, N, H, D]`` tensors.
 
 fp16 CUDA inputs run on the sm_100a tcgen05 flash kernel of ``edgerunner_b200`` (head_dim 64 or 96) instead of flash-attn.
-Padding masks (the varlen branch, reference ``:65-93``: unpad -> ``flash_attn_varlen_func`` -> ``pad_input``) are supported when they
-are RIGHT-padded, which is what ``collate_fn`` produces: sample b then attends over its first ``len_kv[b]`` keys with its first
-``len_q[b]`` queries, and the padded query rows come back as zeros (``pad_input``).  Masks with holes raise ``NotImplementedError``.
+Padding masks (the varlen branch, reference ``:65-93``: unpad -> ``flash_attn_varlen_func`` -> ``pad_input``): sample b attends over its kept
+keys with its kept queries and the masked query rows come back as zeros (``pad_input``).  RIGHT-padded masks — what ``collate_fn`` produces —
+run in place on the prefix; masks with holes are gathered / scattered per sample like ``unpad_input`` / ``pad_input`` do.
 There is no eager / CPU fallback: non-CUDA inputs raise.
 """
 
@@ -36,9 +36,7 @@ def attention(q, k, v, mask_q=None, mask_kv=None, dropout=0, causal=False):
     # varlen branch for right-padded masks (reference :65-93: a missing mask counts as all-True)
     mq = torch.ones(B, N, dtype=torch.bool, device=q.device) if mask_q is None else mask_q.bool()
     mk = torch.ones(B, M, dtype=torch.bool, device=q.device) if mask_kv is None else mask_kv.bool()
-    for m in (mq, mk):
-        if bool((m[:, 1:] & ~m[:, :-1]).any()):
-            raise NotImplementedError('only right-padded attention masks are supported (collate_fn pads at the end)')
+    right_padded = not any(bool((m[:, 1:] & ~m[:, :-1]).any()) for m in (mq, mk))
     len_q, len_k = mq.sum(1).tolist(), mk.sum(1).tolist()
     out = torch.zeros_like(q16)                                   # pad_input: masked query rows are zero
     row = H * D * 2                                              # bytes per (batch, position) row
@@ -48,6 +46,14 @@ def attention(q, k, v, mask_q=None, mask_kv=None, dropout=0, causal=False):
             continue
         if causal and nq > 1 and nq != nk:
             raise NotImplementedError('causal varlen attention needs equal query / key lengths per sample')
-        _lib.check(lib.er_attention_bnhd(q16.data_ptr() + b * N * row, k16.data_ptr() + b * M * row, v16.data_ptr() + b * M * row,
-                                         out.data_ptr() + b * N * row, 1, nq, nk, H, D, 1 if (causal and nq > 1) else 0, stream))
+        c = 1 if (causal and nq > 1) else 0
+        if right_padded:                                         # collate_fn's case: the kept rows are a prefix, no copies
+            _lib.check(lib.er_attention_bnhd(q16.data_ptr() + b * N * row, k16.data_ptr() + b * M * row, v16.data_ptr() + b * M * row,
+                                             out.data_ptr() + b * N * row, 1, nq, nk, H, D, c, stream))
+        else:                                                    # masks with holes: unpad_input (gather) -> attention -> pad_input (scatter)
+            iq, ik = mq[b].nonzero().squeeze(1), mk[b].nonzero().squeeze(1)
+            qb, kb, vb = q16[b].index_select(0, iq), k16[b].index_select(0, ik), v16[b].index_select(0, ik)
+            ob = torch.empty_like(qb)
+            _lib.check(lib.er_attention_bnhd(qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), ob.data_ptr(), 1, nq, nk, H, D, c, stream))
+            out[b].index_copy_(0, iq, ob)
     return out.to(in_dtype)

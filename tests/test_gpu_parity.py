@@ -471,7 +471,7 @@ def test_eos_stops_the_persistent_kernel(variant):
 
 def test_attention_seam_right_padded_masks():
     """attention(q, k, v, mask_q, mask_kv, causal): the varlen branch (reference attention.py:65-93) for right-padded masks against a masked
-    fp32 torch softmax; padded query rows are zero (pad_input); masks with holes raise."""
+    fp32 torch softmax; padded query rows are zero (pad_input); masks with holes go through the gather / scatter path."""
     from core.transformer.attention import attention
     torch.manual_seed(1)
     for (B, N, M, H, D, causal) in [(3, 150, 150, 2, 96, True), (2, 70, 200, 2, 64, False)]:
@@ -490,6 +490,22 @@ def test_attention_seam_right_padded_masks():
         ref = ref * mq[:, :, None, None]
         assert (out.float() - ref).abs().max().item() < 4e-3
         assert (out[~mq] == 0).all()
-    holed = mq.clone(); holed[0, 3] = False
-    with pytest.raises(NotImplementedError):
-        attention(q, k, v, mask_q=holed, mask_kv=mk, causal=False)
+    # masks with holes (unpad_input / pad_input semantics): non-causal with independent masks, causal self-attention with one shared mask
+    g = torch.Generator().manual_seed(5)
+    for causal in (False, True):
+        B, N, H, D = 2, 130, 2, 64
+        M = N if causal else 90
+        q = torch.randn(B, N, H, D, device='cuda', dtype=torch.float16)
+        k = torch.randn(B, M, H, D, device='cuda', dtype=torch.float16)
+        v = torch.randn(B, M, H, D, device='cuda', dtype=torch.float16)
+        mq = (torch.rand(B, N, generator=g) > 0.3).cuda(); mq[:, 0] = True
+        mk = mq if causal else (torch.rand(B, M, generator=g) > 0.4).cuda()
+        mk[:, 0] = True
+        out = attention(q, k, v, mask_q=mq, mask_kv=mk, causal=causal)
+        qf, kf, vf = (t.float().transpose(1, 2) for t in (q, k, v))
+        w = (qf @ kf.transpose(-1, -2) / D ** 0.5).masked_fill(~mk[:, None, None, :], float('-inf'))
+        if causal:      # causal over the COMPACTED sequences == causal in the original order when q and k share the mask
+            w = w + torch.triu(torch.full((N, M), float('-inf'), device='cuda'), diagonal=1)
+        ref = (torch.softmax(w, -1) @ vf).transpose(1, 2) * mq[:, :, None, None]
+        assert (out.float() - ref).abs().max().item() < 4e-3
+        assert (out[~mq] == 0).all()
