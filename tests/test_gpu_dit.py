@@ -184,3 +184,28 @@ def test_mdit_run_feeds_lmm_generate():
     tok, _ = get_tokenizer(lopt)
     meshes, tokens = lmm.generate(lat, num_faces=1000, max_new_tokens=64, tokenizer=tok, clean=True)
     assert len(tokens) == 1 and len(tokens[0]) == 64 and len(meshes) == 1
+
+
+def test_dit_abi_error_behaviour():
+    """strict weight loading and state checks of the er_dit_* entry points (the reference raises on shape mismatches in load_state_dict)."""
+    from edgerunner_b200 import _lib
+    from edgerunner_b200.dit_engine import DiTEngine
+    from dit_oracle import synth_dit_state
+    cfg = dict(hidden_dim=128, num_heads=2, latent_size=40, latent_dim=16, num_layers=1)
+    sd = synth_dit_state(**cfg, cond_dim=32, seed=0)
+    with pytest.raises(_lib.ErError):                                   # head_dim 32 is not a kernel shape
+        DiTEngine(torch.device('cuda:0'), 64, 2, 1, 40, 16, 9, 32)
+    eng = DiTEngine(torch.device('cuda:0'), 128, 2, 1, 40, 16, 9, 32)
+    x, c, t = torch.zeros(1, 40, 16).cuda(), torch.zeros(1, 9, 128).cuda(), torch.zeros(1).cuda()
+    with pytest.raises(_lib.ErError):                                   # not finalized
+        eng.forward(x, c, t)
+    with pytest.raises(_lib.ErError):                                   # a tensor of the schema is missing
+        eng.load_state_dict({k: v for k, v in sd.items() if k != 'dit.proj_out.bias'})
+    with pytest.raises(_lib.ErError):                                   # wrong element count
+        eng.load_state_dict({**sd, 'dit.proj_in.bias': torch.zeros(7)})
+    with pytest.raises(_lib.ErError):                                   # unknown dit.* key
+        eng.load_state_dict({**sd, 'dit.layers.0.attn3.weight': torch.zeros(4)})
+    eng.load_state_dict({**sd, 'image_encoder.foo': torch.zeros(3), 'point_encoder.bar': torch.zeros(3)})     # not the engine's keys: ignored
+    assert torch.isfinite(eng.forward(x, c, t).float()).all()
+    with pytest.raises(_lib.ErError):
+        eng.debug_set('no_such_switch', 1)
