@@ -489,6 +489,8 @@ def main():
     ap.add_argument('--workload', default='decode', choices=['decode', 'tf', 'dit'],
                     help="decode = BASELINE configs[1] (the metric); tf = configs[3]: teacher-forced forward seq 8192 batch 4/GPU, loss all-reduced over NCCL")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: NCCL's own log lines (the box exports NCCL_DEBUG=VERSION) go to stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
     if args.impl == 'reference':
         (run_dit_reference_arm if args.workload == 'dit' else run_reference_arm)(args)
