@@ -193,7 +193,7 @@ def run_reference_arm(args):
     cb = cpu_baseline_leg(args, opt, steps=args.steps, warmup=args.warmup)
     v = cb['value']
     ms = cb.get('sample_s_per_step', 0.0) * 1e3
-    print(json.dumps({
+    emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': {'workload': wl, 'tokens_per_step_per_gpu': T, 'prefix_rows': opt.num_cond_tokens + 1,
@@ -270,7 +270,7 @@ def run_teacher_forced(args):
     peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
     peak = float(json.load(open(peaks_path)).get('bf16_tflops_sustained', 1400.0)) if os.path.exists(peaks_path) else 1400.0
     tf = flops / (ms_step * 1e-3) / 1e12
-    print(json.dumps({
+    emit(json.dumps({
         'metric': 'teacher-forced tokens/sec, ArAE forward seq_len 8192 batch 4/GPU (BASELINE configs[3], forward only)', 'value': world * B * T / (ms_step * 1e-3),
         'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic', 'loss': loss,
@@ -413,7 +413,7 @@ def run_dit(args):
                                     'sample': f"1 denoiser forward of 1 image (batch 2), fp32 torch CPU ops, scaled x{R} to the 4-image step"}
         else:
             line['cpu_baseline'] = rc
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line), flush=True)
 
 
 def dit_pipeline_leg(dev):
@@ -461,15 +461,26 @@ def run_dit_reference_arm(args):
     R = 4
     rc = ref_dit_leg('cpu', 1, max(args.steps, 1), min(args.warmup, 1), timeout=1500)
     if not rc or 's_per_forward' not in rc:
-        print(json.dumps({'impl': 'reference', 'unavailable': str(rc)[:200]}), flush=True)
+        emit(json.dumps({'impl': 'reference', 'unavailable': str(rc)[:200]}), flush=True)
         return
     v = 1.0 / (rc['s_per_forward'] * R)
     cb = {'value': v, 'unit': 'denoiser steps/s', 'cores': rc.get('cores'), 'kind': rc.get('impl'),
           'sample': f"{args.steps} x one denoiser forward of 1 image (batch 2), fp32 torch CPU ops, scaled x{R} to the 4-image step"}
-    print(json.dumps({'impl': 'reference', 'metric': DIT_METRIC, 'value': v, 'unit': 'denoiser steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+    emit(json.dumps({'impl': 'reference', 'metric': DIT_METRIC, 'value': v, 'unit': 'denoiser steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
                       'warmup': args.warmup, 'ms_per_step': rc['s_per_forward'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                       'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': 'reference DiT module forward, CPU', 'sample': cb['sample']},
                       'cpu_baseline': cb, 'e2e': {'value': v, 'unit': 'denoiser steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
+
+
+_STDOUT_FD = None
+
+
+def emit(line, flush=True):
+    """the bench line, on the process's ORIGINAL stdout (see main())"""
+    if _STDOUT_FD is None:
+        print(line, flush=True)
+    else:
+        os.write(_STDOUT_FD, (line + '\n').encode())
 
 
 def main():
@@ -489,8 +500,11 @@ def main():
     ap.add_argument('--workload', default='decode', choices=['decode', 'tf', 'dit'],
                     help="decode = BASELINE configs[1] (the metric); tf = configs[3]: teacher-forced forward seq 8192 batch 4/GPU, loss all-reduced over NCCL")
     args = ap.parse_args()
-    # stdout carries exactly ONE JSON line: NCCL's own log lines (the box exports NCCL_DEBUG=VERSION) go to stderr
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    # stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner under torchrun) is sent to stderr instead
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == 'reference':
         (run_dit_reference_arm if args.workload == 'dit' else run_reference_arm)(args)
@@ -658,7 +672,7 @@ def main():
                    'weights': 'seeded synthetic, fp16 (edgerunner_b200.synth)'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'reference_gpu': ref_gpu, 'comm': comm,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line), flush=True)
 
 
 if __name__ == '__main__':
