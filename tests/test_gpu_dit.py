@@ -171,6 +171,10 @@ def test_mdit_run_feeds_lmm_generate():
     ts = mdit.scheduler.timesteps
     ref = orc.sample_loop(cond, noise, ts.tolist(), mdit.scheduler.step_coefficients(ts), 4.0, 'v_prediction')
     assert float((lat - ref).abs().max()) <= 1.5e-2 * max(1.0, float(ref.abs().mean()))
+    # num_repeat: the condition is repeated, every copy gets its own noise
+    torch.manual_seed(9)
+    rep = mdit.run(img, num_inference_steps=3, guidance_scale=4.0, num_repeat=2)
+    assert rep.shape == (2, opt.point_latent_size, opt.point_latent_dim) and not torch.equal(rep[0], rep[1]) and torch.isfinite(rep).all()
     # strength path of run()
     torch.manual_seed(8)
     lat2 = mdit.run(img, num_inference_steps=6, guidance_scale=4.0, latents=lat, strength=0.5)
