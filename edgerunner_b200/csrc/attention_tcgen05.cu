@@ -13,8 +13,8 @@
 //               TMEM columns 64..64+D; tcgen05.commit publishes S / O_blk and frees the K / V buffers for the next copies
 //   warps 2..9  softmax: TWO threads per query row (TMEM lane): warps 2..5 take keys 0..31 and output dims [0, D/2), warps 6..9 keys 32..63
 //               and dims [D/2, D) (a warp may touch TMEM lanes 32 (warp % 4) .. +31 only, any columns).  Pass 1 reads S for the row maximum
-//               (the two halves meet through shared memory and one named barrier), pass 2 re-reads it (TMEM reads are cheap, registers
-//               are not), exponentiates, rounds to fp16 and stores P in the K-major swizzled layout the MMA wants.  O ACCUMULATES IN TMEM
+//               (the two halves meet through shared memory and one named barrier), pass 2 exponentiates the 32 scores still held in
+//               registers (96 registers per thread: two CTAs per SM still fit; re-reading TMEM cost a round trip per block), rounds to fp16 and stores P in the K-major swizzled layout the MMA wants.  O ACCUMULATES IN TMEM
 //               across key blocks (the MMA's accumulate flag); the reference maximum of a row is only raised when the block maximum exceeds
 //               it by more than 2^8 in the exponent (P stays <= 256, exact in the final O / l), and only then are the row's O (tcgen05.ld /
 //               .st) and l rescaled — rare after the first blocks.  K(j+1) streams in under softmax(j) / P V(j), V(j+1) under Q K^T(j+1).
@@ -230,15 +230,19 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             // pass 1: maximum over this thread's 32 keys, then over the row (other half through shared memory)
             float mx = -INFINITY;
             tmem_ld32(tmem_s + lane_sel, v);
-            if (edge) {
+            {   // four independent chains: a 32-long dependent FMNMX chain costs ~150 cycles per block per warp
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (edge) {
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const bool dead = (a.causal && k0 + i > qi) || k0 + i >= a.Nk;
-                    mx = fmaxf(mx, dead ? -INFINITY : __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; i++) {
+                        const bool dead = (a.causal && k0 + i > qi) || k0 + i >= a.Nk;
+                        m4[i & 3] = fmaxf(m4[i & 3], dead ? -INFINITY : __uint_as_float(v[i]));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(v[i]));
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             }
             xmax[half][r] = mx;
             asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 softmax warps
@@ -272,20 +276,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             // pass 2: p = exp2(s * scale - m_ref * scale), fp16, into the swizzled K-major P tile (row r: 128 B, 16-byte chunk c at position c ^ (r & 7))
             float lsum = 0.f;
             const uint32_t prow = s_addr(sP + (j & 1) * P_BYTES) + (uint32_t)r * 128;
+            // the thread's 32 scores are still in registers from pass 1 (72 -> ~100 registers would still allow two CTAs per SM)
             auto pass2 = [&](const bool masked) {
+                float ls[4] = {0.f, 0.f, 0.f, 0.f};               // independent partial sums (a single accumulator is a 32-long FADD chain)
 #pragma unroll
                 for (int c0 = 0; c0 < 32; c0 += 16) {
-                    tmem_ld16(tmem_s + lane_sel + c0, v);
                     uint32_t ph[8];
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
-                        float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+                        float s0 = __uint_as_float(v[c0 + i]), s1 = __uint_as_float(v[c0 + i + 1]);
                         if (masked) {
                             if ((a.causal && k0 + c0 + i > qi) || k0 + c0 + i >= a.Nk) s0 = -INFINITY;
                             if ((a.causal && k0 + c0 + i + 1 > qi) || k0 + c0 + i + 1 >= a.Nk) s1 = -INFINITY;
                         }
                         const float p0 = fast_exp2(s0 * a.scale_log2 - msc), p1 = fast_exp2(s1 * a.scale_log2 - msc);
-                        lsum += p0 + p1;
+                        ls[(i >> 1) & 3] += p0 + p1;
                         const __half2 hh = __floats2half2_rn(p0, p1);
                         ph[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
                     }
@@ -296,6 +301,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                                      "r"(ph[4 * c + 2]), "r"(ph[4 * c + 3]) : "memory");
                     }
                 }
+                lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
             };
             if (edge) pass2(true); else pass2(false);
             l_run += lsum;
