@@ -98,5 +98,5 @@ def test_reference_infer_dit_py_runs_unmodified(tmp_path):
     obj, npy = os.path.join(ws, 'blob_0_1000f.obj'), os.path.join(ws, 'blob_0_1000f_tokens.npy')
     assert os.path.exists(obj) and os.path.exists(npy) and os.path.exists(os.path.join(ws, 'blob.jpg')), os.listdir(ws)
     toks = np.load(npy)
-    assert len(toks) == 64 and toks[0] == 2                        # BOM (5) - 3; the random LMM never emits EOS within 64 tokens... or stops early
+    assert 1 <= len(toks) <= 64 and toks[0] == 2                   # BOM (5) - 3 first; a randomly initialised LMM may emit EOS before 64 tokens
     assert open(obj).read(2) == 'v '
