@@ -49,6 +49,9 @@ def test_ddim_scheduler_restatement():
     assert np.array_equal(ts.numpy(), ts2) and torch.equal(coef, coef2)
     ac = s.alphas_cumprod
     assert abs(float(ac[0]) - (1 - 0.00085)) < 1e-6 and abs(float(1 - ac[999] / ac[998]) - 0.012) < 1e-5                # scaled-linear end points
+    # known answer: this is the Stable Diffusion v1 schedule (scaled_linear 0.00085 .. 0.012, 1000 steps); its final alpha-bar is the widely
+    # published 0.0047 (terminal SNR 0.0047 / 0.9953), its first 0.99915
+    assert abs(float(ac[999]) - 0.004660) < 2e-6 and abs(float(ac[0]) - 0.99915) < 1e-6
     np.testing.assert_allclose(coef[:, 0] ** 2 + coef[:, 1] ** 2, 1.0, atol=1e-6)
     np.testing.assert_allclose(coef[:-1, 2], coef[1:, 0], atol=0)                   # alpha_prev of step i is alpha_t of step i + 1
     assert float(coef[-1, 2]) == float(ac[0] ** 0.5)                                # set_alpha_to_one=False: the last step lands on alphas_cumprod[0]
