@@ -241,8 +241,30 @@ def run_teacher_forced(args):
             import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
+    # SURVEY §8e / BASELINE configs[3] "grad all-reduce": the flattened fp32 gradient buffer of the model's parameter count, all-reduced over
+    # NCCL in 4 reverse-order slices per step, launched before the forward so that it overlaps it.  SYNTHETIC gradients: no backward exists.
+    fg = None
+    comm_ms = None
+    if args.grad_allreduce and world > 1:
+        from edgerunner_b200.dist import FlatGradAllReduce
+        n_params = sum(p.numel() for p in model.parameters())
+        fg = FlatGradAllReduce(n_params, dev, n_slices=4)
+        for _ in range(2):
+            fg.launch().wait()
+        barrier()
+        ce = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ce[0].record()
+        for _ in range(3):
+            fg.launch().wait()
+        ce[1].record()
+        barrier()
+        comm_ms = ce[0].elapsed_time(ce[1]) / 3
     for _ in range(max(args.warmup, 1)):
+        if fg:
+            fg.launch()
         out = model(data)
+        if fg:
+            fg.wait()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -251,16 +273,21 @@ def run_teacher_forced(args):
     l0 = model._engine.kernel_launches()
     ev[0].record()
     for _ in range(args.steps):
+        if fg:
+            fg.launch()
         out = model(data)
         loss = float(out['loss'])                          # D2H of the step's result
+        if fg:
+            fg.wait()
     ev[1].record()
     barrier()
     ms = ev[0].elapsed_time(ev[1])
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, comm_ms or 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms = float(t[0].item())
+        comm_ms = float(t[1].item()) if fg else None
         dist.destroy_process_group()
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
@@ -282,6 +309,11 @@ def run_teacher_forced(args):
                      'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)'},
         'e2e': {'value': world * B * T / (ms_step * 1e-3), 'unit': 'tokens/s', 'h2d_bytes_per_step': int(tokens.numel() * 4 + data['labels'].numel() * 8),
                 'd2h_bytes_per_step': 4, 'note': 'LMM.forward(data): tokens / labels uploaded and the loss read back every step inside the timed region'},
+        'comm': None if not fg else {
+            'grad_allreduce': 'flattened fp32 buffer of %d elements (%.2f GB), NCCL all-reduce in 4 reverse-order slices per step, overlapped with the forward; '
+                              'SYNTHETIC gradients (no backward pass exists)' % (fg.buf.numel(), fg.buf.numel() * 4 / 1e9),
+            'standalone_ms': comm_ms, 'busbw_GBps': (fg.buf.numel() * 4 * 2 * (world - 1) / world) / (comm_ms * 1e-3) / 1e9 if comm_ms else None,
+            'ms_per_step_includes_it': True},
     }), flush=True)
 
 
@@ -496,6 +528,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-reference-gpu', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3, help='timed LMM.generate calls of the e2e leg (bounded: each is a full 16k request)')
+    ap.add_argument('--grad-allreduce', action='store_true', help='--workload tf under torchrun: also all-reduce a flattened synthetic gradient buffer every step (SURVEY 8e)')
     ap.add_argument('--dit-pipeline', action='store_true', help='--workload dit: also time one image end to end (MDiT.run -> LMM.generate) at the preset sizes')
     ap.add_argument('--workload', default='decode', choices=['decode', 'tf', 'dit'],
                     help="decode = BASELINE configs[1] (the metric); tf = configs[3]: teacher-forced forward seq 8192 batch 4/GPU, loss all-reduced over NCCL")

@@ -6,6 +6,10 @@
 * The teacher-forced forward shards by batch (data parallel).  Its one collective is an all-reduce of the
   (sum of per-token losses, token count, KL sum) triple, which reproduces the single-process mean exactly
   (``F.cross_entropy(..., ignore_index=-100)`` is a mean over the non-ignored tokens of the WHOLE batch).
+* ``FlatGradAllReduce``: the collective a data-parallel TRAINING step needs (one flattened gradient buffer,
+  sum then / world, in a few slices in reverse-layer order so that it can start while earlier layers are still in
+  backward).  No backward pass exists in this repository: the class is the host-side plumbing, exercised by
+  ``bench.py --workload tf --grad-allreduce`` on a synthetic buffer of the model's parameter count and by the gloo test.
 
 Works with backend 'nccl' on the GPU box and 'gloo' on CPU (tests/test_dist_cpu.py, world_size 2).
 """
@@ -70,3 +74,43 @@ def dp_reduce_losses(ce_sum: torch.Tensor, n_tokens: torch.Tensor, kl_sum: torch
     loss_kl = buf[2]
     w = float(np.float32(kl_weight))          # the C ABI takes kl_weight as fp32: same constant as the single-process kernel
     return (loss_ce + w * loss_kl).float(), loss_ce.float(), loss_kl.float()
+
+
+class FlatGradAllReduce:
+    """One flat fp32 buffer for all gradients (what DDP / accelerate build for the reference, main.py:133-142), all-reduced in ``n_slices``
+    contiguous slices from the END of the buffer to its start (parameters are registered input-to-output, backward produces them
+    output-to-input), asynchronously; ``wait()`` completes them and divides by the world size."""
+
+    def __init__(self, numel: int, device, n_slices: int = 4, dtype=torch.float32):
+        self.buf = torch.zeros(numel, dtype=dtype, device=device)
+        self.n_slices = max(1, int(n_slices))
+        self.handles = []
+        step = -(-numel // self.n_slices)
+        self.bounds = [(max(0, numel - (i + 1) * step), numel - i * step) for i in range(self.n_slices) if numel - i * step > 0]
+
+    def views(self, shapes):
+        """Per-parameter views into the flat buffer, in registration order (what a backward pass would write its gradients into)."""
+        out, off = [], 0
+        for shp in shapes:
+            n = int(np.prod(shp)) if len(shp) else 1
+            out.append(self.buf[off:off + n].view(shp))
+            off += n
+        assert off <= self.buf.numel()
+        return out
+
+    def launch(self):
+        rank, ws = world()
+        self.handles = []
+        if ws > 1:
+            for lo, hi in self.bounds:
+                self.handles.append(dist.all_reduce(self.buf[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        return self
+
+    def wait(self):
+        rank, ws = world()
+        for h in self.handles:
+            h.wait()
+        self.handles = []
+        if ws > 1:
+            self.buf.div_(ws)
+        return self.buf

@@ -31,6 +31,14 @@ def _worker(rank, ws, port, q):
     kl_all = rng.rand(ws).astype(np.float32)
     shard = ce_all[rank::ws]
     loss, lce, lkl = erd.dp_reduce_losses(torch.tensor(shard.sum()), torch.tensor(float(len(shard))), torch.tensor(kl_all[rank]), 1e-3)
+    # flattened gradient buffer: sliced, reverse-order, averaged
+    fg = erd.FlatGradAllReduce(1003, 'cpu', n_slices=4)
+    va, vb = fg.views([(10, 50), (503,)])
+    va.fill_(float(rank + 1)); vb.copy_(torch.arange(503, dtype=torch.float32) * (rank + 1))
+    flat = fg.launch().wait()
+    ok_flat = bool(torch.all(flat[:500] == 1.5)) and bool(torch.allclose(flat[500:], torch.arange(503, dtype=torch.float32) * 1.5)) \
+        and fg.bounds[0][1] == 1003 and fg.bounds[-1][0] == 0 and all(a[0] == b[1] for a, b in zip(fg.bounds[:-1], fg.bounds[1:]))
+    assert ok_flat
     q.put((rank, mine, None if allt is None else [a.tolist() for a in allt], slow, float(loss), float(lce), float(lkl),
            float(ce_all.mean()), float(kl_all.sum())))
     dist.destroy_process_group()
