@@ -182,6 +182,16 @@ int er_dit_debug_set(er_dit* e, const char* key, int64_t value);   /* "graph": 0
                                                                       residuals as separate kernels instead of GEMM epilogues; "uncond_shortcut": 0 = run the
                                                                       cross-attention of the zero-condition half in full (all A/B timing, bit-identical) */
 
+/* ---- Optimizer half of the training step (no backward pass exists here) ---------------------------------
+ * main.py:133 `torch.optim.AdamW(model.parameters(), lr, weight_decay=0.01, betas=(0.9, 0.95))` and main.py:175-177
+ * `accelerator.clip_grad_norm_(model.parameters(), opt.gradient_clip)` over flat fp32 buffers (16-byte aligned, n elements).
+ * er_grad_norm_clip: *norm_out_dev = ||g||_2, *scale_out_dev = min(1, max_norm / (norm + 1e-6)) (torch.nn.utils.clip_grad_norm_); scratch_dev:
+ * 592 doubles.  er_adamw_step: one AdamW update, `step` counted from 1; grad_scale_dev (optional) = the clipping coefficient, applied to the
+ * gradient as it is read; param16_out_dev (optional) receives the fp16 copy of the updated parameters (what the forward kernels consume). */
+int er_grad_norm_clip(const float* grad_dev, int64_t n, float max_norm, double* scratch_dev, float* norm_out_dev, float* scale_out_dev, void* stream);
+int er_adamw_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, void* param16_out_dev, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* grad_scale_dev, void* stream);
+
 /* meto tokenizer backends of the reference's pybind module `_meto` (meto/src/bindings.cpp:11-28) */
 #define ER_METO_LR_ABSCO 0   /* Engine_LR_ABSCO: absolute coordinates, vocabulary bins + 3 (the ArAE / DiT presets) */
 #define ER_METO_LR 1         /* Engine_LR: parallelogram residuals, vocabulary 2 * bins + 3 (Options.meto_backend = 'LR') */

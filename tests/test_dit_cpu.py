@@ -95,3 +95,14 @@ def test_mdit_schema_and_refusals():
         m.forward({})
     with pytest.raises(RuntimeError):
         m.run(torch.rand(1, 3, 32, 32), num_inference_steps=2)
+
+
+def test_cosine_lr_lambda_matches_main_py():
+    """main.py:136-141: linear warm-up to 1 over warmup_ratio of the run, cosine decay to min_ratio = 0.1 at the end."""
+    from edgerunner_b200.optim import cosine_lr_lambda as f
+    T = 1000
+    assert f(0, T, 0.01) == 0.0 and abs(f(5, T, 0.01) - 0.5) < 1e-12 and abs(f(10, T, 0.01) - 1.0) < 1e-12
+    assert abs(f(T, T, 0.01) - 0.1) < 1e-12 and abs(f(505, T, 0.01) - 0.55) < 1e-9
+    assert f(0, T, 0) == 1.0                                           # ArAE preset: warmup_ratio = 0
+    vals = [f(s, T, 0.01) for s in range(10, T + 1)]
+    assert all(a >= b for a, b in zip(vals, vals[1:]))
