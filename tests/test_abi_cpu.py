@@ -76,3 +76,29 @@ def test_decode_partition_invariants(tmp_path):
     subprocess.check_call(['g++', '-std=c++17', '-O2', '-o', exe, os.path.join(REPO, 'tests', 'partition_check.cpp')])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.startswith('ok '), out.stdout[-500:]
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: include/edgerunner_b200.h compiles as strict C99 (no C++ / torch types) and a C program links against the
+    shared library and calls two entry points that need no GPU."""
+    import shutil
+    import subprocess
+    from edgerunner_b200 import _lib
+    if shutil.which('gcc') is None or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip('gcc or the built library is missing')
+    src = tmp_path / 'abi.c'
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "edgerunner_b200.h"\n'
+                   'int main(void) {\n'
+                   '    er_dit_config c; memset(&c, 0, sizeof c);\n'
+                   '    er_dit* e = 0;\n'
+                   '    int rc = er_dit_create(&c, &e);            /* bad dimensions: refused before any CUDA call */\n'
+                   '    printf("%d %d %s\\n", er_version(), rc, er_last_error());\n'
+                   '    return (er_version() > 0 && rc == ER_ERR_INVALID) ? 0 : 1;\n}\n')
+    exe = tmp_path / 'abi'
+    inc = os.path.join(REPO, 'include')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', inc, str(src), '-o', str(exe), _lib.LIB_PATH,
+                        '-Wl,-rpath,' + os.path.dirname(_lib.LIB_PATH)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.stdout, out.stderr)
+    assert 'bad DiT dimensions' in out.stdout
