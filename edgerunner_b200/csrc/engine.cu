@@ -1,37 +1,10 @@
 // Engine: owns packed fp16 weights, the KV cache and workspaces; implements the C ABI of include/edgerunner_b200.h
 // by orchestrating the kernels of this directory.  No CPU fallback anywhere: every entry point launches CUDA work
 // or fails with an error string.
-#include "../../include/edgerunner_b200.h"
+#include "engine_internal.h"
 
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <set>
-#include <string>
-#include <vector>
-
-#include "decode_kernel.h"
-#include "decode_partition.h"
-#include "kernels.h"
-
-#ifndef ER_DEFAULT_PF_DIST
-#define ER_DEFAULT_PF_DIST (128 * 1024)   // L2 run-ahead per CTA: +3..5 % measured (profiles/r02_diag_runahead_nosync_fuse.json); >= 512 KB thrashes L2
-#endif
-#ifndef ER_DEFAULT_FUSE
-#define ER_DEFAULT_FUSE 1   // tensor-parallel layer where the shape allows it (parity: tests/test_gpu_longctx.py, both variants)
-#endif
-
-static thread_local char g_err[512] = "";
-static int g_poison_alloc = 0;   // er_debug_set_global("poison_alloc", 1 everything | 2 K cache | 3 V cache | 4 the rest)
-static int set_err(int code, const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
+thread_local char g_err[512] = "";
+int g_poison_alloc = 0;
 int er_set_error(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -39,12 +12,6 @@ int er_set_error(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
-#define CK(call)                                                                                              \
-    do {                                                                                                      \
-        cudaError_t _e = (call);                                                                              \
-        if (_e != cudaSuccess) return set_err(ER_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
-    } while (0)
-#define CKL(e, call) do { (e)->launches++; CK(call); } while (0)
 
 namespace {
 
@@ -99,80 +66,11 @@ __global__ void pack_transposed_kernel(const __half* w2, int C, int F, __half* d
     dst[i] = c < C ? w2[(size_t)c * F + j] : __float2half_rn(0.f);
 }
 
-struct Slot { __half* dst; int rows, cols, dst_ld; };
-
 }  // namespace
-
-struct er_engine {
-    er_config cfg;
-    int C, H, D, F, V, NL, P, E, EH, LQ, LD, LDP;
-    int Lmax, nkb, grid, S, sc_len, nstage;
-    size_t dec_smem;
-    long long launches = 0;
-    std::vector<void*> allocs;
-    std::map<std::string, Slot> slots;
-    std::set<std::string> loaded;
-    bool finalized = false;
-    // decoder weights
-    __half *wqkv, *bqkv, *wo, *bo, *ln1w, *ln1b, *w1, *b1, *w2, *b2, *ln2w, *ln2b, *lm_head, *embd, *pos;
-    __half* wdec; int ustride, upstage, use_mma;   // decode-stream copy of the decoder weights (padded units)
-    // encoder + conditioner weights
-    __half *qe, *basis, *mlp_w, *mlp_b, *ln_w, *ln_b, *cl1w, *cl1b, *cq_w, *cq_b, *ckv_w, *ckv_b, *co_w, *co_b, *cl2w, *cl2b;
-    __half *ff0w, *ff0b, *ff2w, *ff2b, *lin_w, *lin_b, *pc_w, *pc_b, *ncw, *ncb, *enf;
-    // cache + decode scratch
-    __half *kc, *vc, *q16, *y1, *h1, *y2, *attn16;
-    float *part, *logits, *cond32;
-    unsigned long long* ll = nullptr; size_t ll_words = 0;      // flagged exchange words of the tensor-parallel decode layer
-    __half* wfuse = nullptr; unsigned long long* acc = nullptr; int use_fuse = ER_DEFAULT_FUSE, S_fuse = 0;   // tensor-parallel decode layer
-    er::DecodeState* st;
-    unsigned* bar;
-    int32_t* ids_dev;
-    int32_t *gen_ids_dev, *gen_len_dev;   // for er_generate_host
-    float* conds_dev_buf;
-    // dense workspace
-    int maxrows;
-    float* x32; __half *x16, *qkv16, *a16, *h16;
-    float* logits_all; double* tf_acc; int* tf_cnt; float* tf_rows = nullptr; unsigned char* tf_valid = nullptr; float* tf_part = nullptr;
-    __half* lat16;   // [B][LQ][LDP]
-    // encoder workspace
-    __half *emb16, *pf16, *kvx16, *kvo16, *qln16, *qq16, *ea16, *ex1, *ex1ln, *eff, *egg, *ex2, *pc16;
-    int cache_rows = 0;
-    bool cache_rows_stale = false;     // a decode ran since cache_rows was set: the exact row count lives in the device state
-    unsigned long long* prof = nullptr; int prof_token = -1, prof_cta = 0;
-    // decode-kernel knobs (defaults = the production configuration; changed only through er_debug_set)
-    int red_group4 = 0, split_handicap = 4, split_handicap_fuse = 0, xrep = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
-    int lat_batch_cap = 1;
-};
-
-template <typename T>
-static int dev_alloc(er_engine* e, T** p, size_t n) {
-    void* q = nullptr;
-    CK(cudaMalloc(&q, n * sizeof(T) + 256));
-    // debugging aid (tests/test_gpu_parity.py::test_poisoned_memory): fill every allocation with 0xFF bytes (fp16 / fp32 NaN) so that
-    // any read of memory the engine did not write first shows up as NaN instead of passing by luck on zeroed pages
-    if (g_poison_alloc) {
-        const bool is_kc = (void*)p == (void*)&e->kc, is_vc = (void*)p == (void*)&e->vc;
-        const bool want = g_poison_alloc == 1 || (g_poison_alloc == 2 && is_kc) || (g_poison_alloc == 3 && is_vc) ||
-                          (g_poison_alloc == 4 && !is_kc && !is_vc);
-        if (want) CK(cudaMemset(q, 0xFF, n * sizeof(T) + 256));
-    }
-    e->allocs.push_back(q);
-    *p = (T*)q;
-    return ER_OK;
-}
-#define ALLOC(ptr, n) do { int _r = dev_alloc(e, &(ptr), (size_t)(n)); if (_r) return _r; } while (0)
-template <typename T>
-static void dev_free(er_engine* e, T** p) {
-    if (!*p) return;
-    for (auto it = e->allocs.begin(); it != e->allocs.end(); ++it)
-        if (*it == (void*)*p) { e->allocs.erase(it); break; }
-    cudaFree(*p);
-    *p = nullptr;
-}
 
 // Dense (N > 1 rows) workspace: sized for the 2050-row generate prefix at creation and grown on demand, so that a long resume prompt
 // (LMM.generate(resume_ids=...), infer.py --test_resume_tokens: up to max_seq_length rows in the reference) is not refused.
-static int ensure_dense_rows(er_engine* e, int rows) {
+int ensure_dense_rows(er_engine* e, int rows) {
     if (rows <= e->maxrows) return ER_OK;
     CK(cudaDeviceSynchronize());
     dev_free(e, &e->x32); dev_free(e, &e->x16); dev_free(e, &e->qkv16); dev_free(e, &e->a16); dev_free(e, &e->h16);
@@ -361,6 +259,7 @@ extern "C" void er_destroy(er_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
+    er_train_destroy(e);
     for (void* p : e->allocs) cudaFree(p);
     delete e;
 }
@@ -424,7 +323,7 @@ extern "C" int er_finalize_weights(er_engine* e, void* stream) {
     return ER_OK;
 }
 
-static er::GemmArgs mk_gemm(const __half* A, int lda, const __half* W, int ldw, const __half* bias, int M, int N, int K, int mode) {
+er::GemmArgs mk_gemm(const __half* A, int lda, const __half* W, int ldw, const __half* bias, int M, int N, int K, int mode) {
     er::GemmArgs g{};
     g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.M = M; g.N = N; g.K = K; g.mode = mode;
     return g;
@@ -455,17 +354,17 @@ static int encode_points(er_engine* e, const float* pts, int n, __half* lat, cud
 }
 
 // latents -> cond32 [P][C]: norm_cond(proj_cond(lat)) ++ embed_num_face[bucket]   (models.py:124,135-141)
-static int quantize_num_faces(int n) { return n <= 0 ? 0 : n <= 1000 ? 1 : n <= 2000 ? 2 : n <= 4000 ? 3 : n <= 8000 ? 4 : 5; }
+int er_quantize_num_faces(int n) { return n <= 0 ? 0 : n <= 1000 ? 1 : n <= 2000 ? 2 : n <= 4000 ? 3 : n <= 8000 ? 4 : 5; }
 static int latents_to_cond(er_engine* e, const __half* lat, int num_faces, float* cond32, cudaStream_t st) {
     const int C = e->C, LQ = e->LQ;
     er::GemmArgs g = mk_gemm(lat, e->LDP, e->pc_w, e->LDP, e->pc_b, LQ, C, e->LDP, er::GEMM_F16);
     g.out16 = e->pc16; g.ldo = C; CKL(e, er_gemm(g, st));
     CKL(e, er_layernorm(nullptr, e->pc16, C, e->ncw, e->ncb, cond32, nullptr, C, LQ, C, st));
-    if (e->cfg.use_num_face_cond) CKL(e, er_f16_to_f32(e->enf + (size_t)quantize_num_faces(num_faces) * C, cond32 + (size_t)LQ * C, C, st));
+    if (e->cfg.use_num_face_cond) CKL(e, er_f16_to_f32(e->enf + (size_t)er_quantize_num_faces(num_faces) * C, cond32 + (size_t)LQ * C, C, st));
     return ER_OK;
 }
 
-static int encode_one(er_engine* e, const float* conds_dev, int n_points, int is_latent, int num_faces, __half* lat, float* cond32, cudaStream_t st) {
+int encode_one(er_engine* e, const float* conds_dev, int n_points, int is_latent, int num_faces, __half* lat, float* cond32, cudaStream_t st) {
     if (is_latent) {
         if (n_points != e->LQ) return set_err(ER_ERR_INVALID, "latent rows %d != latent_size %d", n_points, e->LQ);
         e->launches++;

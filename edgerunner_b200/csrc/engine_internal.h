@@ -1,0 +1,120 @@
+// Engine internals shared by engine.cu (inference entry points) and train.cu (training step): the handle, allocation helpers, error macros.
+#pragma once
+#include "../../include/edgerunner_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "decode_kernel.h"
+#include "decode_partition.h"
+#include "kernels.h"
+
+#ifndef ER_DEFAULT_PF_DIST
+#define ER_DEFAULT_PF_DIST (128 * 1024)   // L2 run-ahead per CTA: +3..5 % measured (profiles/r02_diag_runahead_nosync_fuse.json); >= 512 KB thrashes L2
+#endif
+#ifndef ER_DEFAULT_FUSE
+#define ER_DEFAULT_FUSE 1   // tensor-parallel layer where the shape allows it (parity: tests/test_gpu_longctx.py, both variants)
+#endif
+
+extern thread_local char g_err[512];
+extern int g_poison_alloc;   // er_debug_set(NULL, "poison_alloc", 1 everything | 2 K cache | 3 V cache | 4 the rest)
+static inline int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t _e = (call);                                                                              \
+        if (_e != cudaSuccess) return set_err(ER_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+#define CKL(e, call) do { (e)->launches++; CK(call); } while (0)
+
+
+struct Slot { __half* dst; int rows, cols, dst_ld; };
+
+struct er_train;   // train.cu
+
+struct er_engine {
+    er_config cfg;
+    int C, H, D, F, V, NL, P, E, EH, LQ, LD, LDP;
+    int Lmax, nkb, grid, S, sc_len, nstage;
+    size_t dec_smem;
+    long long launches = 0;
+    std::vector<void*> allocs;
+    std::map<std::string, Slot> slots;
+    std::set<std::string> loaded;
+    bool finalized = false;
+    // decoder weights
+    __half *wqkv, *bqkv, *wo, *bo, *ln1w, *ln1b, *w1, *b1, *w2, *b2, *ln2w, *ln2b, *lm_head, *embd, *pos;
+    __half* wdec; int ustride, upstage, use_mma;   // decode-stream copy of the decoder weights (padded units)
+    // encoder + conditioner weights
+    __half *qe, *basis, *mlp_w, *mlp_b, *ln_w, *ln_b, *cl1w, *cl1b, *cq_w, *cq_b, *ckv_w, *ckv_b, *co_w, *co_b, *cl2w, *cl2b;
+    __half *ff0w, *ff0b, *ff2w, *ff2b, *lin_w, *lin_b, *pc_w, *pc_b, *ncw, *ncb, *enf;
+    // cache + decode scratch
+    __half *kc, *vc, *q16, *y1, *h1, *y2, *attn16;
+    float *part, *logits, *cond32;
+    unsigned long long* ll = nullptr; size_t ll_words = 0;      // flagged exchange words of the tensor-parallel decode layer
+    __half* wfuse = nullptr; unsigned long long* acc = nullptr; int use_fuse = ER_DEFAULT_FUSE, S_fuse = 0;   // tensor-parallel decode layer
+    er::DecodeState* st;
+    unsigned* bar;
+    int32_t* ids_dev;
+    int32_t *gen_ids_dev, *gen_len_dev;   // for er_generate_host
+    float* conds_dev_buf;
+    // dense workspace
+    int maxrows;
+    float* x32; __half *x16, *qkv16, *a16, *h16;
+    float* logits_all; double* tf_acc; int* tf_cnt; float* tf_rows = nullptr; unsigned char* tf_valid = nullptr; float* tf_part = nullptr;
+    __half* lat16;   // [B][LQ][LDP]
+    // encoder workspace
+    __half *emb16, *pf16, *kvx16, *kvo16, *qln16, *qq16, *ea16, *ex1, *ex1ln, *eff, *egg, *ex2, *pc16;
+    int cache_rows = 0;
+    bool cache_rows_stale = false;     // a decode ran since cache_rows was set: the exact row count lives in the device state
+    unsigned long long* prof = nullptr; int prof_token = -1, prof_cta = 0;
+    // decode-kernel knobs (defaults = the production configuration; changed only through er_debug_set)
+    int red_group4 = 0, split_handicap = 4, split_handicap_fuse = 0, xrep = 1, poll_rounds = 4, pf_dist = ER_DEFAULT_PF_DIST, dbg_nosync = 0;
+    int lat_batch_cap = 1;
+    er_train* train = nullptr;      // training-step state (train.cu), created by the first er_train_step
+};
+
+template <typename T>
+static int dev_alloc(er_engine* e, T** p, size_t n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, n * sizeof(T) + 256));
+    // debugging aid (tests/test_gpu_parity.py::test_poisoned_memory): fill every allocation with 0xFF bytes (fp16 / fp32 NaN) so that
+    // any read of memory the engine did not write first shows up as NaN instead of passing by luck on zeroed pages
+    if (g_poison_alloc) {
+        const bool is_kc = (void*)p == (void*)&e->kc, is_vc = (void*)p == (void*)&e->vc;
+        const bool want = g_poison_alloc == 1 || (g_poison_alloc == 2 && is_kc) || (g_poison_alloc == 3 && is_vc) ||
+                          (g_poison_alloc == 4 && !is_kc && !is_vc);
+        if (want) CK(cudaMemset(q, 0xFF, n * sizeof(T) + 256));
+    }
+    e->allocs.push_back(q);
+    *p = (T*)q;
+    return ER_OK;
+}
+#define ALLOC(ptr, n) do { int _r = dev_alloc(e, &(ptr), (size_t)(n)); if (_r) return _r; } while (0)
+template <typename T>
+static void dev_free(er_engine* e, T** p) {
+    if (!*p) return;
+    for (auto it = e->allocs.begin(); it != e->allocs.end(); ++it)
+        if (*it == (void*)*p) { e->allocs.erase(it); break; }
+    cudaFree(*p);
+    *p = nullptr;
+}
+
+// engine.cu
+int ensure_dense_rows(er_engine* e, int rows);
+int encode_one(er_engine* e, const float* conds_dev, int n_points, int is_latent, int num_faces, __half* lat, float* cond32, cudaStream_t st);
+int er_quantize_num_faces(int n);
+er::GemmArgs mk_gemm(const __half* A, int lda, const __half* W, int ldw, const __half* bias, int M, int N, int K, int mode);
+// train.cu
+void er_train_destroy(er_engine* e);

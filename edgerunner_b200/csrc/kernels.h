@@ -71,3 +71,32 @@ cudaError_t er_cross_entropy(const float* logits_pre, int ld, const int64_t* lab
 cudaError_t er_sum_squares(const __half* x, size_t n, float* partial296, double* out, cudaStream_t stream);
 // rows of a16 [M][C] whose mask byte is 0 become zero (flash_attn pad_input)
 cudaError_t er_zero_masked_rows(__half* a16, const unsigned char* mask, int M, int C, cudaStream_t stream);
+
+// ---- training step: backward-pass kernels (backward.cu) ------------------------------------------------------------------------------
+#define ER_BW_SLABS 64      // row slabs of the two-stage column reductions (bias / LayerNorm parameter gradients)
+// out [Cn][ld_out] = in [R][ld_in]^T, columns [R, round_up(R, 64)) of out zeroed; ld_out >= round_up(R, 64)
+cudaError_t er_transpose_f16(const __half* in, int R, int Cn, int ld_in, __half* out, int ld_out, cudaStream_t st);
+// out32 = res32 + dropout_p(y16) over n elements; the keep mask is a counter-based function of (seed, site, element index); p == 0: plain add
+cudaError_t er_add_dropout(const float* res32, const __half* y16, float* out32, size_t n, float p, unsigned long long seed, unsigned site, cudaStream_t st);
+// LayerNorm backward (eps 1e-5): dy32 [M][C] (gradient of the output), s32 | s16 [M][ld_s] (the input) -> ds32 [M][C] (optional), dbr16 [M][C]
+// (optional: f16 of ds through the dropout mask of (p, seed, site)), mean / rstd [M]
+cudaError_t er_ln_bwd(const float* dy32, const float* s32, const __half* s16, int ld_s, const __half* gamma, float* ds32, __half* dbr16, float* mean,
+                      float* rstd, int M, int C, float p, unsigned long long seed, unsigned site, cudaStream_t st);
+// dgamma [C] = sum_r dy * xhat, dbeta [C] = sum_r dy; partial: scratch of ER_BW_SLABS * 2 * C floats
+cudaError_t er_ln_param_grad(const float* dy32, const float* s32, const __half* s16, int ld_s, const float* mean, const float* rstd, int M, int C,
+                             float* partial, float* dgamma, float* dbeta, cudaStream_t st);
+// out [ncols] = column sums of x16 [M][ld]; partial: scratch of ER_BW_SLABS * ncols floats
+cudaError_t er_colsum_f16(const __half* x16, int ld, int M, int ncols, float* partial, float* out, cudaStream_t st);
+// dh16 = h16 > 0 ? dh16 : 0 (in place), n multiple of 8
+cudaError_t er_relu_bwd(__half* dh16, const __half* h16, size_t n, cudaStream_t st);
+// dl [B*N][ldo] = f16(loss_scale / *count * (softmax(round_f16(logits)) - onehot(label of the NEXT row))), zero for ignored rows and pad columns
+cudaError_t er_ce_bwd(const float* logits_pre, int ld, const int64_t* labels, int B, int N, int V, const int* count_dev, float loss_scale, __half* dl, int ldo,
+                      cudaStream_t st);
+// gradients of embed_positions rows [0, N), embd [V][C] and (optional) embed_num_face [10][C] from dx0 [B*N][C]
+cudaError_t er_embed_bwd(const float* dx0, const int32_t* ids, const int32_t* bucket_dev, int B, int T, int N, int P, int C, int V, int numface_row,
+                         float* dpos, float* dembd, float* denf, cudaStream_t st);
+cudaError_t er_export_f32(const float* src, int ld, int rows, int cols, float scale, float* dst, cudaStream_t st);
+// flash-attention backward for the forward described by `a` (a.out = the forward output): dq / dk / dv with their own pitches and batch strides;
+// lse2, dsum: scratch of B * H * Nq floats each
+cudaError_t er_attention_bwd(const er::AttnArgs& a, const __half* dout, __half* dq, __half* dk, __half* dv, int ld_dq, int ld_dk, int ld_dv, long long dq_bs,
+                             long long dk_bs, long long dv_bs, float* lse2, float* dsum, cudaStream_t st);

@@ -182,7 +182,28 @@ int er_dit_debug_set(er_dit* e, const char* key, int64_t value);   /* "graph": 0
                                                                       residuals as separate kernels instead of GEMM epilogues; "uncond_shortcut": 0 = run the
                                                                       cross-attention of the zero-condition half in full (all A/B timing, bit-identical) */
 
-/* ---- Optimizer half of the training step (no backward pass exists here) ---------------------------------
+/* ---- Training step: forward in training mode + backward ---------------------------------------------------------------------
+ * Replaces, for one batch, `out = model(data); accelerator.backward(out['loss'])` (main.py:168-172) = torch autograd over LMM.forward
+ * (core/models.py:147-202 -> core/transformer/modeling_opt.py:253-298 post-LN layers with F.dropout(p) on both branches, :464-517 lm_head +
+ * shifted cross-entropy), with opt.checkpointing (every layer re-run in the backward pass) and opt.freeze_encoder (the point encoder and the KL
+ * term carry no gradient).  Arguments as er_forward_tf2, plus dropout_p (ShapeOPTConfig.dropout, 0.1 in the reference; the keep mask is a
+ * counter-based function of `seed`, not torch's Philox stream), loss_scale (static scale of the fp16 activation gradients; exported gradients are
+ * unscaled).  losses_dev[3] = {loss, mean CE, KL} of this rank's batch (the reference's DDP averages per-rank means: no cross-rank loss sums here);
+ * sums_dev (optional) as er_forward_tf2.  The engine must have been created with max_tf_rows >= B * (num_cond_tokens + T).
+ * er_grad_get: copy the fp32 gradient of one state-dict entry (reference key schema, dense [rows][cols], numel checked) to out_dev after a
+ * step.  er_grad_has: 1 if the entry is trainable here (decoder, lm_head, embeddings, proj_cond, norm_cond, embed_num_face), 0 for the frozen
+ * point encoder / unknown keys. */
+int er_train_step(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, const int32_t* tokens_dev, const int64_t* labels_dev,
+                  const uint8_t* mask_dev, const int32_t* num_faces_host, int32_t B, int32_t T, float kl_weight, float dropout_p, uint64_t seed,
+                  float loss_scale, float* losses_dev, double* sums_dev, void* stream);
+int er_grad_get(er_engine* e, const char* name, float* out_dev, int64_t numel, void* stream);
+int32_t er_grad_has(er_engine* e, const char* name);
+/* Backward of the attention() op seam (core/transformer/attention.py:27-95; forward: er_attention_bnhd): tensors [B][N][H][D] fp16 contiguous,
+ * out = the forward result, dout = the gradient of it; writes dq, dk, dv.  D in {64, 96}; causal needs Nq == Nk.  Deterministic (no atomics). */
+int er_attention_bwd_bnhd(const void* q_dev, const void* k_dev, const void* v_dev, const void* out_dev, const void* dout_dev, void* dq_dev, void* dk_dev,
+                          void* dv_dev, int32_t B, int32_t Nq, int32_t Nk, int32_t H, int32_t D, int32_t causal, void* stream);
+
+/* ---- Optimizer half of the training step ---------------------------------------------------------------------------------------
  * main.py:133 `torch.optim.AdamW(model.parameters(), lr, weight_decay=0.01, betas=(0.9, 0.95))` and main.py:175-177
  * `accelerator.clip_grad_norm_(model.parameters(), opt.gradient_clip)` over flat fp32 buffers (16-byte aligned, n elements).
  * er_grad_norm_clip: *norm_out_dev = ||g||_2, *scale_out_dev = min(1, max_norm / (norm + 1e-6)) (torch.nn.utils.clip_grad_norm_); scratch_dev:
