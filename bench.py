@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — mesh-tokens/sec of the auto-regressive decode hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--max-new T]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--max-new T] [--workload decode|tf|dit|train]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, replicas)
 
 A "step" is one complete pass of the hot path over one synthetic request of BASELINE.json configs[1]:
@@ -317,6 +317,95 @@ def run_teacher_forced(args):
     }), flush=True)
 
 
+def run_train(args):
+    """BASELINE configs[3] as a FULL training step: ArAE, seq_len 8192 (+ 2049 condition rows + BOS/EOS = 10 243 rows), batch 4 per GPU,
+    data parallel.  A step = edgerunner_b200.train.FlatTrainer.step: training-mode forward (dropout 0.1) + backward with per-layer recomputation
+    (opt.checkpointing) + flat fp32 gradient all-reduce over NCCL + global-norm clipping + fused AdamW + fp16 weight refresh; tokens / labels are
+    uploaded and the loss is read back every step.  The point encoder is frozen (opt.freeze_encoder).  value = supervised tokens/s over all ranks;
+    roofline: tensor-bound, MODEL FLOPs (forward + 2 x GEMM + 2.5 x attention; the recomputation is not counted) against bf16_tflops_sustained."""
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from dataclasses import replace
+    from core.models import LMM
+    from core.options import config_defaults
+    from edgerunner_b200 import synth
+    from edgerunner_b200.train import FlatTrainer
+    opt = replace(config_defaults['ArAE'], generate_mode='greedy', freeze_encoder=True) if not args.tiny else synth.tiny_options(freeze_encoder=True)
+    B, T = (4, 8194) if not args.tiny else (2, 48)
+    P, C, NL = opt.num_cond_tokens, opt.hidden_dim, opt.num_layers
+    N = P + T
+    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
+    with torch.device('meta'):
+        model = LMM(opt)
+    model.load_state_dict(sd, strict=True, assign=True)
+    del sd
+    model = model.half().train().to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    tokens = torch.randint(6, model.vocab_size, (B, T), generator=g)
+    tokens[:, 0] = opt.bos_token_id
+    data = {'conds': torch.cat([synth.synth_point_cloud(rank * B + b, opt.point_num) for b in range(B)]).to(dev), 'tokens': tokens.pin_memory(),
+            'labels': torch.cat([torch.full((B, P), -100, dtype=torch.long), tokens.long()], dim=1).pin_memory(), 'masks': None,
+            'num_faces': torch.tensor([4000] * B)}
+    tr = FlatTrainer(model, total_steps=1000, max_batch=B, max_tokens=T)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+    hist = []
+    for _ in range(max(args.warmup, 1)):
+        hist.append(float(tr.step(data)['loss']))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    l0 = tr.engine.kernel_launches()
+    ev[0].record()
+    for _ in range(args.steps):
+        out = tr.step(data)
+        hist.append(float(out['loss']))                       # D2H of the step's result
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0].item())
+        dist.destroy_process_group()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    ms_step = ms / args.steps
+    gemm_f, attn_f = 2 * 680_752_128 * B * N, 2 * N * N * C * NL * B
+    flops = (3 * gemm_f + 3.5 * attn_f + 0.16e12 * B) if not args.tiny else float('nan')
+    peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    peak = float(json.load(open(peaks_path)).get('bf16_tflops_sustained', 1400.0)) if os.path.exists(peaks_path) else 1400.0
+    tf = flops / (ms_step * 1e-3) / 1e12
+    emit(json.dumps({
+        'metric': 'training tokens/sec, ArAE full step seq_len 8192 batch 4/GPU (BASELINE configs[3]; decoder trained, point encoder frozen)',
+        'value': world * B * T / (ms_step * 1e-3), 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic', 'loss_history': hist,
+        'config': {'workload': f'ArAE training step B={B}/GPU N={N} (P={P} + T={T}): training forward (dropout {tr.dropout_p}) + backward with per-layer '
+                               f'recomputation + flat gradient all-reduce x{world} + clip + fused AdamW + fp16 weight refresh',
+                   'trainable_parameters': int(tr.numel), 'l2': f'activations of {B * N} rows x 1536 exceed L2'},
+        'clocks': clocks, 'gpu_launches': int(tr.engine.kernel_launches() - l0),
+        'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'traffic': None,
+                     'kernel': 'er::tc::gemm_tcgen05_kernel (forward, dgrad, wgrad) + er::fa::attention_tcgen05_kernel + er::bw::attn_bwd_* (wmma)',
+                     'algorithmic_flops_per_step_per_gpu': flops, 'note': 'model FLOPs: 3 x GEMM + 3.5 x causal attention of the forward; the recomputed '
+                     'forward of the checkpointed layers and the 1.6 x redundant score products of the two-kernel attention backward are not counted',
+                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)'},
+        'e2e': {'value': world * B * T / (ms_step * 1e-3), 'unit': 'tokens/s', 'h2d_bytes_per_step': int(tokens.numel() * 4 + data['labels'].numel() * 8),
+                'd2h_bytes_per_step': 4, 'note': 'FlatTrainer.step(data): tokens / labels uploaded from pinned host memory, loss read back, every step'},
+    }), flush=True)
+
+
 def ref_dit_leg(kind, images, steps, warmup, layers=24, timeout=900):
     """oracle/ref_dit_leg.py in its own process -> dict (reference DiT module when oracle/_ref/py travelled, else the oracle port)."""
     cmd = [sys.executable, os.path.join(REPO, 'oracle', 'ref_dit_leg.py'), kind, '--images', str(images), '--steps', str(steps), '--warmup', str(warmup),
@@ -530,7 +619,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=3, help='timed LMM.generate calls of the e2e leg (bounded: each is a full 16k request)')
     ap.add_argument('--grad-allreduce', action='store_true', help='--workload tf under torchrun: also all-reduce a flattened synthetic gradient buffer every step (SURVEY 8e)')
     ap.add_argument('--dit-pipeline', action='store_true', help='--workload dit: also time one image end to end (MDiT.run -> LMM.generate) at the preset sizes')
-    ap.add_argument('--workload', default='decode', choices=['decode', 'tf', 'dit'],
+    ap.add_argument('--workload', default='decode', choices=['decode', 'tf', 'dit', 'train'],
                     help="decode = BASELINE configs[1] (the metric); tf = configs[3]: teacher-forced forward seq 8192 batch 4/GPU, loss all-reduced over NCCL")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner under torchrun) is sent to stderr instead
@@ -547,6 +636,9 @@ def main():
         return
     if args.workload == 'tf':
         run_teacher_forced(args)
+        return
+    if args.workload == 'train':
+        run_train(args)
         return
 
     rank = int(os.environ.get('RANK', '0'))

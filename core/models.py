@@ -112,11 +112,10 @@ class LMM(nn.Module):
     def forward(self, data, step_ratio=1):
         """Teacher-forced forward -> {'loss', 'loss_ce', 'loss_kl', 'logits'}  (reference :147-202).
 
-        Inference-mode numerics (no dropout, no num-face dropout, dense causal attention): the masks must be all-True.
-        No autograd graph is produced (the backward pass is the next row of the scope table)."""
+        ``model.eval()``: inference-mode numerics (no dropout, no num-face dropout), no autograd graph.  ``model.train()``: the training step of
+        main.py:168-172 — see ``_forward_train``."""
         if self.training:
-            raise NotImplementedError('training-mode forward (dropout, num-face dropout, autograd graph) is not on the B200 path: '
-                                      'call model.eval(); the returned loss carries no graph')
+            return self._forward_train(data)
         masks = data.get('masks')                      # [B, P+T] bool; right-padded batches (collate_fn) take the masked path
         tokens, labels = data['tokens'], data['labels']
         B, T = tokens.shape
@@ -134,6 +133,31 @@ class LMM(nn.Module):
         out = {'loss': losses[0], 'loss_ce': losses[1], 'logits': logits}
         if self.opt.cond_mode == 'point':
             out['loss_kl'] = losses[2]
+        return out
+
+    def _forward_train(self, data):
+        """Training-mode forward (reference :147-202 with self.training): num-face dropout (:161-164), F.dropout(config.dropout) on both branches of
+        every decoder layer, and a loss that carries a graph: ``out['loss'].backward()`` fills ``.grad`` of the decoder, lm_head, embeddings,
+        proj_cond / norm_cond / embed_num_face parameters.  The forward AND the backward run inside one library call (er_train_step: checkpointed
+        layers, tcgen05 dgrad / wgrad GEMMs, flash-attention backward); the autograd node only hands the stored gradients out.  As with
+        ``opt.freeze_encoder = True`` (the Options default) the point encoder runs without a graph, so loss_kl carries no gradient;
+        ``freeze_encoder = False`` (encoder training) is not built.  The dropout mask is a counter-based function of a seed drawn from torch's
+        global generator (reproducible per seed; not torch's Philox stream).  'logits' is None in this mode (main.py never reads it while training)."""
+        if self.opt.cond_mode == 'point' and not self.opt.freeze_encoder:
+            raise NotImplementedError('training the point encoder (freeze_encoder=False) is not built: the B200 training step covers the decoder, '
+                                      'lm_head, embeddings and the conditioner projection (set opt.freeze_encoder = True)')
+        tokens, labels = data['tokens'], data['labels']
+        B, T = tokens.shape
+        num_faces = data['num_faces']
+        if self.opt.use_num_face_cond:                                            # random num_faces dropout (reference :161-164, in place like it)
+            unprog_mask = torch.rand((B,), device=num_faces.device) < self.opt.nof_dropout_ratio
+            num_faces[unprog_mask] = -1
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+        loss, loss_ce, loss_kl = _TrainStep.apply(self, data, seed, *[p for _, p in named])
+        out = {'loss': loss, 'loss_ce': loss_ce, 'logits': None}
+        if self.opt.cond_mode == 'point':
+            out['loss_kl'] = loss_kl
         return out
 
     @torch.no_grad()
@@ -165,6 +189,35 @@ class LMM(nn.Module):
             tokens = np.concatenate((resume_ids[0].detach().cpu().numpy(), tokens), axis=0)
         mesh = save_mesh(tokens, self.opt, tokenizer=tokenizer, clean=clean, verbose=True)
         return [mesh], [tokens]
+
+
+class _TrainStep(torch.autograd.Function):
+    """loss = er_train_step(batch); d loss / d parameter = the gradients the same call left in the engine (fp32, exported on backward)."""
+
+    @staticmethod
+    def forward(ctx, model, data, seed, *params):
+        tokens = data['tokens']
+        B, T = tokens.shape
+        e = model.get_engine(max_new_tokens=getattr(model._engine, 'max_new_tokens', 64) if model._engine else 64,
+                             max_tf_rows=B * (model.opt.num_cond_tokens + T))
+        losses, _ = e.train_step(data['conds'], tokens, data['labels'], data['num_faces'].tolist(), model.opt.kl_weight, masks=data.get('masks'),
+                                 dropout_p=float(model.config.dropout), seed=seed, loss_scale=getattr(model, 'loss_scale', None))
+        ctx.engine = e
+        ctx.names = [n for n, p in model.named_parameters() if p.requires_grad]
+        ctx.meta = [(p.shape, p.dtype) for p in params]
+        return losses[0].clone(), losses[1].clone(), losses[2].clone()
+
+    @staticmethod
+    def backward(ctx, g_loss, g_ce, g_kl):
+        e = ctx.engine
+        grads = []
+        for name, (shape, dtype) in zip(ctx.names, ctx.meta):
+            if not e.grad_has(name):
+                grads.append(None)
+                continue
+            g = e.grad(name, shape)
+            grads.append((g * g_loss).to(dtype))
+        return (None, None, None, *grads)
 
 
 ArAE = LMM   # the tyro preset name of the reference (core/options.py:158) — convenience alias

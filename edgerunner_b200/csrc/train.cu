@@ -69,11 +69,17 @@ static int row_alloc(er_engine* e, er_train* t, T** p, size_t n) {
 #define RALLOC(ptr, n) do { int _r = row_alloc(e, t, &(ptr), (size_t)(n)); if (_r) return _r; } while (0)
 
 // one-time state: gradient buffers mirroring the engine's weight arrays, slot views by state-dict key
+static int create_train_impl(er_engine* e, er_train* t);
 static int create_train(er_engine* e) {
-    er_train* t = new er_train();
-    e->train = t;
-    const size_t C = e->C, F = e->F, V = e->V, NL = e->NL, LDP = e->LDP;
     if (e->C % 64 || e->F % 64 || e->LDP % 8) return set_err(ER_ERR_INVALID, "training needs hidden_dim and ffn_dim multiples of 64 (got %d, %d)", e->C, e->F);
+    er_train* t = new er_train();
+    const int r = create_train_impl(e, t);
+    if (r) { delete t; return r; }        // device buffers already recorded in e->allocs are released by er_destroy
+    e->train = t;
+    return ER_OK;
+}
+static int create_train_impl(er_engine* e, er_train* t) {
+    const size_t C = e->C, F = e->F, V = e->V, NL = e->NL, LDP = e->LDP;
     t->Vp = round64(e->V);
     t->wide = (int)std::max(F, 3 * C);
     struct Arr { const __half* w; size_t n; float** g; };

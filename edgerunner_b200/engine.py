@@ -69,8 +69,9 @@ class Engine:
                 pass
 
     # ---- weights ----------------------------------------------------------------------------------------------------
-    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
-        """Upload a checkpoint in the reference key schema (fp32 or fp16 tensors on any device)."""
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], persistent: bool = False):
+        """Upload a checkpoint in the reference key schema (fp32 or fp16 tensors on any device).  persistent=True: the tensors outlive the call
+        (device-resident views of a long-lived buffer, as the training loop passes), so the stream is not synchronised after every entry."""
         with torch.cuda.device(self.device):
             for name, t in sd.items():
                 t = t.detach()
@@ -80,7 +81,8 @@ class Engine:
                 shape = (C.c_int64 * max(t.dim(), 1))(*(t.shape if t.dim() else (1,)))
                 dt = _lib.C.c_int32(0 if t.dtype == torch.float16 else 1)
                 _lib.check(self.lib.er_load_weight(self.h, name.encode(), t.data_ptr(), dt, shape, max(t.dim(), 1), _stream()))
-                torch.cuda.current_stream().synchronize()   # t may be a temporary
+                if not persistent:
+                    torch.cuda.current_stream().synchronize()   # t may be a temporary
             _lib.check(self.lib.er_finalize_weights(self.h, _stream()))
 
     # ---- generate pieces --------------------------------------------------------------------------------------------------
@@ -163,6 +165,52 @@ class Engine:
                                                sums.data_ptr(), logits.data_ptr() if logits is not None else None, _stream()))
         self._keep = [m8]
         return (losses, logits, sums) if want_sums else (losses, logits)
+
+    # ---- training step ------------------------------------------------------------------------------------------
+    def train_step(self, conds: torch.Tensor, tokens: torch.Tensor, labels: torch.Tensor, num_faces, kl_weight: float,
+                   masks: Optional[torch.Tensor] = None, dropout_p: float = 0.1, seed: int = 0, loss_scale: Optional[float] = None):
+        """Training-mode forward + backward of LMM.forward on this batch (er_train_step): -> (losses[3] = loss, mean CE, KL; sums[3]).
+        The gradients stay in the engine until ``grad(name, ...)`` exports them.  Arguments as ``forward_tf``.  loss_scale: static scale of the fp16
+        activation gradients (removed again on export); default: the power of two that puts 4..8 on each supervised row's d loss / d logits
+        (the mean over n rows carries 1/n), so the scale does not depend on the batch size."""
+        B, T = tokens.shape
+        is_latent = int(self.opt.cond_mode == 'point_latent')
+        conds = conds.to(self.device, torch.float32).contiguous()
+        tok = tokens.to(self.device, torch.int32).contiguous()
+        lab = labels.to(self.device, torch.int64).contiguous()
+        nf = (C.c_int32 * B)(*[int(x) for x in num_faces])
+        if loss_scale is None:
+            n_sup = max(1, int((lab[:, 1:] >= 0).sum().item()))
+            loss_scale = float(2 ** int(np.ceil(np.log2(4.0 * n_sup))))
+        losses = torch.zeros(3, dtype=torch.float32, device=self.device)
+        sums = torch.zeros(3, dtype=torch.float64, device=self.device)
+        m8 = None
+        if masks is not None:
+            m = masks.to(self.device).bool()
+            if m.shape != (B, self.P + T):
+                raise ValueError(f'masks must be [B, P+T] = {(B, self.P + T)}, got {tuple(m.shape)}')
+            if bool((m[:, 1:] & ~m[:, :-1]).any()):
+                raise NotImplementedError('only right-padded attention masks are supported (collate_fn pads at the end)')
+            if not bool(m.all()):
+                m8 = m.to(torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.er_train_step(self.h, conds.data_ptr(), conds.shape[1], is_latent, tok.data_ptr(), lab.data_ptr(),
+                                              m8.data_ptr() if m8 is not None else None, nf, B, T, C.c_float(kl_weight), C.c_float(dropout_p),
+                                              C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_float(loss_scale), losses.data_ptr(), sums.data_ptr(), _stream()))
+        self._keep = [m8, conds, tok, lab]
+        return losses, sums
+
+    def grad_has(self, name: str) -> bool:
+        return bool(self.lib.er_grad_has(self.h, name.encode()))
+
+    def grad(self, name: str, shape=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 gradient of one state-dict entry from the last ``train_step`` (loss scale removed); ``out``: a contiguous fp32 CUDA tensor to fill."""
+        if out is None:
+            out = torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.er_grad_get(self.h, name.encode(), out.data_ptr(), out.numel(), _stream()))
+        return out
 
     # ---- introspection ----------------------------------------------------------------------------------------------------
     def weight_bytes_per_token(self) -> int:

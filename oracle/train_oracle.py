@@ -1,0 +1,104 @@
+"""CPU ORACLE of the training step — TEST INFRASTRUCTURE ONLY (see oracle/er_oracle.py for the rules).
+
+What the reference does in a training step (main.py:168-172): ``out = model(data); accelerator.backward(out['loss'])`` — torch autograd over
+``LMM.forward`` (core/models.py:147-202) in ``model.train()`` mode:
+
+    encode_cond        core/models.py:101-144; with ``opt.freeze_encoder`` the point encoder runs under ``torch.no_grad()`` (:105, :115-117)
+    decoder layer      core/transformer/modeling_opt.py:253-298 — post-LN; ``F.dropout(p=config.dropout)`` on the attention branch (:272) and on the
+                       MLP branch (:285) before the residual adds
+    padded batches     core/transformer/attention.py:65-93 (unpad -> varlen causal -> pad_input: masked rows come back as zeros)
+    loss               modeling_opt.py:497-505 (lm_head, shift, cross_entropy(ignore_index=-100)); models.py:191-197 (+ kl_weight * KL)
+
+``forward_train`` restates that forward with plain differentiable torch ops over a dict of leaf tensors, so that ``loss.backward()`` IS the
+reference's backward (autograd).  Pinning: with ``dropout_p = 0`` and no num-face dropout its loss must equal ``Oracle.forward_tf`` (itself pinned
+against the reference modules by tests/golden) — tests/test_train_cpu.py checks that here on the CPU.  The dropout mask cannot be torch's (the CUDA
+path draws it from a counter-based generator, edgerunner_b200/csrc/backward.cu::drop_keep): ``dropout_keep`` restates that generator bit for bit so
+that oracle and engine drop the same elements.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle.er_oracle import Oracle, quantize_num_faces
+
+_M64 = (1 << 64) - 1
+
+
+def dropout_keep(seed: int, site: int, n: int, p: float) -> np.ndarray:
+    """keep[i] for i in [0, n): splitmix64 of (seed, site, i), upper 32 bits >= p * 2^32  (backward.cu::drop_keep)."""
+    if p <= 0:
+        return np.ones(n, dtype=bool)
+    thr = min(int(float(np.float32(p)) * 4294967296.0), 4294967295)
+    idx = np.arange(1, n + 1, dtype=np.uint64)
+    with np.errstate(over='ignore'):
+        z = np.uint64(seed & _M64) + np.uint64(0x9E3779B97F4A7C15) * idx + np.uint64((0xD1B54A32D192ED03 * (site + 1)) & _M64)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(32)).astype(np.uint64) >= np.uint64(thr)
+
+
+def _dropout(y: torch.Tensor, seed: int, site: int, p: float) -> torch.Tensor:
+    if p <= 0:
+        return y
+    keep = torch.from_numpy(dropout_keep(seed, site, y.numel(), p)).view(y.shape)
+    return torch.where(keep, y / (1.0 - float(np.float32(p))), torch.zeros_like(y))
+
+
+def trainable_leaves(state_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """fp16-rounded copies (what the engine holds) of every non-encoder tensor as fp32 leaves with requires_grad."""
+    return {k: v.detach().to(torch.float16).float().requires_grad_(True) for k, v in state_dict.items() if not k.startswith('point_encoder.')}
+
+
+def forward_train(opt, state_dict, w: Dict[str, torch.Tensor], conds, tokens, labels, num_faces, masks: Optional[torch.Tensor] = None,
+                  dropout_p: float = 0.0, seed: int = 0):
+    """-> dict(loss, loss_ce, loss_kl).  ``w``: trainable leaves (``trainable_leaves``); the frozen point encoder comes from ``state_dict``.
+    fp32 arithmetic throughout (the gradient reference; the engine's fp16 rounding is what the test tolerance covers)."""
+    orc = Oracle(opt, state_dict, mode='ledger')                     # frozen encoder as the engine runs it (fp16 ledger), no graph
+    B, T = tokens.shape
+    C, H, NL = opt.hidden_dim, opt.num_heads, opt.num_layers
+    D = C // H
+    with torch.no_grad():
+        lat_all = orc.encode_points(conds) if opt.cond_mode == 'point' else orc.r(conds.float())
+    xs = []
+    for b in range(B):
+        ce = F.layer_norm(lat_all[b] @ w['proj_cond.weight'].t() + w['proj_cond.bias'], (C,), w['norm_cond.weight'], w['norm_cond.bias'], 1e-5)
+        if opt.use_num_face_cond:
+            ce = torch.cat([ce, w['embed_num_face.weight'][quantize_num_faces(int(num_faces[b]))][None]], 0)
+        tok = w['mesh_decoder.model.embd.weight'][tokens[b].long()]
+        x = torch.cat([ce, tok], 0)
+        xs.append(x + w['mesh_decoder.model.embed_positions.weight'][:x.shape[0]])
+    h = torch.stack(xs)                                               # [B, N, C]
+    N = h.shape[1]
+    causal = torch.triu(torch.ones(N, N, dtype=torch.bool), 1)
+    valid = torch.ones(B, N, dtype=torch.bool) if masks is None else masks.bool()
+    md = 'mesh_decoder.model.layers.'
+    for i in range(NL):
+        lp = md + '%d.' % i
+
+        def lin(x, name):
+            return x @ w[lp + name + '.weight'].t() + w[lp + name + '.bias']
+        q = lin(h, 'self_attn.q_proj').view(B, N, H, D).transpose(1, 2)
+        k = lin(h, 'self_attn.k_proj').view(B, N, H, D).transpose(1, 2)
+        v = lin(h, 'self_attn.v_proj').view(B, N, H, D).transpose(1, 2)
+        s = (q @ k.transpose(-1, -2)) / (D ** 0.5)
+        s = s.masked_fill(causal, float('-inf'))
+        a = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, N, C)
+        a = a * valid[..., None]                                      # pad_input: masked rows are zeros
+        o = _dropout(lin(a, 'self_attn.out_proj'), seed, 2 * i, dropout_p)
+        h = F.layer_norm(h + o, (C,), w[lp + 'self_attn_layer_norm.weight'], w[lp + 'self_attn_layer_norm.bias'], 1e-5)
+        f = _dropout(lin(torch.relu(lin(h, 'fc1')), 'fc2'), seed, 2 * i + 1, dropout_p)
+        h = F.layer_norm(h + f, (C,), w[lp + 'final_layer_norm.weight'], w[lp + 'final_layer_norm.bias'], 1e-5)
+    logits = h @ w['mesh_decoder.lm_head.weight'].t()
+    V = logits.shape[-1]
+    loss_ce = F.cross_entropy(logits[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1).long(), ignore_index=-100)
+    out = dict(loss_ce=loss_ce, loss=loss_ce)
+    if opt.cond_mode == 'point':
+        out['loss_kl'] = 0.5 * torch.sum(lat_all.float() ** 2)
+        out['loss'] = loss_ce + opt.kl_weight * out['loss_kl']
+    return out
