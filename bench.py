@@ -394,7 +394,7 @@ def run_train(args):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic', 'loss_history': hist,
         'config': {'workload': f'ArAE training step B={B}/GPU N={N} (P={P} + T={T}): training forward (dropout {tr.dropout_p}) + backward with per-layer '
                                f'recomputation + flat gradient all-reduce x{world} + clip + fused AdamW + fp16 weight refresh',
-                   'trainable_parameters': int(tr.numel), 'l2': f'activations of {B * N} rows x 1536 exceed L2'},
+                   'trainable_parameters': int(tr.numel), 'debug': args.debug, 'l2': f'activations of {B * N} rows x 1536 exceed L2'},
         'clocks': clocks, 'gpu_launches': int(tr.engine.kernel_launches() - l0),
         'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'traffic': None,
                      'kernel': 'er::tc::gemm_tcgen05_kernel (forward, dgrad, wgrad) + er::fa::attention_tcgen05_kernel + er::bw::attn_bwd_* (wmma)',
@@ -621,6 +621,7 @@ def main():
     ap.add_argument('--dit-pipeline', action='store_true', help='--workload dit: also time one image end to end (MDiT.run -> LMM.generate) at the preset sizes')
     ap.add_argument('--workload', default='decode', choices=['decode', 'tf', 'dit', 'train'],
                     help="decode = BASELINE configs[1] (the metric); tf = configs[3]: teacher-forced forward seq 8192 batch 4/GPU, loss all-reduced over NCCL")
+    ap.add_argument('--debug', action='append', default=[], metavar='KEY=VALUE', help='process-wide experiment switch of the library (er_debug_set(NULL, KEY, VALUE)), e.g. attn_bwd_wmma=1')
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner under torchrun) is sent to stderr instead
     global _STDOUT_FD
@@ -628,6 +629,10 @@ def main():
     _STDOUT_FD = os.dup(1)
     os.dup2(2, 1)
 
+    for kv in args.debug:
+        from edgerunner_b200 import _lib
+        k, v = kv.split('=')
+        _lib.check(_lib.load().er_debug_set(None, k.encode(), int(v)))
     if args.impl == 'reference':
         (run_dit_reference_arm if args.workload == 'dit' else run_reference_arm)(args)
         return

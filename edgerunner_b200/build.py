@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libedgerunner_b200.so')
-SOURCES = ['engine.cu', 'decode_kernel.cu', 'gemm.cu', 'gemm_tcgen05.cu', 'attention.cu', 'attention_tcgen05.cu', 'elementwise.cu', 'dit.cu', 'optim.cu', 'backward.cu', 'train.cu', 'meto.cpp', 'meto_encode.cpp', 'mesh_clean.cpp']
+SOURCES = ['engine.cu', 'decode_kernel.cu', 'gemm.cu', 'gemm_tcgen05.cu', 'attention.cu', 'attention_tcgen05.cu', 'elementwise.cu', 'dit.cu', 'optim.cu', 'backward.cu', 'attention_bwd_mma.cu', 'train.cu', 'meto.cpp', 'meto_encode.cpp', 'mesh_clean.cpp']
 HEADERS = ['common.cuh', 'decode_kernel.h', 'decode_partition.h', 'kernels.h', 'engine_internal.h', os.path.join('..', '..', 'include', 'edgerunner_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']

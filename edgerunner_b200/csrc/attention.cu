@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnArgs a) {
         const int row = qrow0 + r * 8;
         if (row >= a.Nq) continue;
         const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+        if (a.lse2 && tq == 0) a.lse2[((size_t)b * a.H + h) * a.Nq + row] = m_run[r] * sl2 + log2f(l_run[r]);
 #pragma unroll
         for (int i = 0; i < D / 8; i++) {
             const uint32_t v = pack_h2(o[i][r * 2] * inv, o[i][r * 2 + 1] * inv);

@@ -114,6 +114,7 @@ struct Args {
     __half* out; long long o_bs; int ldo;
     int B, H, Nq, Nk, causal;
     float scale_log2;        // softmax scale * log2(e)
+    float* lse2;             // optional [B][H][Nq]: m * scale_log2 + log2(l) of every row (the training backward's softmax statistic)
 };
 
 template <int D>
@@ -322,6 +323,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         {   // every lane takes part in the TMEM loads; only rows inside the tile store
             const float l = xsum[r];
             const float inv = l > 0.f ? 1.f / l : 0.f;
+            if (a.lse2 && half == 0 && qi < a.Nq) a.lse2[((size_t)b * a.H + h) * a.Nq + qi] = m_ref * a.scale_log2 + log2f(l);
             __half* op = a.out + (size_t)b * a.o_bs + (size_t)qi * a.ldo + (size_t)h * D + half * DH;
 #pragma unroll
             for (int c0 = 0; c0 < DH; c0 += 16) {
@@ -374,6 +376,7 @@ static cudaError_t launch(const er::AttnArgs& a, cudaStream_t stream) {
     Args g{};
     g.out = a.out; g.o_bs = a.o_bs; g.ldo = a.ldo; g.B = a.B; g.H = a.H; g.Nq = a.Nq; g.Nk = a.Nk; g.causal = a.causal;
     g.scale_log2 = rsqrtf((float)D) * 1.4426950408889634f;
+    g.lse2 = a.lse2;
     constexpr int NA = (D + 63) / 64;
     constexpr int NB = (D <= 64) ? 2 : 1;
     const size_t smem = (size_t)NA * ATOM_Q + 2 * (size_t)NB * NA * ATOM_K + 2 * (size_t)BQ * 128 + 1024;

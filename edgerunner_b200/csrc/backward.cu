@@ -243,16 +243,6 @@ constexpr int BT = 64;          // tile rows (queries or keys)
 constexpr int SLD = BT + 4;     // fp32 scratch pitch
 constexpr int HLD = BT + 8;     // fp16 scratch pitch
 
-struct AttnBwdArgs {
-    const __half *q, *k, *v, *o, *dout;      // q/k/v with row pitch ld_qkv, o / dout with row pitch ld_o
-    __half *dq, *dk, *dv;                    // row pitch ld_dqkv
-    float *lse2, *dsum;                      // [B][H][Nq]: log2-domain log-sum-exp of the scaled scores, rowsum(dO * O)
-    long long q_bs, k_bs, v_bs, o_bs, dq_bs, dk_bs, dv_bs;
-    int ld_qkv_q, ld_qkv_k, ld_qkv_v, ld_o, ld_dq, ld_dk, ld_dv;
-    int B, H, Nq, Nk, causal;
-    float scale, scale_log2;                 // 1/sqrt(D), scale * log2(e)
-};
-
 template <int D>
 __device__ __forceinline__ void load_tile(__half* dst, const __half* src, int ld, int row0, int nrows_total) {
     // 64 rows x D fp16 -> dst [64][D + 8]; rows >= nrows_total are zero.  128 threads, 16-byte vectors.
@@ -506,6 +496,27 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdArgs p) 
     store_rows<D>(dv, STf, p.dv + (size_t)b * p.dv_bs + h * D, p.ld_dv, kt * BT + warp * 16, p.Nk);
 }
 
+// dsum[b][h][r] = sum_d dO[r][h*D + d] * O[r][h*D + d]: one warp per (row, head)
+template <int D>
+__global__ void attn_rowdot_kernel(const AttnBwdArgs p) {
+    const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const size_t total = (size_t)p.B * p.Nq * p.H;
+    if (w >= total) return;
+    const int h = (int)(w % p.H);
+    const size_t br = w / p.H;
+    const int r = (int)(br % p.Nq), b = (int)(br / p.Nq);
+    const __half* op = p.o + (size_t)b * p.o_bs + (size_t)r * p.ld_o + h * D;
+    const __half* dp = p.dout + (size_t)b * p.o_bs + (size_t)r * p.ld_o + h * D;
+    float a = 0.f;
+    for (int c = lane * 2; c < D; c += 64) {
+        const float2 x = __half22float2(*reinterpret_cast<const __half2*>(op + c)), y = __half22float2(*reinterpret_cast<const __half2*>(dp + c));
+        a += x.x * y.x + x.y * y.y;
+    }
+    a = warp_sum(a);
+    if (lane == 0) p.dsum[((size_t)b * p.H + h) * p.Nq + r] = a;
+}
+
 template <int D>
 static cudaError_t launch_attn_bwd(const AttnBwdArgs& p, cudaStream_t st) {
     const int smem = attn_bwd_smem<D>();
@@ -514,7 +525,8 @@ static cudaError_t launch_attn_bwd(const AttnBwdArgs& p, cudaStream_t st) {
     if ((e = cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
     const dim3 gq((p.Nq + BT - 1) / BT, p.H, p.B), gk((p.Nk + BT - 1) / BT, p.H, p.B);
-    attn_bwd_stats_kernel<D><<<gq, 128, smem, st>>>(p);
+    if (!p.have_lse) attn_bwd_stats_kernel<D><<<gq, 128, smem, st>>>(p);
+    else attn_rowdot_kernel<D><<<(unsigned)(((size_t)p.B * p.Nq * p.H + 7) / 8), 256, 0, st>>>(p);
     attn_bwd_dq_kernel<D><<<gq, 128, smem, st>>>(p);
     attn_bwd_dkv_kernel<D><<<gk, 128, smem, st>>>(p);
     return cudaGetLastError();
@@ -591,6 +603,17 @@ cudaError_t er_export_f32(const float* src, int ld, int rows, int cols, float sc
     return cudaGetLastError();
 }
 
+// wmma version (first implementation; kept as the A/B reference of the register-resident kernels in attention_bwd_mma.cu)
+cudaError_t er_attn_bwd_wmma(const er::AttnBwdArgs& p, int D, cudaStream_t st) { return D == 96 ? launch_attn_bwd<96>(p, st) : launch_attn_bwd<64>(p, st); }
+
+int g_er_attn_bwd_wmma = 0;     // er_debug_set(NULL, "attn_bwd_wmma", 1): use the wmma kernels of this file
+
+cudaError_t er_attn_rowdot(const er::AttnBwdArgs& p, int D, cudaStream_t st) {
+    const unsigned grid = (unsigned)(((size_t)p.B * p.Nq * p.H + 7) / 8);
+    if (D == 96) attn_rowdot_kernel<96><<<grid, 256, 0, st>>>(p); else attn_rowdot_kernel<64><<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t er_attention_bwd(const er::AttnArgs& a, const __half* dout, __half* dq, __half* dk, __half* dv, int ld_dq, int ld_dk, int ld_dv, long long dq_bs,
                              long long dk_bs, long long dv_bs, float* lse2, float* dsum, cudaStream_t st) {
     if (a.B <= 0 || a.Nq <= 0 || a.Nk <= 0) return cudaSuccess;
@@ -604,5 +627,6 @@ cudaError_t er_attention_bwd(const er::AttnArgs& a, const __half* dout, __half* 
     p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.causal = a.causal;
     p.scale = 1.f / sqrtf((float)a.D);
     p.scale_log2 = p.scale * 1.4426950408889634f;
-    return a.D == 96 ? launch_attn_bwd<96>(p, st) : launch_attn_bwd<64>(p, st);
+    p.have_lse = a.lse2 != nullptr && a.lse2 == lse2;      // the forward described by `a` already wrote the row statistic into the same buffer
+    return g_er_attn_bwd_wmma ? er_attn_bwd_wmma(p, a.D, st) : er_attn_bwd_mma(p, a.D, st);
 }

@@ -35,6 +35,18 @@ struct AttnArgs {   // softmax(q k^T / sqrt(D)) v ; q [B][Nq][H][D], k/v [B][Nk]
     long long q_bs, k_bs, v_bs, o_bs;   // batch strides (elements)
     int ldq, ldk, ldv, ldo;             // row strides (elements); head h starts at h*D inside a row
     int B, H, Nq, Nk, D, causal;
+    float* lse2;                        // optional output [B][H][Nq]: log2-domain log-sum-exp of the scaled scores (training: saves the backward's statistics pass)
+};
+
+struct AttnBwdArgs {
+    const __half *q, *k, *v, *o, *dout;      // q/k/v with row pitch ld_qkv, o / dout with row pitch ld_o
+    __half *dq, *dk, *dv;                    // row pitch ld_dqkv
+    float *lse2, *dsum;                      // [B][H][Nq]: log2-domain log-sum-exp of the scaled scores, rowsum(dO * O)
+    long long q_bs, k_bs, v_bs, o_bs, dq_bs, dk_bs, dv_bs;
+    int ld_qkv_q, ld_qkv_k, ld_qkv_v, ld_o, ld_dq, ld_dk, ld_dv;
+    int B, H, Nq, Nk, causal;
+    float scale, scale_log2;                 // 1/sqrt(D), scale * log2(e)
+    int have_lse;                            // lse2 was written by the forward kernel: skip the statistics pass, compute dsum only
 };
 
 }  // namespace er
@@ -100,3 +112,7 @@ cudaError_t er_export_f32(const float* src, int ld, int rows, int cols, float sc
 // lse2, dsum: scratch of B * H * Nq floats each
 cudaError_t er_attention_bwd(const er::AttnArgs& a, const __half* dout, __half* dq, __half* dk, __half* dv, int ld_dq, int ld_dk, int ld_dv, long long dq_bs,
                              long long dk_bs, long long dv_bs, float* lse2, float* dsum, cudaStream_t st);
+cudaError_t er_attn_bwd_wmma(const er::AttnBwdArgs& p, int D, cudaStream_t st);     // backward.cu: wmma through shared memory
+cudaError_t er_attn_bwd_mma(const er::AttnBwdArgs& p, int D, cudaStream_t st);      // attention_bwd_mma.cu: mma.sync, scores / dS in registers
+// dsum [B][H][Nq] = sum_d dO * O per (row, head): the only statistic the attention backward still needs when the forward wrote lse2
+cudaError_t er_attn_rowdot(const er::AttnBwdArgs& p, int D, cudaStream_t st);

@@ -40,6 +40,8 @@ struct er_train {
     std::vector<void*> row_allocs;      // the buffers sized by M (re-allocated when a larger batch arrives)
 };
 
+int g_er_train_fwd_lse = 0;     // er_debug_set(NULL, "train_fwd_lse", 1): the recomputed forward attention writes the row log-sum-exp, the backward skips its statistics pass
+
 static inline int round64(int x) { return (x + 63) / 64 * 64; }
 
 void er_train_destroy(er_engine* e) {
@@ -155,6 +157,7 @@ static int layer_fwd(er_engine* e, int l, const float* in32, const __half* in16,
     a.q = e->qkv16; a.k = e->qkv16 + C; a.v = e->qkv16 + 2 * C; a.out = e->a16;
     a.ldq = a.ldk = a.ldv = 3 * C; a.ldo = C; a.q_bs = a.k_bs = a.v_bs = (long long)N * 3 * C; a.o_bs = (long long)N * C;
     a.B = B; a.H = H; a.Nq = N; a.Nk = N; a.D = 96; a.causal = 1;
+    if (!out32 && g_er_train_fwd_lse) a.lse2 = t->lse2;         // backward recomputation: let the forward kernel leave the softmax statistic for the attention backward
     CKL(e, er_attention(a, st));
     if (row_mask) CKL(e, er_zero_masked_rows(e->a16, row_mask, M, C, st));
     g = mk_gemm(e->a16, C, e->wo + (size_t)l * C * C, C, e->bo + (size_t)l * C, M, C, C, er::GEMM_F16);
@@ -224,6 +227,7 @@ static int layer_bwd(er_engine* e, int l, int B, int N, const unsigned char* row
     a.q = e->qkv16; a.k = e->qkv16 + C; a.v = e->qkv16 + 2 * C; a.out = e->a16;
     a.ldq = a.ldk = a.ldv = 3 * C; a.ldo = C; a.q_bs = a.k_bs = a.v_bs = (long long)N * 3 * C; a.o_bs = (long long)N * C;
     a.B = B; a.H = H; a.Nq = N; a.Nk = N; a.D = 96; a.causal = 1;
+    if (g_er_train_fwd_lse) a.lse2 = t->lse2;
     e->launches += 2;
     CKL(e, er_attention_bwd(a, t->da16, t->dwide16, t->dwide16 + C, t->dwide16 + 2 * C, 3 * C, 3 * C, 3 * C, a.q_bs, a.q_bs, a.q_bs, t->lse2, t->dsum, st));
     // ---- q/k/v projections: g32a = g32b + dqkv Wqkv ----

@@ -1,11 +1,13 @@
 #!/bin/bash
 # One GPU call: every training-step test in its own process (a faulting kernel poisons only its own CUDA context), compute-sanitizer on the first
-# failure, then a short `bench.py --workload train` when everything passed.  Logs under gpurun_out/.
+# failure, then short `bench.py --workload train` runs of the variants.  Logs under gpurun_out/.
 mkdir -p gpurun_out
+rm -f gpurun_out/train_tests.log
 export CUDA_LAUNCH_BLOCKING=1
 fail=0
-for t in test_attention_backward_matches_autograd "test_train_step_gradients_match_autograd[point_latent]" "test_train_step_gradients_match_autograd[point]" \
-         test_train_step_with_dropout_and_padding test_train_step_mid_size test_lmm_train_mode_backward_and_optimizer_step test_flat_trainer_steps_reduce_the_loss; do
+for t in "test_attention_backward_matches_autograd[mma]" "test_attention_backward_matches_autograd[wmma]" "test_train_step_gradients_match_autograd[point]" \
+         test_train_step_with_dropout_and_padding "test_train_step_mid_size[mma]" "test_train_step_mid_size[mma+fwd_lse]" "test_train_step_mid_size[wmma]" \
+         "test_train_step_mid_size[wmma+fwd_lse]" test_flat_trainer_steps_reduce_the_loss; do
   echo "=== $t" >> gpurun_out/train_tests.log
   timeout 240 python -m pytest "tests/test_gpu_train.py::$t" -q -x 2>&1 | tail -40 >> gpurun_out/train_tests.log
   rc=${PIPESTATUS[0]}
@@ -17,9 +19,11 @@ for t in test_attention_backward_matches_autograd "test_train_step_gradients_mat
     fi
   fi
 done
-grep -E "^===|^rc=|passed|failed|Error|error" gpurun_out/train_tests.log | tail -40
+grep -E "^===|^rc=|passed|failed|Error|error|assert" gpurun_out/train_tests.log | tail -60
 unset CUDA_LAUNCH_BLOCKING
-if [ $fail -eq 0 ]; then
-  timeout 400 python bench.py --workload train --steps 2 --warmup 1 > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err
-  echo "bench rc=$?"; cat gpurun_out/bench_train.json; tail -5 gpurun_out/bench_train.err
-fi
+for v in "" "--debug train_fwd_lse=1"; do
+  timeout 300 python bench.py --workload train --steps 2 --warmup 1 $v > "gpurun_out/bench_train${v// /_}.json" 2> gpurun_out/bench_train.err
+  echo "bench [$v] rc=$?"; python -c "
+import json,sys
+d=json.load(open(sys.argv[1])); print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['loss_history'])" "gpurun_out/bench_train${v// /_}.json"; tail -3 gpurun_out/bench_train.err
+done

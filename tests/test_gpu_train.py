@@ -37,8 +37,35 @@ def _batch(opt, B=2, T=40, seed=0, pad=0):
     return conds, tokens, labels, masks, [1500, 5000, 300, 9000][:B]
 
 
-def test_attention_backward_matches_autograd():
-    """the attention() seam's backward (er_attention_bwd_bnhd) against autograd of the fp32 softmax attention on the same fp16 inputs"""
+class _debug:
+    """process-wide experiment switches of the library (er_debug_set(NULL, key, value)), restored on exit"""
+
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        from edgerunner_b200 import _lib
+        for k, v in self.kv.items():
+            _lib.check(_lib.load().er_debug_set(None, k.encode(), int(v)))
+
+    def __exit__(self, *exc):
+        from edgerunner_b200 import _lib
+        for k in self.kv:
+            _lib.check(_lib.load().er_debug_set(None, k.encode(), DEFAULTS[k]))
+
+
+DEFAULTS = {'attn_bwd_wmma': 0, 'train_fwd_lse': 0}
+
+
+@pytest.mark.parametrize('impl', ['mma', 'wmma'])
+def test_attention_backward_matches_autograd(impl):
+    """the attention() seam's backward (er_attention_bwd_bnhd) against autograd of the fp32 softmax attention on the same fp16 inputs; both
+    implementations: register-resident mma.sync (attention_bwd_mma.cu, the default) and wmma through shared memory (backward.cu)"""
+    with _debug(attn_bwd_wmma=impl == 'wmma'):
+        _attention_backward_cases()
+
+
+def _attention_backward_cases():
     from core.transformer.attention import attention
     from edgerunner_b200 import _lib
     lib = _lib.load()
@@ -134,8 +161,15 @@ def test_train_step_with_dropout_and_padding():
     assert losses2[1] != losses[1]
 
 
-def test_train_step_mid_size():
-    """hidden 768 / 8 heads / 3 layers, 2 x 300 rows: several attention tiles per head, GEMM K tails of the padded transposes"""
+@pytest.mark.parametrize('variant', ['mma', 'mma+fwd_lse', 'wmma', 'wmma+fwd_lse'])
+def test_train_step_mid_size(variant):
+    """hidden 768 / 8 heads / 3 layers, 2 x 300 rows: several attention tiles per head, GEMM K tails of the padded transposes; every variant of the
+    attention backward (mma.sync | wmma kernels; statistics pass | log-sum-exp written by the recomputed forward kernel)"""
+    with _debug(attn_bwd_wmma=variant.startswith('wmma'), train_fwd_lse=variant.endswith('fwd_lse')):
+        _mid_size()
+
+
+def _mid_size():
     opt = synth.tiny_options(hidden_dim=768, num_heads=8, num_layers=3, cond_mode='point_latent')
     sd = synth.synth_state_dict(opt, seed=3, eos_logit=-30.0)
     batch = _batch(opt, B=2, T=235, seed=2, pad=11)
