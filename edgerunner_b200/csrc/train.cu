@@ -40,7 +40,7 @@ struct er_train {
     std::vector<void*> row_allocs;      // the buffers sized by M (re-allocated when a larger batch arrives)
 };
 
-int g_er_train_fwd_lse = 0;     // er_debug_set(NULL, "train_fwd_lse", 1): the recomputed forward attention writes the row log-sum-exp, the backward skips its statistics pass
+int g_er_train_fwd_lse = 1;     // er_debug_set(NULL, "train_fwd_lse", 0): statistics pass in the backward instead of: the recomputed forward attention writes the row log-sum-exp, the backward skips its statistics pass
 
 static inline int round64(int x) { return (x + 63) / 64 * 64; }
 

@@ -54,7 +54,7 @@ class _debug:
             _lib.check(_lib.load().er_debug_set(None, k.encode(), DEFAULTS[k]))
 
 
-DEFAULTS = {'attn_bwd_wmma': 0, 'train_fwd_lse': 0}
+DEFAULTS = {'attn_bwd_wmma': 0, 'train_fwd_lse': 1}
 
 
 @pytest.mark.parametrize('impl', ['mma', 'wmma'])
