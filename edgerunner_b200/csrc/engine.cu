@@ -590,6 +590,7 @@ extern "C" int er_debug_set(er_engine* e, const char* key, int64_t value) {
     if (!key) return set_err(ER_ERR_INVALID, "null key");
     const std::string k = key;
     if (k == "poison_alloc") { g_poison_alloc = (int)value; return ER_OK; }      // process-wide; e may be NULL
+    if (k == "train_recompute") { extern int g_er_train_recompute; g_er_train_recompute = value != 0; return ER_OK; }   // process-wide: per-layer recomputation (opt.checkpointing)
     if (k == "train_fwd_lse") { extern int g_er_train_fwd_lse; g_er_train_fwd_lse = value != 0; return ER_OK; }   // process-wide: forward-written softmax statistic in the training backward
     if (k == "attn_bwd_wmma") { extern int g_er_attn_bwd_wmma; g_er_attn_bwd_wmma = value != 0; return ER_OK; }   // process-wide: wmma attention backward (A/B)
     if (k == "dense_legacy") { extern int g_er_dense_legacy; g_er_dense_legacy = value != 0; return ER_OK; }   // process-wide: mma.sync GEMM / attention

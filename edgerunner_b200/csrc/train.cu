@@ -19,6 +19,10 @@
 #include <algorithm>
 
 struct GradSlot { float* ptr; int rows, cols, ld; };
+// what the backward of one decoder layer reads from its forward: q|k|v, the attention output (+ its row log-sum-exp), the two pre-LayerNorm sums,
+// LN1's fp16 output, the ReLU output.  Either one set per layer (kept from the forward pass: 1.6 GB per layer at 4 x 10 243 rows — 180 GB of HBM
+// make the reference's per-layer recomputation unnecessary) or ONE set refilled by re-running the layer (opt.checkpointing, when memory is short).
+struct LayerAct { __half *qkv16, *a16, *x1_16, *h16; float *s1, *s2, *lse2; };
 
 struct er_train {
     int M_cap = 0, Mp = 0, B_cap = 0;
@@ -38,9 +42,14 @@ struct er_train {
     int Vp = 0, wide = 0;
     bool have_grads = false;
     std::vector<void*> row_allocs;      // the buffers sized by M (re-allocated when a larger batch arrives)
+    bool store = false;                 // activations of every layer kept from the forward pass (else: recomputed per layer in the backward pass)
+    std::vector<LayerAct> acts;         // NL sets (store) or one
+    __half *qkv_all = nullptr, *a_all = nullptr, *x1_all = nullptr, *h_all = nullptr; float *s1_all = nullptr, *s2_all = nullptr, *lse_all = nullptr;
 };
 
 int g_er_train_fwd_lse = 1;     // er_debug_set(NULL, "train_fwd_lse", 0): statistics pass in the backward instead of: the recomputed forward attention writes the row log-sum-exp, the backward skips its statistics pass
+
+int g_er_train_recompute = 0;   // er_debug_set(NULL, "train_recompute", 1): per-layer recomputation in the backward pass (the reference's opt.checkpointing) even when memory allows keeping the activations
 
 static inline int round64(int x) { return (x + 63) / 64 * 64; }
 
@@ -120,7 +129,17 @@ static int ensure_train(er_engine* e, int M, int B) {
     if (!e->train) { int r = create_train(e); if (r) return r; }
     er_train* t = e->train;
     if (B > 4096) return set_err(ER_ERR_CAPACITY, "batch too large");
-    if (M <= t->M_cap && B <= t->B_cap) return ER_OK;
+    const size_t per_layer = (size_t)M * ((size_t)e->C * (3 + 1 + 1) * 2 + (size_t)e->F * 2 + (size_t)e->C * 2 * 4 + (size_t)e->H * 4);
+    bool want_store = !g_er_train_recompute;
+    if (want_store && !(M <= t->M_cap && B <= t->B_cap && t->store)) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t mine = 0;                      // what the current row buffers would give back
+        if (t->M_cap) mine = (size_t)t->M_cap * e->C * 4 * (e->NL + 8) + (t->store ? (size_t)e->NL * per_layer / M * t->M_cap : 0);
+        const size_t need = (size_t)e->NL * per_layer + (size_t)M * e->C * 4 * (e->NL + 12) + (size_t)3 * round64(M) * t->wide * 2 + ((size_t)3 << 30);
+        if (free_b + mine < need) want_store = false;
+    }
+    if (M <= t->M_cap && B <= t->B_cap && want_store == t->store) return ER_OK;
     CK(cudaDeviceSynchronize());
     for (void* p : t->row_allocs) {
         for (auto it = e->allocs.begin(); it != e->allocs.end(); ++it)
@@ -141,35 +160,44 @@ static int ensure_train(er_engine* e, int M, int B) {
     RALLOC(t->dl16, Mc * t->Vp);
     RALLOC(t->lse2, Mc * H); RALLOC(t->dsum, Mc * H); RALLOC(t->mean, Mc); RALLOC(t->rstd, Mc);
     RALLOC(t->pc16_all, RL * C); RALLOC(t->dpc16, RL * C); RALLOC(t->dcond32, RL * C);
+    t->store = want_store;
+    t->acts.assign(want_store ? NL : 1, LayerAct{});
+    if (want_store) {
+        RALLOC(t->qkv_all, NL * Mc * 3 * C); RALLOC(t->a_all, NL * Mc * C); RALLOC(t->x1_all, NL * Mc * C); RALLOC(t->h_all, NL * Mc * F);
+        RALLOC(t->s1_all, NL * Mc * C); RALLOC(t->s2_all, NL * Mc * C); RALLOC(t->lse_all, NL * Mc * H);
+        for (size_t l = 0; l < NL; l++)
+            t->acts[l] = LayerAct{t->qkv_all + l * Mc * 3 * C, t->a_all + l * Mc * C, t->x1_all + l * Mc * C, t->h_all + l * Mc * F,
+                                  t->s1_all + l * Mc * C, t->s2_all + l * Mc * C, t->lse_all + l * Mc * H};
+    }
     t->M_cap = (int)Mc; t->Mp = (int)Mp; t->B_cap = (int)Bc;
     return ER_OK;
 }
 
-// one OPTDecoderLayer in training mode (modeling_opt.py:264-288): in32/in16 -> out32/out16 (skipped when out32 is null: backward recomputation).
-// Leaves qkv16, a16, h16 in the dense workspace and s1, x1_32, x1_16, s2 in the training state.
-static int layer_fwd(er_engine* e, int l, const float* in32, const __half* in16, float* out32, __half* out16, int B, int N, const unsigned char* row_mask,
-                     float p, unsigned long long seed, cudaStream_t st) {
+// one OPTDecoderLayer in training mode (modeling_opt.py:264-288): in32/in16 -> out32/out16 (skipped when out32 is null: backward recomputation);
+// what the backward needs goes to `act`.  want_lse: the attention kernel also writes the rows' log-sum-exp (act.lse2).
+static int layer_fwd(er_engine* e, int l, const LayerAct& act, const float* in32, const __half* in16, float* out32, __half* out16, int B, int N,
+                     const unsigned char* row_mask, float p, unsigned long long seed, bool want_lse, cudaStream_t st) {
     er_train* t = e->train;
     const int C = e->C, F = e->F, H = e->H, M = B * N;
     er::GemmArgs g = mk_gemm(in16, C, e->wqkv + (size_t)l * 3 * C * C, C, e->bqkv + (size_t)l * 3 * C, M, 3 * C, C, er::GEMM_F16);
-    g.out16 = e->qkv16; g.ldo = 3 * C; CKL(e, er_gemm(g, st));
+    g.out16 = act.qkv16; g.ldo = 3 * C; CKL(e, er_gemm(g, st));
     er::AttnArgs a{};
-    a.q = e->qkv16; a.k = e->qkv16 + C; a.v = e->qkv16 + 2 * C; a.out = e->a16;
+    a.q = act.qkv16; a.k = act.qkv16 + C; a.v = act.qkv16 + 2 * C; a.out = act.a16;
     a.ldq = a.ldk = a.ldv = 3 * C; a.ldo = C; a.q_bs = a.k_bs = a.v_bs = (long long)N * 3 * C; a.o_bs = (long long)N * C;
     a.B = B; a.H = H; a.Nq = N; a.Nk = N; a.D = 96; a.causal = 1;
-    if (!out32 && g_er_train_fwd_lse) a.lse2 = t->lse2;         // backward recomputation: let the forward kernel leave the softmax statistic for the attention backward
+    if (want_lse) a.lse2 = act.lse2;
     CKL(e, er_attention(a, st));
-    if (row_mask) CKL(e, er_zero_masked_rows(e->a16, row_mask, M, C, st));
-    g = mk_gemm(e->a16, C, e->wo + (size_t)l * C * C, C, e->bo + (size_t)l * C, M, C, C, er::GEMM_F16);
+    if (row_mask) CKL(e, er_zero_masked_rows(act.a16, row_mask, M, C, st));
+    g = mk_gemm(act.a16, C, e->wo + (size_t)l * C * C, C, e->bo + (size_t)l * C, M, C, C, er::GEMM_F16);
     g.out16 = t->o16; g.ldo = C; CKL(e, er_gemm(g, st));
-    CKL(e, er_add_dropout(in32, t->o16, t->s1, (size_t)M * C, p, seed, 2 * l, st));
-    CKL(e, er_layernorm(t->s1, nullptr, C, e->ln1w + (size_t)l * C, e->ln1b + (size_t)l * C, t->x1_32, t->x1_16, C, M, C, st));
-    g = mk_gemm(t->x1_16, C, e->w1 + (size_t)l * F * C, C, e->b1 + (size_t)l * F, M, F, C, er::GEMM_F16_RELU);
-    g.out16 = e->h16; g.ldo = F; CKL(e, er_gemm(g, st));
-    g = mk_gemm(e->h16, F, e->w2 + (size_t)l * C * F, F, e->b2 + (size_t)l * C, M, C, F, er::GEMM_F16);
+    CKL(e, er_add_dropout(in32, t->o16, act.s1, (size_t)M * C, p, seed, 2 * l, st));
+    CKL(e, er_layernorm(act.s1, nullptr, C, e->ln1w + (size_t)l * C, e->ln1b + (size_t)l * C, t->x1_32, act.x1_16, C, M, C, st));
+    g = mk_gemm(act.x1_16, C, e->w1 + (size_t)l * F * C, C, e->b1 + (size_t)l * F, M, F, C, er::GEMM_F16_RELU);
+    g.out16 = act.h16; g.ldo = F; CKL(e, er_gemm(g, st));
+    g = mk_gemm(act.h16, F, e->w2 + (size_t)l * C * F, F, e->b2 + (size_t)l * C, M, C, F, er::GEMM_F16);
     g.out16 = t->o16; g.ldo = C; CKL(e, er_gemm(g, st));
-    CKL(e, er_add_dropout(t->x1_32, t->o16, t->s2, (size_t)M * C, p, seed, 2 * l + 1, st));
-    if (out32) CKL(e, er_layernorm(t->s2, nullptr, C, e->ln2w + (size_t)l * C, e->ln2b + (size_t)l * C, out32, out16, C, M, C, st));
+    CKL(e, er_add_dropout(t->x1_32, t->o16, act.s2, (size_t)M * C, p, seed, 2 * l + 1, st));
+    if (out32) CKL(e, er_layernorm(act.s2, nullptr, C, e->ln2w + (size_t)l * C, e->ln2b + (size_t)l * C, out32, out16, C, M, C, st));
     return ER_OK;
 }
 
@@ -199,37 +227,41 @@ static int layer_bwd(er_engine* e, int l, int B, int N, const unsigned char* row
     er_train* t = e->train;
     const int C = e->C, F = e->F, H = e->H, M = B * N;
     const float* in32 = t->ckpt + (size_t)l * M * C;
-    // recompute the layer from its checkpointed input (x16 = the fp16 copy the forward pass used)
+    const LayerAct& act = t->store ? t->acts[l] : t->acts[0];
+    // x16 = the fp16 copy of the layer input the forward pass used (operand of the q/k/v weight gradient)
     CKL(e, er_f32_to_f16(in32, e->x16, (size_t)M * C, st));
-    { int r = layer_fwd(e, l, in32, e->x16, nullptr, nullptr, B, N, row_mask, p, seed, st); if (r) return r; }
+    if (!t->store) {        // opt.checkpointing: re-run the layer from its checkpointed input
+        int r = layer_fwd(e, l, act, in32, e->x16, nullptr, nullptr, B, N, row_mask, p, seed, g_er_train_fwd_lse != 0, st);
+        if (r) return r;
+    }
     // ---- final_layer_norm: g32a = dL/d(out) -> g32b = dL/d(s2); dbr16 = dL/d(fc2 output) ----
-    CKL(e, er_ln_bwd(t->g32a, t->s2, nullptr, C, e->ln2w + (size_t)l * C, t->g32b, t->dbr16, t->mean, t->rstd, M, C, p, seed, 2 * l + 1, st));
-    CKL(e, er_ln_param_grad(t->g32a, t->s2, nullptr, C, t->mean, t->rstd, M, C, t->partial, t->gln2w + (size_t)l * C, t->gln2b + (size_t)l * C, st));
+    CKL(e, er_ln_bwd(t->g32a, act.s2, nullptr, C, e->ln2w + (size_t)l * C, t->g32b, t->dbr16, t->mean, t->rstd, M, C, p, seed, 2 * l + 1, st));
+    CKL(e, er_ln_param_grad(t->g32a, act.s2, nullptr, C, t->mean, t->rstd, M, C, t->partial, t->gln2w + (size_t)l * C, t->gln2b + (size_t)l * C, st));
     // ---- fc2 ----
     CKL(e, er_colsum_f16(t->dbr16, C, M, C, t->partial, t->gb2 + (size_t)l * C, st));
     { int r = dgrad(e, t->dbr16, C, C, e->w2 + (size_t)l * C * F, F, M, er::GEMM_F16, t->dwide16, nullptr, nullptr, st); if (r) return r; }
-    { int r = wgrad(e, t->dbr16, C, C, e->h16, F, F, M, t->gw2 + (size_t)l * C * F, F, st); if (r) return r; }
-    CKL(e, er_relu_bwd(t->dwide16, e->h16, (size_t)M * F, st));
+    { int r = wgrad(e, t->dbr16, C, C, act.h16, F, F, M, t->gw2 + (size_t)l * C * F, F, st); if (r) return r; }
+    CKL(e, er_relu_bwd(t->dwide16, act.h16, (size_t)M * F, st));
     // ---- fc1: g32a = g32b + dh W1 ----
     CKL(e, er_colsum_f16(t->dwide16, F, M, F, t->partial, t->gb1 + (size_t)l * F, st));
     { int r = dgrad(e, t->dwide16, F, F, e->w1 + (size_t)l * F * C, C, M, er::GEMM_F32_RES32, nullptr, t->g32a, t->g32b, st); if (r) return r; }
-    { int r = wgrad(e, t->dwide16, F, F, t->x1_16, C, C, M, t->gw1 + (size_t)l * F * C, C, st); if (r) return r; }
+    { int r = wgrad(e, t->dwide16, F, F, act.x1_16, C, C, M, t->gw1 + (size_t)l * F * C, C, st); if (r) return r; }
     // ---- self_attn_layer_norm ----
-    CKL(e, er_ln_bwd(t->g32a, t->s1, nullptr, C, e->ln1w + (size_t)l * C, t->g32b, t->dbr16, t->mean, t->rstd, M, C, p, seed, 2 * l, st));
-    CKL(e, er_ln_param_grad(t->g32a, t->s1, nullptr, C, t->mean, t->rstd, M, C, t->partial, t->gln1w + (size_t)l * C, t->gln1b + (size_t)l * C, st));
+    CKL(e, er_ln_bwd(t->g32a, act.s1, nullptr, C, e->ln1w + (size_t)l * C, t->g32b, t->dbr16, t->mean, t->rstd, M, C, p, seed, 2 * l, st));
+    CKL(e, er_ln_param_grad(t->g32a, act.s1, nullptr, C, t->mean, t->rstd, M, C, t->partial, t->gln1w + (size_t)l * C, t->gln1b + (size_t)l * C, st));
     // ---- out_proj ----
     CKL(e, er_colsum_f16(t->dbr16, C, M, C, t->partial, t->gbo + (size_t)l * C, st));
     { int r = dgrad(e, t->dbr16, C, C, e->wo + (size_t)l * C * C, C, M, er::GEMM_F16, t->da16, nullptr, nullptr, st); if (r) return r; }
-    { int r = wgrad(e, t->dbr16, C, C, e->a16, C, C, M, t->gwo + (size_t)l * C * C, C, st); if (r) return r; }
+    { int r = wgrad(e, t->dbr16, C, C, act.a16, C, C, M, t->gwo + (size_t)l * C * C, C, st); if (r) return r; }
     if (row_mask) CKL(e, er_zero_masked_rows(t->da16, row_mask, M, C, st));         // backward of pad_input's zero rows
     // ---- attention ----
     er::AttnArgs a{};
-    a.q = e->qkv16; a.k = e->qkv16 + C; a.v = e->qkv16 + 2 * C; a.out = e->a16;
+    a.q = act.qkv16; a.k = act.qkv16 + C; a.v = act.qkv16 + 2 * C; a.out = act.a16;
     a.ldq = a.ldk = a.ldv = 3 * C; a.ldo = C; a.q_bs = a.k_bs = a.v_bs = (long long)N * 3 * C; a.o_bs = (long long)N * C;
     a.B = B; a.H = H; a.Nq = N; a.Nk = N; a.D = 96; a.causal = 1;
-    if (g_er_train_fwd_lse) a.lse2 = t->lse2;
+    if (g_er_train_fwd_lse) a.lse2 = act.lse2;          // written by the forward kernel of this layer: no statistics pass
     e->launches += 2;
-    CKL(e, er_attention_bwd(a, t->da16, t->dwide16, t->dwide16 + C, t->dwide16 + 2 * C, 3 * C, 3 * C, 3 * C, a.q_bs, a.q_bs, a.q_bs, t->lse2, t->dsum, st));
+    CKL(e, er_attention_bwd(a, t->da16, t->dwide16, t->dwide16 + C, t->dwide16 + 2 * C, 3 * C, 3 * C, 3 * C, a.q_bs, a.q_bs, a.q_bs, act.lse2, t->dsum, st));
     // ---- q/k/v projections: g32a = g32b + dqkv Wqkv ----
     CKL(e, er_colsum_f16(t->dwide16, 3 * C, M, 3 * C, t->partial, t->gbqkv + (size_t)l * 3 * C, st));
     { int r = dgrad(e, t->dwide16, 3 * C, 3 * C, e->wqkv + (size_t)l * 3 * C * C, C, M, er::GEMM_F32_RES32, nullptr, t->g32a, t->g32b, st); if (r) return r; }
@@ -264,8 +296,10 @@ extern "C" int er_train_step(er_engine* e, const float* conds_dev, int32_t n_poi
         bucket[b] = er_quantize_num_faces(num_faces_host[b]);
     }
     CK(cudaMemcpyAsync(t->bucket_dev, bucket.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    if (!t->store) t->acts[0] = LayerAct{e->qkv16, e->a16, t->x1_16, e->h16, t->s1, t->s2, t->lse2};     // the dense workspace (it may have been re-allocated)
     for (int l = 0; l < NL; l++) {
-        int r = layer_fwd(e, l, t->ckpt + (size_t)l * M * C, e->x16, t->ckpt + (size_t)(l + 1) * M * C, e->x16, B, N, mask_dev, dropout_p, seed, st);
+        int r = layer_fwd(e, l, t->store ? t->acts[l] : t->acts[0], t->ckpt + (size_t)l * M * C, e->x16, t->ckpt + (size_t)(l + 1) * M * C, e->x16, B, N,
+                          mask_dev, dropout_p, seed, t->store && g_er_train_fwd_lse, st);
         if (r) return r;
     }
     er::GemmArgs g = mk_gemm(e->x16, C, e->lm_head, C, nullptr, M, V, C, er::GEMM_F32);

@@ -54,7 +54,7 @@ class _debug:
             _lib.check(_lib.load().er_debug_set(None, k.encode(), DEFAULTS[k]))
 
 
-DEFAULTS = {'attn_bwd_wmma': 0, 'train_fwd_lse': 1}
+DEFAULTS = {'attn_bwd_wmma': 0, 'train_fwd_lse': 1, 'train_recompute': 0}
 
 
 @pytest.mark.parametrize('impl', ['mma', 'wmma'])
@@ -161,11 +161,12 @@ def test_train_step_with_dropout_and_padding():
     assert losses2[1] != losses[1]
 
 
-@pytest.mark.parametrize('variant', ['mma', 'mma+fwd_lse', 'wmma', 'wmma+fwd_lse'])
+@pytest.mark.parametrize('variant', ['default', 'stats_pass', 'wmma', 'recompute', 'recompute+stats_pass', 'recompute+wmma'])
 def test_train_step_mid_size(variant):
-    """hidden 768 / 8 heads / 3 layers, 2 x 300 rows: several attention tiles per head, GEMM K tails of the padded transposes; every variant of the
-    attention backward (mma.sync | wmma kernels; statistics pass | log-sum-exp written by the recomputed forward kernel)"""
-    with _debug(attn_bwd_wmma=variant.startswith('wmma'), train_fwd_lse=variant.endswith('fwd_lse')):
+    """hidden 768 / 8 heads / 3 layers, 2 x 300 rows: several attention tiles per head, padded transposes; every variant of the backward:
+    activations kept from the forward pass (default) | per-layer recomputation (the reference's opt.checkpointing); attention backward with
+    mma.sync (default) | wmma kernels; row log-sum-exp from the forward kernel (default) | from a statistics pass"""
+    with _debug(attn_bwd_wmma='wmma' in variant, train_fwd_lse='stats_pass' not in variant, train_recompute='recompute' in variant):
         _mid_size()
 
 
