@@ -207,7 +207,7 @@ def run_reference_arm(args):
 def run_teacher_forced(args):
     """BASELINE configs[3]: ArAE teacher-forced forward, seq_len 8192 (+ 2049 condition rows + BOS/EOS = 10 243 rows), batch 4 per GPU, data
     parallel: every rank runs the forward on its own batch through LMM.forward, ONE NCCL all-reduce of the fp64 {ce_sum, n_tokens, kl}.  Forward
-    only (no backward exists: DESIGN.md §6).  value = supervised tokens/s over all ranks; roofline: tensor-bound, algorithmic FLOPs
+    only (the full training step is `--workload train`).  value = supervised tokens/s over all ranks; roofline: tensor-bound, algorithmic FLOPs
     against MEASURED_PEAKS bf16_tflops_sustained."""
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     dev = torch.device('cuda', local_rank)
@@ -242,7 +242,8 @@ def run_teacher_forced(args):
             dist.barrier()
         torch.cuda.synchronize()
     # SURVEY §8e / BASELINE configs[3] "grad all-reduce": the flattened fp32 gradient buffer of the model's parameter count, all-reduced over
-    # NCCL in 4 reverse-order slices per step, launched before the forward so that it overlaps it.  SYNTHETIC gradients: no backward exists.
+    # NCCL in 4 reverse-order slices per step, launched before the forward so that it overlaps it.  SYNTHETIC gradients: this workload is forward only
+    # (`--workload train` all-reduces the real ones).
     fg = None
     comm_ms = None
     if args.grad_allreduce and world > 1:
@@ -311,7 +312,7 @@ def run_teacher_forced(args):
                 'd2h_bytes_per_step': 4, 'note': 'LMM.forward(data): tokens / labels uploaded and the loss read back every step inside the timed region'},
         'comm': None if not fg else {
             'grad_allreduce': 'flattened fp32 buffer of %d elements (%.2f GB), NCCL all-reduce in 4 reverse-order slices per step, overlapped with the forward; '
-                              'SYNTHETIC gradients (no backward pass exists)' % (fg.buf.numel(), fg.buf.numel() * 4 / 1e9),
+                              'SYNTHETIC gradients (forward-only workload; --workload train all-reduces real ones)' % (fg.buf.numel(), fg.buf.numel() * 4 / 1e9),
             'standalone_ms': comm_ms, 'busbw_GBps': (fg.buf.numel() * 4 * 2 * (world - 1) / world) / (comm_ms * 1e-3) / 1e9 if comm_ms else None,
             'ms_per_step_includes_it': True},
     }), flush=True)

@@ -3,7 +3,7 @@
 // exp_avg_sq) — the layout a flattened data-parallel gradient buffer gives for free.  HBM-bound streaming kernels: the step reads p, g, m, v and
 // writes p, m, v (+ the fp16 copy the forward kernels consume): 30 bytes per parameter, 23 GB for the 766.8 M parameters of the ArAE preset.
 // The gradient-clipping coefficient is applied to the gradient as it is read (torch scales the gradients in place first: same rounding, one pass
-// over 3 GB less).  No backward pass exists in this repository: these entry points are the optimizer half of SURVEY §8 f2.
+// over 3 GB less).  These entry points are the optimizer half of SURVEY §8 f2; the gradients come from er_train_step (train.cu).
 #include "../../include/edgerunner_b200.h"
 
 #include <cuda_fp16.h>

@@ -8,8 +8,8 @@
   (``F.cross_entropy(..., ignore_index=-100)`` is a mean over the non-ignored tokens of the WHOLE batch).
 * ``FlatGradAllReduce``: the collective a data-parallel TRAINING step needs (one flattened gradient buffer,
   sum then / world, in a few slices in reverse-layer order so that it can start while earlier layers are still in
-  backward).  No backward pass exists in this repository: the class is the host-side plumbing, exercised by
-  ``bench.py --workload tf --grad-allreduce`` on a synthetic buffer of the model's parameter count and by the gloo test.
+  backward).  ``edgerunner_b200.train.FlatTrainer`` exports the gradients of ``er_train_step`` straight into its buffer (``bench.py --workload train``
+  under torchrun); ``bench.py --workload tf --grad-allreduce`` times it on a synthetic buffer next to the forward-only workload, the gloo test covers the plumbing.
 
 Works with backend 'nccl' on the GPU box and 'gloo' on CPU (tests/test_dist_cpu.py, world_size 2).
 """

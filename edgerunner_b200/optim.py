@@ -5,7 +5,7 @@
   the gradient is read), parameters / moments in one flat buffer each, an fp16 copy of the updated parameters for the forward kernels.
 * ``cosine_lr_lambda`` — the LambdaLR function of main.py:136-141 (linear warm-up, cosine decay to ``min_ratio``).
 
-There is no backward pass in this repository: gradients have to come from elsewhere (tests feed random ones and compare with
+Gradients come from ``Engine.train_step`` (er_train_step; edgerunner_b200/train.py::FlatTrainer drives the whole step); tests also feed random ones and compare with
 ``torch.optim.AdamW`` / ``torch.nn.utils.clip_grad_norm_``).  CUDA only — no CPU fallback.
 """
 
