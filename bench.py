@@ -393,14 +393,14 @@ def run_train(args):
         'metric': 'training tokens/sec, ArAE full step seq_len 8192 batch 4/GPU (BASELINE configs[3]; decoder trained, point encoder frozen)',
         'value': world * B * T / (ms_step * 1e-3), 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic', 'loss_history': hist,
-        'config': {'workload': f'ArAE training step B={B}/GPU N={N} (P={P} + T={T}): training forward (dropout {tr.dropout_p}) + backward with per-layer '
-                               f'recomputation + flat gradient all-reduce x{world} + clip + fused AdamW + fp16 weight refresh',
+        'config': {'workload': f'ArAE training step B={B}/GPU N={N} (P={P} + T={T}): training forward (dropout {tr.dropout_p}) + backward (activations kept in HBM unless '
+                               f'--debug train_recompute=1) + flat gradient all-reduce x{world} + clip + fused AdamW + fp16 weight refresh',
                    'trainable_parameters': int(tr.numel), 'debug': args.debug, 'l2': f'activations of {B * N} rows x 1536 exceed L2'},
         'clocks': clocks, 'gpu_launches': int(tr.engine.kernel_launches() - l0),
         'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'traffic': None,
-                     'kernel': 'er::tc::gemm_tcgen05_kernel (forward, dgrad, wgrad) + er::fa::attention_tcgen05_kernel + er::bw::attn_bwd_* (wmma)',
-                     'algorithmic_flops_per_step_per_gpu': flops, 'note': 'model FLOPs: 3 x GEMM + 3.5 x causal attention of the forward; the recomputed '
-                     'forward of the checkpointed layers and the 1.6 x redundant score products of the two-kernel attention backward are not counted',
+                     'kernel': 'er::tc::gemm_tcgen05_kernel (forward, dgrad, wgrad) + er::fa::attention_tcgen05_kernel + er::bwm::dq_kernel / dkv_kernel (mma.sync)',
+                     'algorithmic_flops_per_step_per_gpu': flops, 'note': 'model FLOPs: 3 x GEMM + 3.5 x causal attention of the forward; the 1.4 x redundant score products of the two-kernel attention '
+                     'backward (and the recomputed forward in --debug train_recompute=1 mode) are not counted',
                      'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)'},
         'e2e': {'value': world * B * T / (ms_step * 1e-3), 'unit': 'tokens/s', 'h2d_bytes_per_step': int(tokens.numel() * 4 + data['labels'].numel() * 8),
                 'd2h_bytes_per_step': 4, 'note': 'FlatTrainer.step(data): tokens / labels uploaded from pinned host memory, loss read back, every step'},
