@@ -138,14 +138,11 @@ class LMM(nn.Module):
     def _forward_train(self, data):
         """Training-mode forward (reference :147-202 with self.training): num-face dropout (:161-164), F.dropout(config.dropout) on both branches of
         every decoder layer, and a loss that carries a graph: ``out['loss'].backward()`` fills ``.grad`` of the decoder, lm_head, embeddings,
-        proj_cond / norm_cond / embed_num_face parameters.  The forward AND the backward run inside one library call (er_train_step: checkpointed
+        proj_cond / norm_cond / embed_num_face (and, unless frozen, point-encoder) parameters.  The forward AND the backward run inside one library call (er_train_step: checkpointed
         layers, tcgen05 dgrad / wgrad GEMMs, flash-attention backward); the autograd node only hands the stored gradients out.  As with
-        ``opt.freeze_encoder = True`` (the Options default) the point encoder runs without a graph, so loss_kl carries no gradient;
-        ``freeze_encoder = False`` (encoder training) is not built.  The dropout mask is a counter-based function of a seed drawn from torch's
+        ``opt.freeze_encoder = True`` (the Options default) the point encoder runs without a graph and loss_kl carries no gradient; with
+        ``freeze_encoder = False`` (the ArAE preset) the library call also walks back through the point encoder and the KL term.  The dropout mask is a counter-based function of a seed drawn from torch's
         global generator (reproducible per seed; not torch's Philox stream).  'logits' is None in this mode (main.py never reads it while training)."""
-        if self.opt.cond_mode == 'point' and not self.opt.freeze_encoder:
-            raise NotImplementedError('training the point encoder (freeze_encoder=False) is not built: the B200 training step covers the decoder, '
-                                      'lm_head, embeddings and the conditioner projection (set opt.freeze_encoder = True)')
         tokens, labels = data['tokens'], data['labels']
         B, T = tokens.shape
         num_faces = data['num_faces']
@@ -201,7 +198,8 @@ class _TrainStep(torch.autograd.Function):
         e = model.get_engine(max_new_tokens=getattr(model._engine, 'max_new_tokens', 64) if model._engine else 64,
                              max_tf_rows=B * (model.opt.num_cond_tokens + T))
         losses, _ = e.train_step(data['conds'], tokens, data['labels'], data['num_faces'].tolist(), model.opt.kl_weight, masks=data.get('masks'),
-                                 dropout_p=float(model.config.dropout), seed=seed, loss_scale=getattr(model, 'loss_scale', None))
+                                 dropout_p=float(model.config.dropout), seed=seed, loss_scale=getattr(model, 'loss_scale', None),
+                                 train_encoder=model.opt.cond_mode == 'point' and not model.opt.freeze_encoder)
         ctx.engine = e
         ctx.names = [n for n, p in model.named_parameters() if p.requires_grad]
         ctx.meta = [(p.shape, p.dtype) for p in params]

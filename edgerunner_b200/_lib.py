@@ -54,7 +54,7 @@ SIGNATURES = {
     'er_dit_kernel_launches': (c_i64, [c_vp]),
     'er_dit_flops_per_forward': (C.c_double, [c_vp, c_i32]),
     'er_dit_debug_set': (C.c_int, [c_vp, C.c_char_p, c_i64]),
-    'er_train_step': (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, C.POINTER(c_i32), c_i32, c_i32, c_f32, c_f32, c_u64, c_f32, c_vp, c_vp, c_vp]),
+    'er_train_step': (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, C.POINTER(c_i32), c_i32, c_i32, c_f32, c_f32, c_u64, c_f32, c_i32, c_vp, c_vp, c_vp]),
     'er_grad_get': (C.c_int, [c_vp, C.c_char_p, c_vp, c_i64, c_vp]),
     'er_grad_has': (c_i32, [c_vp, C.c_char_p]),
     'er_attention_bwd_bnhd': (C.c_int, [c_vp] * 8 + [c_i32] * 6 + [c_vp]),

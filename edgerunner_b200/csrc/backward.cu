@@ -235,6 +235,31 @@ __global__ void export_f32_kernel(const float* __restrict__ src, int ld, int row
     dst[i] = src[(size_t)r * ld + c] * scale;
 }
 
+// ---- GEGLU backward (point.py:69-72: h = [a | g], out = a * gelu_erf(g)) ------------------------------------------------------------------------------
+// dh [M][2F] from dout [M][F]: da = dout * gelu(g), dg = dout * a * gelu'(g), gelu'(g) = Phi(g) + g phi(g)
+__global__ void geglu_bwd_kernel(const __half* __restrict__ h, const __half* __restrict__ dout, __half* __restrict__ dh, int M, int F) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)M * F) return;
+    const size_t r = idx / F, c = idx % F;
+    const float a = __half2float(h[r * 2 * F + c]), g = __half2float(h[r * 2 * F + F + c]), d = __half2float(dout[idx]);
+    const float cdf = 0.5f * (1.f + erff(g * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * expf(-0.5f * g * g);
+    dh[r * 2 * F + c] = __float2half_rn(d * g * cdf);
+    dh[r * 2 * F + F + c] = __float2half_rn(d * a * (cdf + g * pdf));
+}
+__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+// dst[r][c] = f16(dst[r][c] + alpha * src[r][c])  (the KL term's gradient, kl_weight * latent, added to the latent gradient)
+__global__ void axpy_f16_kernel(__half* __restrict__ dst, int ld_dst, const __half* __restrict__ src, int ld_src, int rows, int cols, float alpha) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * cols) return;
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const size_t o = (size_t)r * ld_dst + c;
+    dst[o] = __float2half_rn(__half2float(dst[o]) + alpha * __half2float(src[(size_t)r * ld_src + c]));
+}
+
 // ---- flash-attention backward ----------------------------------------------------------------------------------------------------------------------------
 // Geometry shared by the three kernels: CTA = one 64-row tile of one (batch, head), 4 warps x 16 rows.  Tiles live in shared memory as
 // [64][D + 8] fp16 (row pitch 16-byte aligned, wmma ldm multiple of 8); every warp has a private fp32 scratch for the accumulator tiles it has to
@@ -559,19 +584,36 @@ cudaError_t er_ln_bwd(const float* dy32, const float* s32, const __half* s16, in
     return cudaGetLastError();
 }
 cudaError_t er_ln_param_grad(const float* dy32, const float* s32, const __half* s16, int ld_s, const float* mean, const float* rstd, int M, int C,
-                             float* partial /*[ER_BW_SLABS][2][C]*/, float* dgamma, float* dbeta, cudaStream_t st) {
+                             float* partial /*[ER_BW_SLABS][2][C]*/, float* dgamma, float* dbeta, cudaStream_t st, int accumulate) {
     if (M <= 0) return cudaSuccess;
     const dim3 grid((C + 255) / 256, ER_BW_SLABS);
     ln_param_partial_kernel<<<grid, 256, 0, st>>>(dy32, s32, s16, ld_s, mean, rstd, M, C, partial);
-    reduce_partials_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial, ER_BW_SLABS, (size_t)2 * C, C, dgamma, 0);
-    reduce_partials_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial + C, ER_BW_SLABS, (size_t)2 * C, C, dbeta, 0);
+    reduce_partials_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial, ER_BW_SLABS, (size_t)2 * C, C, dgamma, accumulate);
+    reduce_partials_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial + C, ER_BW_SLABS, (size_t)2 * C, C, dbeta, accumulate);
     return cudaGetLastError();
 }
-cudaError_t er_colsum_f16(const __half* x16, int ld, int M, int ncols, float* partial /*[ER_BW_SLABS][ncols]*/, float* out, cudaStream_t st) {
+cudaError_t er_colsum_f16(const __half* x16, int ld, int M, int ncols, float* partial /*[ER_BW_SLABS][ncols]*/, float* out, cudaStream_t st, int accumulate) {
     if (M <= 0 || ncols <= 0) return cudaSuccess;
     const dim3 grid((ncols + 255) / 256, ER_BW_SLABS);
     colsum_f16_partial_kernel<<<grid, 256, 0, st>>>(x16, ld, M, ncols, partial);
-    reduce_partials_kernel<<<(ncols + 255) / 256, 256, 0, st>>>(partial, ER_BW_SLABS, (size_t)ncols, ncols, out, 0);
+    reduce_partials_kernel<<<(ncols + 255) / 256, 256, 0, st>>>(partial, ER_BW_SLABS, (size_t)ncols, ncols, out, accumulate);
+    return cudaGetLastError();
+}
+cudaError_t er_geglu_bwd(const __half* h, const __half* dout, __half* dh, int M, int F, cudaStream_t st) {
+    const size_t n = (size_t)M * F;
+    if (!n) return cudaSuccess;
+    geglu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h, dout, dh, M, F);
+    return cudaGetLastError();
+}
+cudaError_t er_add_f32(float* dst, const float* src, size_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    add_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, src, n);
+    return cudaGetLastError();
+}
+cudaError_t er_axpy_f16(__half* dst, int ld_dst, const __half* src, int ld_src, int rows, int cols, float alpha, cudaStream_t st) {
+    const size_t n = (size_t)rows * cols;
+    if (!n) return cudaSuccess;
+    axpy_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, ld_dst, src, ld_src, rows, cols, alpha);
     return cudaGetLastError();
 }
 cudaError_t er_relu_bwd(__half* dh16, const __half* h16, size_t n, cudaStream_t st) {

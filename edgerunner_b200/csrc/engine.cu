@@ -330,7 +330,7 @@ er::GemmArgs mk_gemm(const __half* A, int lda, const __half* W, int ldw, const _
 }
 
 // PointEncoderEmbed.forward for one cloud -> lat16 [LQ][LDP] (point.py:186-206)
-static int encode_points(er_engine* e, const float* pts, int n, __half* lat, cudaStream_t st) {
+int encode_points(er_engine* e, const float* pts, int n, __half* lat, cudaStream_t st) {
     const int E = e->E, LQ = e->LQ, EH = e->EH;
     if (n > e->cfg.max_points) return set_err(ER_ERR_CAPACITY, "n_points %d > max_points %d", n, e->cfg.max_points);
     CKL(e, er_point_embed(pts, e->basis, e->emb16, 64, n, st));

@@ -115,6 +115,7 @@ static void dev_free(er_engine* e, T** p) {
 int ensure_dense_rows(er_engine* e, int rows);
 int encode_one(er_engine* e, const float* conds_dev, int n_points, int is_latent, int num_faces, __half* lat, float* cond32, cudaStream_t st);
 int er_quantize_num_faces(int n);
+int encode_points(er_engine* e, const float* pts, int n, __half* lat, cudaStream_t st);     // leaves every intermediate of this cloud in the encoder workspace
 er::GemmArgs mk_gemm(const __half* A, int lda, const __half* W, int ldw, const __half* bias, int M, int N, int K, int mode);
 // train.cu
 void er_train_destroy(er_engine* e);

@@ -96,9 +96,13 @@ cudaError_t er_ln_bwd(const float* dy32, const float* s32, const __half* s16, in
                       float* rstd, int M, int C, float p, unsigned long long seed, unsigned site, cudaStream_t st);
 // dgamma [C] = sum_r dy * xhat, dbeta [C] = sum_r dy; partial: scratch of ER_BW_SLABS * 2 * C floats
 cudaError_t er_ln_param_grad(const float* dy32, const float* s32, const __half* s16, int ld_s, const float* mean, const float* rstd, int M, int C,
-                             float* partial, float* dgamma, float* dbeta, cudaStream_t st);
+                             float* partial, float* dgamma, float* dbeta, cudaStream_t st, int accumulate = 0);
 // out [ncols] = column sums of x16 [M][ld]; partial: scratch of ER_BW_SLABS * ncols floats
-cudaError_t er_colsum_f16(const __half* x16, int ld, int M, int ncols, float* partial, float* out, cudaStream_t st);
+cudaError_t er_colsum_f16(const __half* x16, int ld, int M, int ncols, float* partial, float* out, cudaStream_t st, int accumulate = 0);
+// GEGLU backward: h [M][2F] (the forward input), dout [M][F] -> dh [M][2F]
+cudaError_t er_geglu_bwd(const __half* h, const __half* dout, __half* dh, int M, int F, cudaStream_t st);
+cudaError_t er_add_f32(float* dst, const float* src, size_t n, cudaStream_t st);                       // dst += src
+cudaError_t er_axpy_f16(__half* dst, int ld_dst, const __half* src, int ld_src, int rows, int cols, float alpha, cudaStream_t st);   // dst = f16(dst + alpha src)
 // dh16 = h16 > 0 ? dh16 : 0 (in place), n multiple of 8
 cudaError_t er_relu_bwd(__half* dh16, const __half* h16, size_t n, cudaStream_t st);
 // dl [B*N][ldo] = f16(loss_scale / *count * (softmax(round_f16(logits)) - onehot(label of the NEXT row))), zero for ignored rows and pad columns

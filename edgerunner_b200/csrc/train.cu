@@ -44,6 +44,11 @@ struct er_train {
     std::vector<void*> row_allocs;      // the buffers sized by M (re-allocated when a larger batch arrives)
     bool store = false;                 // activations of every layer kept from the forward pass (else: recomputed per layer in the backward pass)
     std::vector<LayerAct> acts;         // NL sets (store) or one
+    // point-encoder backward (opt.freeze_encoder = False): gradient arrays, one cloud's scratch
+    float *gqe = nullptr, *gmlpw, *gmlpb, *glnw, *glnb, *gcl1w, *gcl1b, *gcl2w, *gcl2b, *gcqw, *gcqb, *gckvw, *gckvb, *gcow, *gcob, *gff0w, *gff0b, *gff2w, *gff2b,
+          *glinw, *glinb;
+    __half *dlat16 = nullptr, *ed16a = nullptr, *ed16b = nullptr, *ed16c = nullptr; float *ef32a = nullptr, *ef32b = nullptr, *eacc32 = nullptr, *gtmp = nullptr;
+    bool encoder_grads = false;         // the last er_train_step trained the point encoder
     __half *qkv_all = nullptr, *a_all = nullptr, *x1_all = nullptr, *h_all = nullptr; float *s1_all = nullptr, *s2_all = nullptr, *lse_all = nullptr;
 };
 
@@ -94,7 +99,7 @@ static int create_train_impl(er_engine* e, er_train* t) {
     t->Vp = round64(e->V);
     t->wide = (int)std::max(F, 3 * C);
     struct Arr { const __half* w; size_t n; float** g; };
-    const Arr arrs[] = {
+    std::vector<Arr> arrs = {
         {e->wqkv, NL * 3 * C * C, &t->gwqkv}, {e->bqkv, NL * 3 * C, &t->gbqkv}, {e->wo, NL * C * C, &t->gwo}, {e->bo, NL * C, &t->gbo},
         {e->ln1w, NL * C, &t->gln1w}, {e->ln1b, NL * C, &t->gln1b}, {e->w1, NL * F * C, &t->gw1}, {e->b1, NL * F, &t->gb1},
         {e->w2, NL * C * F, &t->gw2}, {e->b2, NL * C, &t->gb2}, {e->ln2w, NL * C, &t->gln2w}, {e->ln2b, NL * C, &t->gln2b},
@@ -102,16 +107,27 @@ static int create_train_impl(er_engine* e, er_train* t) {
         {e->pc_w, C * LDP, &t->gpcw}, {e->pc_b, C, &t->gpcb}, {e->ncw, C, &t->gncw}, {e->ncb, C, &t->gncb},
         {e->cfg.use_num_face_cond ? e->enf : nullptr, e->cfg.use_num_face_cond ? 10 * C : 0, &t->genf},
     };
+    if (e->cfg.has_point_encoder) {
+        const size_t E = e->E, LQ = e->LQ;
+        const Arr enc[] = {
+            {e->qe, LQ * E, &t->gqe}, {e->mlp_w, E * 64, &t->gmlpw}, {e->mlp_b, E, &t->gmlpb}, {e->ln_w, E, &t->glnw}, {e->ln_b, E, &t->glnb},
+            {e->cl1w, E, &t->gcl1w}, {e->cl1b, E, &t->gcl1b}, {e->cl2w, E, &t->gcl2w}, {e->cl2b, E, &t->gcl2b}, {e->cq_w, E * E, &t->gcqw}, {e->cq_b, E, &t->gcqb},
+            {e->ckv_w, 2 * E * E, &t->gckvw}, {e->ckv_b, 2 * E, &t->gckvb}, {e->co_w, E * E, &t->gcow}, {e->co_b, E, &t->gcob},
+            {e->ff0w, 8 * E * E, &t->gff0w}, {e->ff0b, 8 * E, &t->gff0b}, {e->ff2w, 4 * E * E, &t->gff2w}, {e->ff2b, E, &t->gff2b},
+            {e->lin_w, LDP * E, &t->glinw}, {e->lin_b, LDP, &t->glinb},
+        };
+        for (const Arr& a : enc) arrs.push_back(a);
+    }
     size_t total = 0;
     std::vector<size_t> offs;
     for (const Arr& a : arrs) { offs.push_back(total); total += (a.n + 63) / 64 * 64; }
     t->gtotal = total;
     ALLOC(t->gflat, total);
     CK(cudaMemset(t->gflat, 0, total * 4));
-    for (size_t i = 0; i < sizeof(arrs) / sizeof(arrs[0]); i++) *arrs[i].g = arrs[i].n ? t->gflat + offs[i] : nullptr;
+    for (size_t i = 0; i < arrs.size(); i++) *arrs[i].g = arrs[i].n ? t->gflat + offs[i] : nullptr;
     for (const auto& kv : e->slots) {
         const Slot& s = kv.second;
-        for (size_t i = 0; i < sizeof(arrs) / sizeof(arrs[0]); i++) {
+        for (size_t i = 0; i < arrs.size(); i++) {
             const Arr& a = arrs[i];
             if (a.w && s.dst >= a.w && s.dst < a.w + a.n) {
                 t->gslots[kv.first] = GradSlot{*a.g + (s.dst - a.w), s.rows, s.cols, s.dst_ld};
@@ -119,8 +135,10 @@ static int create_train_impl(er_engine* e, er_train* t) {
             }
         }
     }
-    ALLOC(t->wT, std::max(std::max(F * C, 3 * C * C), C * (size_t)t->Vp) + 64);
-    ALLOC(t->partial, (size_t)ER_BW_SLABS * 2 * t->wide);
+    const size_t E8 = e->cfg.has_point_encoder ? (size_t)8 * e->E : 0;
+    ALLOC(t->wT, std::max(std::max(std::max(F * C, 3 * C * C), C * (size_t)t->Vp), E8 * e->E) + 64);
+    ALLOC(t->partial, (size_t)ER_BW_SLABS * 2 * std::max((size_t)t->wide, E8));
+    if (e->cfg.has_point_encoder) ALLOC(t->gtmp, E8 * e->E);
     ALLOC(t->bucket_dev, 4096);
     return ER_OK;
 }
@@ -156,9 +174,19 @@ static int ensure_train(er_engine* e, int M, int B) {
     RALLOC(t->s1, Mc * C); RALLOC(t->s2, Mc * C); RALLOC(t->x1_32, Mc * C); RALLOC(t->g32a, Mc * C); RALLOC(t->g32b, Mc * C);
     RALLOC(t->x1_16, Mc * C); RALLOC(t->o16, Mc * C); RALLOC(t->dbr16, Mc * C); RALLOC(t->da16, Mc * C);
     RALLOC(t->dwide16, Mc * t->wide);
-    RALLOC(t->tA, (size_t)std::max<size_t>(t->wide, e->V) * Mp); RALLOC(t->tB, std::max<size_t>(std::max(F, C), e->LDP) * Mp);
+    // one cloud of the point encoder (its backward runs per sample): np points, LQ queries, width E
+    const size_t E = e->cfg.has_point_encoder ? e->E : 0, np = e->cfg.has_point_encoder ? e->cfg.max_points : 0, LQ = e->LQ;
+    const size_t enc_tA = std::max(8 * E * round64((int)LQ), 2 * E * round64((int)np)), enc_tB = std::max(4 * E * round64((int)LQ), std::max(E, (size_t)64) * round64((int)np));
+    RALLOC(t->tA, std::max((size_t)std::max<size_t>(t->wide, e->V) * Mp, enc_tA)); RALLOC(t->tB, std::max(std::max<size_t>(std::max(F, C), e->LDP) * Mp, enc_tB));
     RALLOC(t->dl16, Mc * t->Vp);
-    RALLOC(t->lse2, Mc * H); RALLOC(t->dsum, Mc * H); RALLOC(t->mean, Mc); RALLOC(t->rstd, Mc);
+    const size_t enc_stats = e->cfg.has_point_encoder ? (size_t)e->EH * LQ : 0;       // attention statistics of one cloud
+    RALLOC(t->lse2, std::max(Mc * H, enc_stats)); RALLOC(t->dsum, std::max(Mc * H, enc_stats)); RALLOC(t->mean, std::max(Mc, np)); RALLOC(t->rstd, std::max(Mc, np));
+    RALLOC(t->dlat16, RL * 64 * ((e->LDP + 63) / 64));
+    CK(cudaMemset(t->dlat16, 0, RL * 64 * ((e->LDP + 63) / 64) * 2));            // pad columns [LDP, round64) stay zero: they are K of the lin dgrad GEMM
+    if (e->cfg.has_point_encoder) {
+        const size_t big = std::max(LQ * 8 * E, np * 2 * E), rows = std::max(LQ, np);
+        RALLOC(t->ed16a, big); RALLOC(t->ed16b, big); RALLOC(t->ed16c, big); RALLOC(t->ef32a, rows * E); RALLOC(t->ef32b, rows * E); RALLOC(t->eacc32, LQ * E);
+    }
     RALLOC(t->pc16_all, RL * C); RALLOC(t->dpc16, RL * C); RALLOC(t->dcond32, RL * C);
     t->store = want_store;
     t->acts.assign(want_store ? NL : 1, LayerAct{});
@@ -214,12 +242,12 @@ static int wgrad(er_engine* e, const __half* dy, int ldy, int Nout, const __half
 // dX = dY W for dY [M][Nout] (pitch ldy), W [Nout][Kin] row-major: W is transposed into wT [Kin][Nout]; mode GEMM_F16 -> out16, GEMM_F32 -> out32,
 // GEMM_F32_RES32 -> out32 = res32 + f16(dY W)
 static int dgrad(er_engine* e, const __half* dy, int ldy, int Nout, const __half* W, int Kin, int M, int mode, __half* out16, float* out32, const float* res32,
-                 cudaStream_t st) {
+                 cudaStream_t st, int ldo = 0) {
     er_train* t = e->train;
     const int Np = round64(Nout);
     CKL(e, er_transpose_f16(W, Nout, Kin, Kin, t->wT, Np, st));
     er::GemmArgs g = mk_gemm(dy, ldy, t->wT, Np, nullptr, M, Kin, Np, mode);
-    g.out16 = out16; g.out32 = out32; g.ldo = Kin; g.res32 = res32; g.ldr = Kin; CKL(e, er_gemm(g, st));
+    g.out16 = out16; g.out32 = out32; g.ldo = ldo ? ldo : Kin; g.res32 = res32; g.ldr = Kin; CKL(e, er_gemm(g, st));
     return ER_OK;
 }
 
@@ -269,12 +297,81 @@ static int layer_bwd(er_engine* e, int l, int B, int N, const unsigned char* row
     return ER_OK;
 }
 
+// dW += dY^T X (the point encoder's weights collect one cloud at a time): wgrad into the fp32 scratch, then a plain add
+static int wgrad_acc(er_engine* e, const __half* dy, int ldy, int Nout, const __half* x, int ldx, int Kin, int M, float* dW, int ldw, cudaStream_t st) {
+    er_train* t = e->train;
+    int r = wgrad(e, dy, ldy, Nout, x, ldx, Kin, M, t->gtmp, ldw, st);
+    if (r) return r;
+    CKL(e, er_add_f32(dW, t->gtmp, (size_t)Nout * ldw, st));
+    return ER_OK;
+}
+
+// Backward of PointEncoderEmbed.forward (core/transformer/point.py:186-206, 117-126, 74-84) for ONE cloud: the forward is re-run into the encoder
+// workspace (encode_points), then walked back.  dlat: gradient of this cloud's latents [LQ][round64(LDP)] (fp16, loss-scaled).  Weight gradients
+// accumulate over the clouds of the batch (the gradient buffer was zeroed at the start of the step).
+static int encoder_bwd(er_engine* e, const float* pts, int n, const __half* dlat, cudaStream_t st) {
+    er_train* t = e->train;
+    const int E = e->E, LQ = e->LQ, EH = e->EH, LDP = e->LDP, LDPp = round64(e->LDP);
+    { int r = encode_points(e, pts, n, e->pc16 /* scratch: the latents are not needed again */, st); if (r) return r; }
+    // ---- linear: lat = ex2 W^T + b ----
+    CKL(e, er_colsum_f16(dlat, LDPp, LQ, LDP, t->partial, t->glinb, st, 1));
+    { int r = wgrad_acc(e, dlat, LDPp, LDP, e->ex2, E, E, LQ, t->glinw, E, st); if (r) return r; }
+    { int r = dgrad(e, dlat, LDPp, LDP, e->lin_w, E, LQ, er::GEMM_F16, t->ed16a, nullptr, nullptr, st); if (r) return r; }       // ed16a = d ex2
+    CKL(e, er_f16_to_f32(t->ed16a, t->eacc32, LQ * E, st));                                                                  // eacc32 = d ex1 (residual path)
+    // ---- mlp.net.2: ex2 = ex1 + egg W^T + b ----
+    CKL(e, er_colsum_f16(t->ed16a, E, LQ, E, t->partial, t->gff2b, st, 1));
+    { int r = wgrad_acc(e, t->ed16a, E, E, e->egg, 4 * E, 4 * E, LQ, t->gff2w, 4 * E, st); if (r) return r; }
+    { int r = dgrad(e, t->ed16a, E, E, e->ff2w, 4 * E, LQ, er::GEMM_F16, t->ed16b, nullptr, nullptr, st); if (r) return r; }     // ed16b = d egg
+    CKL(e, er_geglu_bwd(e->eff, t->ed16b, t->ed16c, LQ, 4 * E, st));                                                            // ed16c = d eff
+    // ---- mlp.net.0: eff = ex1ln W^T + b ----
+    CKL(e, er_colsum_f16(t->ed16c, 8 * E, LQ, 8 * E, t->partial, t->gff0b, st, 1));
+    { int r = wgrad_acc(e, t->ed16c, 8 * E, 8 * E, e->ex1ln, E, E, LQ, t->gff0w, E, st); if (r) return r; }
+    { int r = dgrad(e, t->ed16c, 8 * E, 8 * E, e->ff0w, E, LQ, er::GEMM_F16, t->ed16a, nullptr, nullptr, st); if (r) return r; } // ed16a = d ex1ln
+    // ---- cross_att.ln2 (input ex1, fp16) ----
+    CKL(e, er_f16_to_f32(t->ed16a, t->ef32a, LQ * E, st));
+    CKL(e, er_ln_bwd(t->ef32a, nullptr, e->ex1, E, e->cl2w, t->ef32b, nullptr, t->mean, t->rstd, LQ, E, 0.f, 0, 0, st));
+    CKL(e, er_ln_param_grad(t->ef32a, nullptr, e->ex1, E, t->mean, t->rstd, LQ, E, t->partial, t->gcl2w, t->gcl2b, st, 1));
+    CKL(e, er_add_f32(t->eacc32, t->ef32b, (size_t)LQ * E, st));
+    // ---- ex1 = query_embed + out_proj(attention) ----
+    CKL(e, er_add_f32(t->gqe, t->eacc32, (size_t)LQ * E, st));
+    CKL(e, er_f32_to_f16(t->eacc32, t->ed16a, (size_t)LQ * E, st));                                                            // ed16a = d (out_proj output)
+    CKL(e, er_colsum_f16(t->ed16a, E, LQ, E, t->partial, t->gcob, st, 1));
+    { int r = wgrad_acc(e, t->ed16a, E, E, e->ea16, E, E, LQ, t->gcow, E, st); if (r) return r; }
+    { int r = dgrad(e, t->ed16a, E, E, e->co_w, E, LQ, er::GEMM_F16, t->ed16b, nullptr, nullptr, st); if (r) return r; }         // ed16b = d ea
+    // ---- cross attention: q = qq16 [LQ][E], k | v = kvo16 [n][2E] ----
+    er::AttnArgs a{};
+    a.q = e->qq16; a.k = e->kvo16; a.v = e->kvo16 + E; a.out = e->ea16;
+    a.ldq = E; a.ldk = 2 * E; a.ldv = 2 * E; a.ldo = E; a.B = 1; a.H = EH; a.Nq = LQ; a.Nk = n; a.D = 64; a.causal = 0;
+    e->launches += 2;
+    CKL(e, er_attention_bwd(a, t->ed16b, t->ed16a, t->ed16c, t->ed16c + E, E, 2 * E, 2 * E, 0, 0, 0, t->lse2, t->dsum, st));      // ed16a = d qq, ed16c = d k|v
+    // ---- q_proj and cross_att.ln1 (input query_embed) ----
+    CKL(e, er_colsum_f16(t->ed16a, E, LQ, E, t->partial, t->gcqb, st, 1));
+    { int r = wgrad_acc(e, t->ed16a, E, E, e->qln16, E, E, LQ, t->gcqw, E, st); if (r) return r; }
+    { int r = dgrad(e, t->ed16a, E, E, e->cq_w, E, LQ, er::GEMM_F16, t->ed16b, nullptr, nullptr, st); if (r) return r; }         // ed16b = d qln
+    CKL(e, er_f16_to_f32(t->ed16b, t->ef32a, LQ * E, st));
+    CKL(e, er_ln_bwd(t->ef32a, nullptr, e->qe, E, e->cl1w, t->ef32b, nullptr, t->mean, t->rstd, LQ, E, 0.f, 0, 0, st));
+    CKL(e, er_ln_param_grad(t->ef32a, nullptr, e->qe, E, t->mean, t->rstd, LQ, E, t->partial, t->gcl1w, t->gcl1b, st, 1));
+    CKL(e, er_add_f32(t->gqe, t->ef32b, (size_t)LQ * E, st));
+    // ---- k_proj | v_proj: kvo = kvx W^T + b ----
+    CKL(e, er_colsum_f16(t->ed16c, 2 * E, n, 2 * E, t->partial, t->gckvb, st, 1));
+    { int r = wgrad_acc(e, t->ed16c, 2 * E, 2 * E, e->kvx16, E, E, n, t->gckvw, E, st); if (r) return r; }
+    { int r = dgrad(e, t->ed16c, 2 * E, 2 * E, e->ckv_w, E, n, er::GEMM_F16, t->ed16a, nullptr, nullptr, st); if (r) return r; } // ed16a = d kvx [n][E]
+    // ---- ln (input pf16) and point_embed.mlp ----
+    CKL(e, er_f16_to_f32(t->ed16a, t->ef32a, n * E, st));
+    CKL(e, er_ln_bwd(t->ef32a, nullptr, e->pf16, E, e->ln_w, nullptr, t->ed16b, t->mean, t->rstd, n, E, 0.f, 0, 0, st));          // ed16b = d pf [n][E]
+    CKL(e, er_ln_param_grad(t->ef32a, nullptr, e->pf16, E, t->mean, t->rstd, n, E, t->partial, t->glnw, t->glnb, st, 1));
+    CKL(e, er_colsum_f16(t->ed16b, E, n, E, t->partial, t->gmlpb, st, 1));
+    { int r = wgrad_acc(e, t->ed16b, E, E, e->emb16, 64, 64, n, t->gmlpw, 64, st); if (r) return r; }
+    return ER_OK;
+}
+
 extern "C" int er_train_step(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, const int32_t* tokens_dev, const int64_t* labels_dev,
                              const uint8_t* mask_dev, const int32_t* num_faces_host, int32_t B, int32_t T, float kl_weight, float dropout_p, uint64_t seed,
-                             float loss_scale, float* losses_dev, double* sums_dev, void* stream) {
+                             float loss_scale, int32_t train_encoder, float* losses_dev, double* sums_dev, void* stream) {
     if (!e || !conds_dev || !tokens_dev || !labels_dev || !num_faces_host || !losses_dev) return set_err(ER_ERR_INVALID, "null argument");
     if (!e->finalized) return set_err(ER_ERR_STATE, "weights not finalized");
     if (B < 1 || T < 1) return set_err(ER_ERR_INVALID, "bad batch shape");
+    if (train_encoder && (is_latent || !e->cfg.has_point_encoder)) return set_err(ER_ERR_INVALID, "train_encoder needs cond_mode 'point' (an engine with a point encoder)");
     if (!(dropout_p >= 0.f && dropout_p < 1.f) || !(loss_scale > 0.f)) return set_err(ER_ERR_INVALID, "dropout_p must be in [0, 1), loss_scale > 0");
     cudaStream_t st = (cudaStream_t)stream;
     const int C = e->C, P = e->P, N = P + T, M = B * N, V = e->V, NL = e->NL;
@@ -338,6 +435,18 @@ extern "C" int er_train_step(er_engine* e, const float* conds_dev, int32_t n_poi
     CKL(e, er_ln_param_grad(t->dcond32, nullptr, t->pc16_all, C, t->mean, t->rstd, RL, C, t->partial, t->gncw, t->gncb, st));
     CKL(e, er_colsum_f16(t->dpc16, C, RL, C, t->partial, t->gpcb, st));
     { int r = wgrad(e, t->dpc16, C, C, e->lat16, e->LDP, e->LDP, RL, t->gpcw, e->LDP, st); if (r) return r; }
+    t->encoder_grads = train_encoder != 0;
+    if (train_encoder) {
+        // d latents = dpc W_proj_cond + kl_weight * latents (DummyLatent.kl = 0.5 sum lat^2, point.py:33-35; models.py:191-197), loss-scaled like everything else
+        const int LDPp = round64(e->LDP);
+        // written with row pitch round64(LDP): the pad columns (zero since allocation) are the K tail of the encoder's first dgrad GEMM
+        { int r = dgrad(e, t->dpc16, C, C, e->pc_w, e->LDP, RL, er::GEMM_F16, t->dlat16, nullptr, nullptr, st, LDPp); if (r) return r; }
+        CKL(e, er_axpy_f16(t->dlat16, LDPp, e->lat16, e->LDP, RL, e->LDP, kl_weight * loss_scale, st));
+        for (int b = 0; b < B; b++) {
+            int r = encoder_bwd(e, conds_dev + b * cstride, n_points, t->dlat16 + (size_t)b * LQ * LDPp, st);
+            if (r) return r;
+        }
+    }
     t->have_grads = true;
     return ER_OK;
 }
@@ -350,6 +459,7 @@ extern "C" int er_grad_get(er_engine* e, const char* name, float* out_dev, int64
     auto it = t->gslots.find(name);
     if (it == t->gslots.end()) return set_err(ER_ERR_INVALID, "no gradient for '%s' (unknown key, or a frozen point-encoder tensor)", name);
     const GradSlot& s = it->second;
+    if (!t->encoder_grads && strncmp(name, "point_encoder.", 14) == 0) return set_err(ER_ERR_STATE, "'%s': the last er_train_step ran with the point encoder frozen", name);
     if (numel != (int64_t)s.rows * s.cols) return set_err(ER_ERR_INVALID, "'%s' has %d x %d elements, buffer holds %lld", name, s.rows, s.cols, (long long)numel);
     CKL(e, er_export_f32(s.ptr, s.ld, s.rows, s.cols, 1.f / t->loss_scale, out_dev, (cudaStream_t)stream));
     return ER_OK;

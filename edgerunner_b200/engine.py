@@ -168,11 +168,13 @@ class Engine:
 
     # ---- training step ------------------------------------------------------------------------------------------
     def train_step(self, conds: torch.Tensor, tokens: torch.Tensor, labels: torch.Tensor, num_faces, kl_weight: float,
-                   masks: Optional[torch.Tensor] = None, dropout_p: float = 0.1, seed: int = 0, loss_scale: Optional[float] = None):
+                   masks: Optional[torch.Tensor] = None, dropout_p: float = 0.1, seed: int = 0, loss_scale: Optional[float] = None,
+                   train_encoder: bool = False):
         """Training-mode forward + backward of LMM.forward on this batch (er_train_step): -> (losses[3] = loss, mean CE, KL; sums[3]).
         The gradients stay in the engine until ``grad(name, ...)`` exports them.  Arguments as ``forward_tf``.  loss_scale: static scale of the fp16
         activation gradients (removed again on export); default: the power of two that puts 4..8 on each supervised row's d loss / d logits
-        (the mean over n rows carries 1/n), so the scale does not depend on the batch size."""
+        (the mean over n rows carries 1/n), so the scale does not depend on the batch size.  train_encoder: also back-propagate through the point
+        encoder of cond_mode 'point' and the KL term (opt.freeze_encoder = False); otherwise both are constants (the Options default)."""
         B, T = tokens.shape
         is_latent = int(self.opt.cond_mode == 'point_latent')
         conds = conds.to(self.device, torch.float32).contiguous()
@@ -196,11 +198,17 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.er_train_step(self.h, conds.data_ptr(), conds.shape[1], is_latent, tok.data_ptr(), lab.data_ptr(),
                                               m8.data_ptr() if m8 is not None else None, nf, B, T, C.c_float(kl_weight), C.c_float(dropout_p),
-                                              C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_float(loss_scale), losses.data_ptr(), sums.data_ptr(), _stream()))
+                                              C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_float(loss_scale), int(bool(train_encoder)), losses.data_ptr(), sums.data_ptr(),
+                                              _stream()))
+        self.encoder_trained = bool(train_encoder)
         self._keep = [m8, conds, tok, lab]
         return losses, sums
 
-    def grad_has(self, name: str) -> bool:
+    def grad_has(self, name: str, train_encoder: Optional[bool] = None) -> bool:
+        """does ``name`` receive a gradient?  point_encoder.* entries only when the encoder is trained (default: as in the last train_step)"""
+        te = getattr(self, 'encoder_trained', False) if train_encoder is None else train_encoder
+        if name.startswith('point_encoder.') and not te:
+            return False
         return bool(self.lib.er_grad_has(self.h, name.encode()))
 
     def grad(self, name: str, shape=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -9,7 +9,7 @@
 
 ``core.models.LMM`` in ``train()`` mode offers the same backward through torch autograd (``loss.backward()`` + any torch optimizer); this
 class is the B200-first form: no per-parameter tensors, no autograd graph, master weights / moments / gradients in four flat buffers.
-Trainable: decoder, lm_head, embeddings, proj_cond, norm_cond, embed_num_face; the point encoder is frozen (``opt.freeze_encoder``).
+Trainable: decoder, lm_head, embeddings, proj_cond, norm_cond, embed_num_face, and the point encoder unless ``opt.freeze_encoder``.
 CUDA only — no CPU fallback.
 """
 
@@ -29,10 +29,11 @@ class FlatTrainer:
         self.model, self.opt_cfg = model, opt
         self.engine = model.get_engine(max_new_tokens=64, max_tf_rows=max_batch * (opt.num_cond_tokens + max_tokens))
         e = self.engine
+        self.train_encoder = opt.cond_mode == 'point' and not opt.freeze_encoder
         self.entries = []                                     # (name, offset, numel, shape) in registration order
         off = 0
         for name, p in model.named_parameters():
-            if e.grad_has(name):
+            if e.grad_has(name, self.train_encoder):
                 self.entries.append((name, off, p.numel(), tuple(p.shape)))
                 off += (p.numel() + 3) // 4 * 4               # 16-byte aligned slices
         self.numel = off
@@ -61,7 +62,7 @@ class FlatTrainer:
             num_faces[drop.to(num_faces.device)] = -1
         seed = int(torch.randint(0, 2 ** 62, (1,), generator=self._rng).item())
         losses, _ = e.train_step(data['conds'], data['tokens'], data['labels'], num_faces.tolist(), opt.kl_weight, masks=data.get('masks'),
-                                 dropout_p=self.dropout_p, seed=seed, loss_scale=loss_scale)
+                                 dropout_p=self.dropout_p, seed=seed, loss_scale=loss_scale, train_encoder=self.train_encoder)
         for name, o, n, shp in self.entries:
             e.grad(name, out=self.grad[o:o + n])
         self.reducer.launch().wait()

@@ -188,14 +188,15 @@ int er_dit_debug_set(er_dit* e, const char* key, int64_t value);   /* "graph": 0
  * shifted cross-entropy), with opt.checkpointing (every layer re-run in the backward pass) and opt.freeze_encoder (the point encoder and the KL
  * term carry no gradient).  Arguments as er_forward_tf2, plus dropout_p (ShapeOPTConfig.dropout, 0.1 in the reference; the keep mask is a
  * counter-based function of `seed`, not torch's Philox stream), loss_scale (static scale of the fp16 activation gradients; exported gradients are
- * unscaled).  losses_dev[3] = {loss, mean CE, KL} of this rank's batch (the reference's DDP averages per-rank means: no cross-rank loss sums here);
+ * unscaled), train_encoder (0: opt.freeze_encoder, the point encoder and the KL term carry no gradient; 1: the point encoder of cond_mode 'point' is
+ * trained too — its forward is re-run per cloud in the backward pass — and the KL term kl_weight * 0.5 sum(latent^2) contributes).  losses_dev[3] = {loss, mean CE, KL} of this rank's batch (the reference's DDP averages per-rank means: no cross-rank loss sums here);
  * sums_dev (optional) as er_forward_tf2.  The engine must have been created with max_tf_rows >= B * (num_cond_tokens + T).
  * er_grad_get: copy the fp32 gradient of one state-dict entry (reference key schema, dense [rows][cols], numel checked) to out_dev after a
- * step.  er_grad_has: 1 if the entry is trainable here (decoder, lm_head, embeddings, proj_cond, norm_cond, embed_num_face), 0 for the frozen
- * point encoder / unknown keys. */
+ * step (point_encoder.* keys only after a step with train_encoder = 1).  er_grad_has: 1 if the entry can receive a gradient (every parameter of the
+ * reference's LMM in cond_mode point / point_latent), 0 for buffers / unknown keys. */
 int er_train_step(er_engine* e, const float* conds_dev, int32_t n_points, int32_t is_latent, const int32_t* tokens_dev, const int64_t* labels_dev,
                   const uint8_t* mask_dev, const int32_t* num_faces_host, int32_t B, int32_t T, float kl_weight, float dropout_p, uint64_t seed,
-                  float loss_scale, float* losses_dev, double* sums_dev, void* stream);
+                  float loss_scale, int32_t train_encoder, float* losses_dev, double* sums_dev, void* stream);
 int er_grad_get(er_engine* e, const char* name, float* out_dev, int64_t numel, void* stream);
 int32_t er_grad_has(er_engine* e, const char* name);
 /* Backward of the attention() op seam (core/transformer/attention.py:27-95; forward: er_attention_bnhd): tensors [B][N][H][D] fp16 contiguous,

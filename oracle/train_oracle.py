@@ -50,21 +50,66 @@ def _dropout(y: torch.Tensor, seed: int, site: int, p: float) -> torch.Tensor:
     return torch.where(keep, y / (1.0 - float(np.float32(p))), torch.zeros_like(y))
 
 
-def trainable_leaves(state_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """fp16-rounded copies (what the engine holds) of every non-encoder tensor as fp32 leaves with requires_grad."""
-    return {k: v.detach().to(torch.float16).float().requires_grad_(True) for k, v in state_dict.items() if not k.startswith('point_encoder.')}
+def trainable_leaves(state_dict: Dict[str, torch.Tensor], train_encoder: bool = False) -> Dict[str, torch.Tensor]:
+    """fp16-rounded copies (what the engine holds) of every trainable tensor as fp32 leaves with requires_grad: everything but the point encoder, or
+    (train_encoder, opt.freeze_encoder = False) its parameters too — `point_embed.basis` is a buffer, not a parameter (point.py:50)."""
+    return {k: v.detach().to(torch.float16).float().requires_grad_(True) for k, v in state_dict.items()
+            if (train_encoder and k != 'point_encoder.point_embed.basis') or not k.startswith('point_encoder.')}
+
+
+def encode_points_train(opt, state_dict, w: Dict[str, torch.Tensor], pc: torch.Tensor) -> torch.Tensor:
+    """PointEncoderEmbed.forward (core/transformer/point.py:186-206; ResCrossAttBlock :117-126; GEGLU FFN :74-84) as differentiable fp32 ops over the
+    leaves `w`.  The Fourier features are data (no parameter in front of them): they are taken with the fp16 rounding the autocast forward applies
+    (Oracle.encode_points) — at |x * basis| up to 400 rad an unrounded product would be a different input, not a more accurate one."""
+    pe = 'point_encoder.'
+    basis = state_dict[pe + 'point_embed.basis'].to(torch.float16).float()
+    E = w[pe + 'query_embed'].shape[-1]
+    Hh = opt.point_num_heads
+    Dh = E // Hh
+
+    def lin(x, name):
+        return x @ w[pe + name + '.weight'].t() + w[pe + name + '.bias']
+
+    def ln(x, name):
+        return F.layer_norm(x, (x.shape[-1],), w[pe + name + '.weight'], w[pe + name + '.bias'], 1e-5)
+    outs = []
+    for b in range(pc.shape[0]):
+        x = pc[b].float()
+        with torch.no_grad():
+            proj = _r16(_r16(x) @ basis)
+            emb = torch.cat([_r16(torch.sin(proj)), _r16(torch.cos(proj)), _r16(x)], dim=1)
+        kvx = ln(lin(emb, 'point_embed.mlp'), 'ln')
+        q0 = w[pe + 'query_embed'][0]
+        q = lin(ln(q0, 'cross_att.ln1'), 'cross_att.att.q_proj').view(-1, Hh, Dh).transpose(0, 1)
+        k = lin(kvx, 'cross_att.att.k_proj').view(-1, Hh, Dh).transpose(0, 1)
+        v = lin(kvx, 'cross_att.att.v_proj').view(-1, Hh, Dh).transpose(0, 1)
+        a = (torch.softmax(q @ k.transpose(-1, -2) / Dh ** 0.5, -1) @ v).transpose(0, 1).reshape(-1, E)
+        x1 = q0 + lin(a, 'cross_att.att.out_proj')
+        h = lin(ln(x1, 'cross_att.ln2'), 'cross_att.mlp.net.0')
+        a_, g_ = h.chunk(2, dim=-1)
+        x2 = x1 + lin(a_ * F.gelu(g_), 'cross_att.mlp.net.2')
+        outs.append(lin(x2, 'linear'))
+    return torch.stack(outs)
+
+
+def _r16(t):
+    return t.to(torch.float16).to(torch.float32)
 
 
 def forward_train(opt, state_dict, w: Dict[str, torch.Tensor], conds, tokens, labels, num_faces, masks: Optional[torch.Tensor] = None,
-                  dropout_p: float = 0.0, seed: int = 0):
+                  dropout_p: float = 0.0, seed: int = 0, train_encoder: bool = False):
     """-> dict(loss, loss_ce, loss_kl).  ``w``: trainable leaves (``trainable_leaves``); the frozen point encoder comes from ``state_dict``.
     fp32 arithmetic throughout (the gradient reference; the engine's fp16 rounding is what the test tolerance covers)."""
     orc = Oracle(opt, state_dict, mode='ledger')                     # frozen encoder as the engine runs it (fp16 ledger), no graph
     B, T = tokens.shape
     C, H, NL = opt.hidden_dim, opt.num_heads, opt.num_layers
     D = C // H
-    with torch.no_grad():
-        lat_all = orc.encode_points(conds) if opt.cond_mode == 'point' else orc.r(conds.float())
+    if train_encoder:                                                # opt.freeze_encoder = False: the encoder and the KL term are part of the graph
+        assert opt.cond_mode == 'point'
+        lat_all = encode_points_train(opt, state_dict, w, conds)
+    else:
+        with torch.no_grad():
+            lat_all = orc.encode_points(conds) if opt.cond_mode == 'point' else orc.r(conds.float())
     xs = []
     for b in range(B):
         ce = F.layer_norm(lat_all[b] @ w['proj_cond.weight'].t() + w['proj_cond.bias'], (C,), w['norm_cond.weight'], w['norm_cond.bias'], 1e-5)

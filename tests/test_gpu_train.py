@@ -92,22 +92,24 @@ def _attention_backward_cases():
             assert float((got.float() - want).abs().max()) < 2e-2 * float(want.abs().max()) + 2e-3, (name, B, N, M, H, D)
 
 
-def _engine_grads(opt, sd, batch, dropout_p, seed, use_masks):
+def _engine_grads(opt, sd, batch, dropout_p, seed, use_masks, train_encoder=False):
     from edgerunner_b200.engine import Engine
     conds, tokens, labels, masks, nf = batch
     B, T = tokens.shape
     eng = Engine(opt, torch.device('cuda:0'), max_new_tokens=64, max_points=opt.point_num, max_tf_rows=B * (opt.num_cond_tokens + T))
     eng.load_state_dict(sd)
-    losses, sums = eng.train_step(conds.cuda(), tokens, labels, nf, opt.kl_weight, masks=masks if use_masks else None, dropout_p=dropout_p, seed=seed)
+    losses, sums = eng.train_step(conds.cuda(), tokens, labels, nf, opt.kl_weight, masks=masks if use_masks else None, dropout_p=dropout_p, seed=seed,
+                                   train_encoder=train_encoder)
     grads = {k: eng.grad(k, v.shape).cpu() for k, v in sd.items() if eng.grad_has(k)}
     return eng, losses.cpu().numpy(), sums.cpu().numpy(), grads
 
 
-def _oracle_grads(opt, sd, batch, dropout_p, seed, use_masks):
+def _oracle_grads(opt, sd, batch, dropout_p, seed, use_masks, train_encoder=False):
     from oracle.train_oracle import forward_train, trainable_leaves
     conds, tokens, labels, masks, nf = batch
-    w = trainable_leaves(sd)
-    out = forward_train(opt, sd, w, conds, tokens, labels, nf, masks=masks if use_masks else None, dropout_p=dropout_p, seed=seed)
+    w = trainable_leaves(sd, train_encoder)
+    out = forward_train(opt, sd, w, conds, tokens, labels, nf, masks=masks if use_masks else None, dropout_p=dropout_p, seed=seed,
+                        train_encoder=train_encoder)
     out['loss'].backward()
     return {k: float(v) for k, v in out.items()}, {k: v.grad for k, v in w.items()}
 
@@ -144,6 +146,30 @@ def test_train_step_gradients_match_autograd(cond_mode):
     assert np.array_equal(l2.cpu().numpy(), losses)
     k = 'mesh_decoder.model.layers.0.fc1.weight'
     assert torch.equal(eng.grad(k, sd[k].shape).cpu(), grads[k])
+
+
+def test_train_step_trains_the_point_encoder():
+    """opt.freeze_encoder = False (the ArAE preset): the backward continues through proj_cond into the point encoder (cross-attention with D = 64,
+    GEGLU, three LayerNorms, the Fourier-feature Linear, query_embed) and the KL term kl_weight * 0.5 sum(latent^2) contributes (kl_weight raised
+    from the preset's 1e-8 so that its gradient is visible); three clouds, so the per-cloud accumulation of the encoder's weight gradients is covered"""
+    opt = synth.tiny_options(kl_weight=3e-3)
+    sd = synth.synth_state_dict(opt, seed=2, eos_logit=-30.0)
+    batch = _batch(opt, B=3, T=30, seed=4, pad=5)
+    eng, losses, sums, grads = _engine_grads(opt, sd, batch, 0.1, 99, True, train_encoder=True)
+    ref_losses, ref = _oracle_grads(opt, sd, batch, 0.1, 99, True, train_encoder=True)
+    np.testing.assert_allclose(losses[1], ref_losses['loss_ce'], rtol=3e-3)
+    np.testing.assert_allclose(losses[2], ref_losses['loss_kl'], rtol=5e-3)
+    assert sum(k.startswith('point_encoder.') for k in grads) == 23 and 'point_encoder.point_embed.basis' not in grads
+    _compare(grads, ref)
+    # with the encoder frozen the same engine refuses to hand out encoder gradients and the others lose the encoder-side KL / nothing else
+    conds, tokens, labels, masks, nf = batch
+    eng.train_step(conds.cuda(), tokens, labels, nf, opt.kl_weight, masks=masks, dropout_p=0.1, seed=99, train_encoder=False)
+    assert not eng.grad_has('point_encoder.linear.weight')
+    from edgerunner_b200 import _lib
+    with pytest.raises(_lib.ErError):
+        eng.grad('point_encoder.linear.weight', sd['point_encoder.linear.weight'].shape)
+    k = 'mesh_decoder.model.layers.1.fc2.weight'
+    assert torch.equal(eng.grad(k, sd[k].shape).cpu(), grads[k])          # the decoder's gradients do not depend on whether the encoder is trained
 
 
 def test_train_step_with_dropout_and_padding():
@@ -209,10 +235,16 @@ def test_lmm_train_mode_backward_and_optimizer_step():
     with torch.no_grad():
         ev = model(data)
     assert float(ev['loss']) < hist[0]
-    opt2 = synth.tiny_options(freeze_encoder=False)
-    m2 = LMM(opt2).cuda().train()
-    with pytest.raises(NotImplementedError):
-        m2(data)
+    # freeze_encoder = False (the ArAE preset): the encoder's parameters receive gradients through the same autograd node
+    opt2 = synth.tiny_options(freeze_encoder=False, nof_dropout_ratio=0.0)
+    m2 = LMM(opt2)
+    m2.load_state_dict(sd, strict=True)
+    m2 = m2.cuda().train()
+    out2 = m2(data)
+    out2['loss'].backward()
+    enc = [p for n, p in m2.named_parameters() if n.startswith('point_encoder.')]
+    assert enc and all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in enc)
+    assert float(m2.point_encoder.query_embed.grad.abs().max()) > 0
 
 
 def test_flat_trainer_steps_reduce_the_loss():
