@@ -322,7 +322,8 @@ def run_train(args):
     """BASELINE configs[3] as a FULL training step: ArAE, seq_len 8192 (+ 2049 condition rows + BOS/EOS = 10 243 rows), batch 4 per GPU,
     data parallel.  A step = edgerunner_b200.train.FlatTrainer.step: training-mode forward (dropout 0.1) + backward with per-layer recomputation
     (opt.checkpointing) + flat fp32 gradient all-reduce over NCCL + global-norm clipping + fused AdamW + fp16 weight refresh; tokens / labels are
-    uploaded and the loss is read back every step.  The point encoder is frozen (opt.freeze_encoder).  value = supervised tokens/s over all ranks;
+    uploaded and the loss is read back every step.  All 766.8 M parameters are trained as in the ArAE preset (--freeze-encoder: the point encoder and the
+    KL term are constants).  value = supervised tokens/s over all ranks;
     roofline: tensor-bound, MODEL FLOPs (forward + 2 x GEMM + 2.5 x attention; the recomputation is not counted) against bf16_tflops_sustained."""
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     dev = torch.device('cuda', local_rank)
@@ -335,7 +336,9 @@ def run_train(args):
     from core.options import config_defaults
     from edgerunner_b200 import synth
     from edgerunner_b200.train import FlatTrainer
-    opt = replace(config_defaults['ArAE'], generate_mode='greedy', freeze_encoder=True) if not args.tiny else synth.tiny_options(freeze_encoder=True)
+    # the ArAE preset trains the point encoder too (options.py:167 freeze_encoder=False); --freeze-encoder = the Options default instead
+    fz = bool(args.freeze_encoder)
+    opt = replace(config_defaults['ArAE'], generate_mode='greedy', freeze_encoder=fz) if not args.tiny else synth.tiny_options(freeze_encoder=fz)
     B, T = (4, 8194) if not args.tiny else (2, 48)
     P, C, NL = opt.num_cond_tokens, opt.hidden_dim, opt.num_layers
     N = P + T
@@ -385,12 +388,12 @@ def run_train(args):
         return
     ms_step = ms / args.steps
     gemm_f, attn_f = 2 * 680_752_128 * B * N, 2 * N * N * C * NL * B
-    flops = (3 * gemm_f + 3.5 * attn_f + 0.16e12 * B) if not args.tiny else float('nan')
+    flops = (3 * gemm_f + 3.5 * attn_f + (1 if fz else 3) * 0.16e12 * B) if not args.tiny else float('nan')
     peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
     peak = float(json.load(open(peaks_path)).get('bf16_tflops_sustained', 1400.0)) if os.path.exists(peaks_path) else 1400.0
     tf = flops / (ms_step * 1e-3) / 1e12
     emit(json.dumps({
-        'metric': 'training tokens/sec, ArAE full step seq_len 8192 batch 4/GPU (BASELINE configs[3]; decoder trained, point encoder frozen)',
+        'metric': 'training tokens/sec, ArAE full step seq_len 8192 batch 4/GPU (BASELINE configs[3]; ' + ('decoder trained, point encoder frozen)' if fz else 'all parameters trained)'),
         'value': world * B * T / (ms_step * 1e-3), 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic', 'loss_history': hist,
         'config': {'workload': f'ArAE training step B={B}/GPU N={N} (P={P} + T={T}): training forward (dropout {tr.dropout_p}) + backward (activations kept in HBM unless '
@@ -622,6 +625,7 @@ def main():
     ap.add_argument('--dit-pipeline', action='store_true', help='--workload dit: also time one image end to end (MDiT.run -> LMM.generate) at the preset sizes')
     ap.add_argument('--workload', default='decode', choices=['decode', 'tf', 'dit', 'train'],
                     help="decode = BASELINE configs[1] (the metric); tf = configs[3]: teacher-forced forward seq 8192 batch 4/GPU, loss all-reduced over NCCL")
+    ap.add_argument('--freeze-encoder', action='store_true', help='--workload train: opt.freeze_encoder = True (the Options default) instead of the ArAE preset (encoder trained)')
     ap.add_argument('--debug', action='append', default=[], metavar='KEY=VALUE', help='process-wide experiment switch of the library (er_debug_set(NULL, KEY, VALUE)), e.g. attn_bwd_wmma=1')
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner under torchrun) is sent to stderr instead
