@@ -2,8 +2,8 @@
 //
 // Reference: main.py:160-172 (`out = model(data); accelerator.backward(out['loss'])`) over models.py:147-202 (LMM.forward), modeling_opt.py:253-298
 // (post-LN decoder layer with F.dropout(p = config.dropout) on both branches), :464-517 (lm_head + shifted cross-entropy), with
-// `opt.checkpointing = True` (options.py:126: every decoder layer is re-run in the backward pass) and `opt.freeze_encoder = True` (options.py:67:
-// the point encoder runs under no_grad, so the KL term carries no gradient).  The reference autocasts to bf16; this engine computes in fp16 (weights
+// `opt.checkpointing = True` (options.py:126: every decoder layer is re-run in the backward pass) and `opt.freeze_encoder` (options.py:67: True = the
+// point encoder runs under no_grad and the KL term carries no gradient; False, the ArAE preset = both are trained).  The reference autocasts to bf16; this engine computes in fp16 (weights
 // are the engine's fp16 copies, activations fp16, residual stream / LayerNorm / softmax / loss fp32) with a static loss scale on the fp16 activation
 // gradients; weight gradients are accumulated in fp32 by the tensor-core GEMM and exported unscaled.
 //
@@ -12,8 +12,9 @@
 // (both activations transposed to K-major: er_transpose_f16) on the tcgen05 kernel, plus the row kernels of backward.cu.  Everything is
 // deterministic: no float atomics anywhere, the dropout mask is a counter-based function of (seed, site, element).
 //
-// Gradients are produced for: every decoder layer, lm_head, embd, embed_positions, proj_cond, norm_cond, embed_num_face.  The point encoder is
-// frozen (er_grad_get on its keys fails).
+// Gradients are produced for: every decoder layer, lm_head, embd, embed_positions, proj_cond, norm_cond, embed_num_face and — with train_encoder
+// (opt.freeze_encoder = False, the ArAE preset) — the point encoder and the KL term (encoder_bwd below); with the encoder frozen er_grad_get on its
+// keys fails.
 #include "engine_internal.h"
 
 #include <algorithm>

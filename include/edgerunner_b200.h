@@ -185,11 +185,12 @@ int er_dit_debug_set(er_dit* e, const char* key, int64_t value);   /* "graph": 0
 /* ---- Training step: forward in training mode + backward ---------------------------------------------------------------------
  * Replaces, for one batch, `out = model(data); accelerator.backward(out['loss'])` (main.py:168-172) = torch autograd over LMM.forward
  * (core/models.py:147-202 -> core/transformer/modeling_opt.py:253-298 post-LN layers with F.dropout(p) on both branches, :464-517 lm_head +
- * shifted cross-entropy), with opt.checkpointing (every layer re-run in the backward pass) and opt.freeze_encoder (the point encoder and the KL
- * term carry no gradient).  Arguments as er_forward_tf2, plus dropout_p (ShapeOPTConfig.dropout, 0.1 in the reference; the keep mask is a
+ * shifted cross-entropy); the activations of every layer are kept from the forward pass when device memory allows, else every layer is re-run in
+ * the backward pass as the reference's opt.checkpointing does.  Arguments as er_forward_tf2, plus dropout_p (ShapeOPTConfig.dropout, 0.1 in the reference; the keep mask is a
  * counter-based function of `seed`, not torch's Philox stream), loss_scale (static scale of the fp16 activation gradients; exported gradients are
  * unscaled), train_encoder (0: opt.freeze_encoder, the point encoder and the KL term carry no gradient; 1: the point encoder of cond_mode 'point' is
- * trained too — its forward is re-run per cloud in the backward pass — and the KL term kl_weight * 0.5 sum(latent^2) contributes).  losses_dev[3] = {loss, mean CE, KL} of this rank's batch (the reference's DDP averages per-rank means: no cross-rank loss sums here);
+ * trained too — its forward is re-run per cloud in the backward pass — and the KL term kl_weight * 0.5 sum(latent^2) contributes).
+ * losses_dev[3] = {loss, mean CE, KL} of this rank's batch (the reference's DDP averages per-rank means: no cross-rank loss sums here);
  * sums_dev (optional) as er_forward_tf2.  The engine must have been created with max_tf_rows >= B * (num_cond_tokens + T).
  * er_grad_get: copy the fp32 gradient of one state-dict entry (reference key schema, dense [rows][cols], numel checked) to out_dev after a
  * step (point_encoder.* keys only after a step with train_encoder = 1).  er_grad_has: 1 if the entry can receive a gradient (every parameter of the
