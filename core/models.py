@@ -141,7 +141,8 @@ class LMM(nn.Module):
         proj_cond / norm_cond / embed_num_face (and, unless frozen, point-encoder) parameters.  The forward AND the backward run inside one library call (er_train_step: checkpointed
         layers, tcgen05 dgrad / wgrad GEMMs, flash-attention backward); the autograd node only hands the stored gradients out.  As with
         ``opt.freeze_encoder = True`` (the Options default) the point encoder runs without a graph and loss_kl carries no gradient; with
-        ``freeze_encoder = False`` (the ArAE preset) the library call also walks back through the point encoder and the KL term.  The dropout mask is a counter-based function of a seed drawn from torch's
+        ``freeze_encoder = False`` (the ArAE preset; the only value the reference accepts in 'point' mode, reference :54) the library call also walks back
+        through the point encoder and the KL term.  The dropout mask is a counter-based function of a seed drawn from torch's
         global generator (reproducible per seed; not torch's Philox stream).  'logits' is None in this mode (main.py never reads it while training)."""
         tokens, labels = data['tokens'], data['labels']
         B, T = tokens.shape

@@ -1,6 +1,6 @@
 """Generate golden vectors by EXECUTING THE REFERENCE (build container only; needs /root/reference).
 
-TEST INFRASTRUCTURE.  Run as a standalone process:  ``python oracle/gen_golden.py [--only tiny|arae|meto|meta|provider]``
+TEST INFRASTRUCTURE.  Run as a standalone process:  ``python oracle/gen_golden.py [--only tiny|arae|meto|meta|provider|train]``
 
 The reference modules (``core.models.LMM``, ``core.transformer.*``) are imported from /root/reference
 with ``flash_attn`` masked (so ``core/transformer/attention.py:19-25`` picks its naive bmm path on CPU)
@@ -204,6 +204,57 @@ def gen_model_goldens(synth, name, opt, steps, num_faces, sample_steps=0, tf_len
         out['tf_logits_tail'] = res['logits'][:, -8:].numpy()
     np.savez_compressed(os.path.join(GOLD, name + '.npz'), **out)
     print(f'[gen] wrote {name}.npz', flush=True)
+
+
+def train_probe_indices(numel, k=48):
+    """the positions of a gradient tensor the training fixture records (shared with tests/test_train_cpu.py)"""
+    return np.unique(np.linspace(0, numel - 1, num=min(k, numel)).astype(np.int64))
+
+
+def gen_train_goldens(synth):
+    """The REFERENCE's own training step on the CPU (fp32, naive attention): ``model.train(); out = model(data); out['loss'].backward()``
+    (main.py:160-172) for the tiny preset in cond_mode 'point' (the reference always trains the point encoder there: models.py:54 asserts
+    ``not opt.freeze_encoder``) and 'point_latent' (no encoder, conds = latents).  Stochastic parts are
+    switched off so that the gradients are a function of the inputs alone: config.dropout = 0, nof_dropout_ratio = 0; opt.checkpointing = False
+    (same arithmetic, no torch.utils.checkpoint).  Recorded per parameter: the gradient's L2 norm and probe values at fixed positions."""
+    out = {}
+    for tag, cond_mode in (('point', 'point'), ('latent', 'point_latent')):
+        opt = synth.tiny_options(cond_mode=cond_mode, freeze_encoder=False, nof_dropout_ratio=0.0, checkpointing=False, kl_weight=3e-3)
+        model, sd = build_reference_model(synth, opt, seed=0, eos_logit=-30.0)
+        model.config.dropout = 0.0
+        assert all(l.config.dropout == 0.0 for l in model.mesh_decoder.model.layers)
+        model.train()
+        B, tf_len, num_faces = 2, 40, 1000
+        rng = np.random.RandomState(11)
+        body = grammar_tokens(rng, tf_len, opt.discrete_bins)
+        toks_tf = np.stack([np.concatenate([[1], np.roll(body, 4 * b), [2]]) for b in range(B)])
+        P = opt.num_cond_tokens
+        labels = np.concatenate([np.full((B, P + 1), -100), toks_tf[:, 1:]], axis=1)
+        if cond_mode == 'point':
+            conds = torch.cat([synth.synth_point_cloud(seed=b, n=opt.point_num) for b in range(B)])
+        else:
+            conds = torch.randn(B, opt.point_latent_size, opt.point_latent_dim, generator=torch.Generator().manual_seed(5)) * 0.5
+            out['latent_conds'] = conds.numpy()
+        data = dict(conds=conds, tokens=torch.from_numpy(toks_tf).long(), labels=torch.from_numpy(labels).long(),
+                    masks=torch.ones(labels.shape, dtype=torch.bool), num_faces=torch.tensor([num_faces, 2500]),
+                    num_tokens=torch.tensor([tf_len, tf_len]))
+        res = model(data)
+        res['loss'].backward()
+        out[f'{tag}_loss'] = np.array([float(res['loss']), float(res['loss_ce']), float(res.get('loss_kl', 0.0))])
+        names = []
+        for n, p in model.named_parameters():
+            if p.grad is None:
+                continue
+            g = p.grad.detach().double().reshape(-1).numpy()
+            names.append(n)
+            out[f'{tag}|{n}|norm'] = np.array(np.linalg.norm(g))
+            out[f'{tag}|{n}|probe'] = g[train_probe_indices(g.size)].astype(np.float32)
+        out[f'{tag}_names'] = np.array(names)
+        print(f'[gen] train/{tag}: loss {float(res["loss"]):.6f}, {len(names)} tensors with gradients', flush=True)
+        if tag == 'point':
+            out['tokens'], out['labels'], out['num_faces'] = toks_tf, labels, np.array([num_faces, 2500])
+    np.savez_compressed(os.path.join(GOLD, 'train.npz'), **out)
+    print('[gen] wrote train.npz', flush=True)
 
 
 def grammar_tokens(rng, n, bins):
@@ -480,6 +531,8 @@ def main():
         gen_dit_goldens()
     if args.only in ('all', 'provider'):
         gen_provider_goldens(synth)
+    if args.only in ('all', 'train'):
+        gen_train_goldens(synth)
     if args.only in ('all', 'tiny'):
         opt = synth.tiny_options()
         gen_model_goldens(synth, 'tiny', opt, steps=160, num_faces=1000, sample_steps=64, tf_len=40)

@@ -11,7 +11,9 @@ What the reference does in a training step (main.py:168-172): ``out = model(data
 
 ``forward_train`` restates that forward with plain differentiable torch ops over a dict of leaf tensors, so that ``loss.backward()`` IS the
 reference's backward (autograd).  Pinning: with ``dropout_p = 0`` and no num-face dropout its loss must equal ``Oracle.forward_tf`` (itself pinned
-against the reference modules by tests/golden) — tests/test_train_cpu.py checks that here on the CPU.  The dropout mask cannot be torch's (the CUDA
+against the reference modules by tests/golden) — tests/test_train_cpu.py checks that here on the CPU — and its GRADIENTS are pinned against the
+reference's own `loss.backward()` executed on the CPU (oracle/gen_golden.py --only train -> tests/golden/train.npz: every parameter's gradient norm and
+probe values, cond_mode 'point' with the encoder trained and 'point_latent').  The dropout mask cannot be torch's (the CUDA
 path draws it from a counter-based generator, edgerunner_b200/csrc/backward.cu::drop_keep): ``dropout_keep`` restates that generator bit for bit so
 that oracle and engine drop the same elements.
 """
@@ -50,19 +52,20 @@ def _dropout(y: torch.Tensor, seed: int, site: int, p: float) -> torch.Tensor:
     return torch.where(keep, y / (1.0 - float(np.float32(p))), torch.zeros_like(y))
 
 
-def trainable_leaves(state_dict: Dict[str, torch.Tensor], train_encoder: bool = False) -> Dict[str, torch.Tensor]:
+def trainable_leaves(state_dict: Dict[str, torch.Tensor], train_encoder: bool = False, round_fp16: bool = True) -> Dict[str, torch.Tensor]:
     """fp16-rounded copies (what the engine holds) of every trainable tensor as fp32 leaves with requires_grad: everything but the point encoder, or
     (train_encoder, opt.freeze_encoder = False) its parameters too — `point_embed.basis` is a buffer, not a parameter (point.py:50)."""
-    return {k: v.detach().to(torch.float16).float().requires_grad_(True) for k, v in state_dict.items()
+    return {k: (v.detach().to(torch.float16).float() if round_fp16 else v.detach().float().clone()).requires_grad_(True) for k, v in state_dict.items()
             if (train_encoder and k != 'point_encoder.point_embed.basis') or not k.startswith('point_encoder.')}
 
 
-def encode_points_train(opt, state_dict, w: Dict[str, torch.Tensor], pc: torch.Tensor) -> torch.Tensor:
+def encode_points_train(opt, state_dict, w: Dict[str, torch.Tensor], pc: torch.Tensor, round_embed: bool = True) -> torch.Tensor:
     """PointEncoderEmbed.forward (core/transformer/point.py:186-206; ResCrossAttBlock :117-126; GEGLU FFN :74-84) as differentiable fp32 ops over the
     leaves `w`.  The Fourier features are data (no parameter in front of them): they are taken with the fp16 rounding the autocast forward applies
     (Oracle.encode_points) — at |x * basis| up to 400 rad an unrounded product would be a different input, not a more accurate one."""
     pe = 'point_encoder.'
-    basis = state_dict[pe + 'point_embed.basis'].to(torch.float16).float()
+    r = _r16 if round_embed else (lambda t: t)          # round_embed = False: the reference's CPU / fp32 arithmetic (the pinning test)
+    basis = r(state_dict[pe + 'point_embed.basis'].float())
     E = w[pe + 'query_embed'].shape[-1]
     Hh = opt.point_num_heads
     Dh = E // Hh
@@ -76,8 +79,8 @@ def encode_points_train(opt, state_dict, w: Dict[str, torch.Tensor], pc: torch.T
     for b in range(pc.shape[0]):
         x = pc[b].float()
         with torch.no_grad():
-            proj = _r16(_r16(x) @ basis)
-            emb = torch.cat([_r16(torch.sin(proj)), _r16(torch.cos(proj)), _r16(x)], dim=1)
+            proj = r(r(x) @ basis)
+            emb = torch.cat([r(torch.sin(proj)), r(torch.cos(proj)), r(x)], dim=1)
         kvx = ln(lin(emb, 'point_embed.mlp'), 'ln')
         q0 = w[pe + 'query_embed'][0]
         q = lin(ln(q0, 'cross_att.ln1'), 'cross_att.att.q_proj').view(-1, Hh, Dh).transpose(0, 1)
@@ -97,19 +100,20 @@ def _r16(t):
 
 
 def forward_train(opt, state_dict, w: Dict[str, torch.Tensor], conds, tokens, labels, num_faces, masks: Optional[torch.Tensor] = None,
-                  dropout_p: float = 0.0, seed: int = 0, train_encoder: bool = False):
+                  dropout_p: float = 0.0, seed: int = 0, train_encoder: bool = False, exact_fp32: bool = False):
     """-> dict(loss, loss_ce, loss_kl).  ``w``: trainable leaves (``trainable_leaves``); the frozen point encoder comes from ``state_dict``.
-    fp32 arithmetic throughout (the gradient reference; the engine's fp16 rounding is what the test tolerance covers)."""
-    orc = Oracle(opt, state_dict, mode='ledger')                     # frozen encoder as the engine runs it (fp16 ledger), no graph
+    fp32 arithmetic throughout (the gradient reference; the engine's fp16 rounding is what the test tolerance covers).  exact_fp32: no fp16 rounding
+    of inputs either (Fourier features, latents) — the reference's own CPU arithmetic, used to pin this function against tests/golden/train.npz."""
+    orc = Oracle(opt, state_dict, mode='fp32' if exact_fp32 else 'ledger')     # frozen encoder as the engine runs it (fp16 ledger), no graph
     B, T = tokens.shape
     C, H, NL = opt.hidden_dim, opt.num_heads, opt.num_layers
     D = C // H
     if train_encoder:                                                # opt.freeze_encoder = False: the encoder and the KL term are part of the graph
         assert opt.cond_mode == 'point'
-        lat_all = encode_points_train(opt, state_dict, w, conds)
+        lat_all = encode_points_train(opt, state_dict, w, conds, round_embed=not exact_fp32)
     else:
         with torch.no_grad():
-            lat_all = orc.encode_points(conds) if opt.cond_mode == 'point' else orc.r(conds.float())
+            lat_all = orc.encode_points(conds) if opt.cond_mode == 'point' else (conds.float() if exact_fp32 else orc.r(conds.float()))
     xs = []
     for b in range(B):
         ce = F.layer_norm(lat_all[b] @ w['proj_cond.weight'].t() + w['proj_cond.bias'], (C,), w['norm_cond.weight'], w['norm_cond.bias'], 1e-5)

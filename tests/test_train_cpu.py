@@ -68,3 +68,32 @@ def test_dropout_generator():
         x ^= x >> 31
         z.append((x >> 32) >= int(0.5 * 2 ** 32))
     assert list(dropout_keep(0, 0, 4, 0.5)) == z
+
+
+def test_oracle_gradients_match_the_reference_backward(golden_dir):
+    """tests/golden/train.npz was produced by executing the REFERENCE's training step (model.train(); model(data)['loss'].backward(), fp32 CPU, dropout
+    off) — oracle/gen_golden.py --only train.  The oracle's autograd over its restated forward must reproduce every parameter's gradient."""
+    import os
+    g = np.load(os.path.join(golden_dir, 'train.npz'))
+    tokens, labels, nf = torch.from_numpy(g['tokens']), torch.from_numpy(g['labels']), g['num_faces'].tolist()
+    for tag, cond_mode in (('point', 'point'), ('latent', 'point_latent')):
+        opt = synth.tiny_options(cond_mode=cond_mode, kl_weight=3e-3)
+        sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0)
+        if cond_mode == 'point':
+            conds = torch.cat([synth.synth_point_cloud(b, opt.point_num) for b in range(2)])
+        else:
+            conds = torch.from_numpy(g['latent_conds'])
+        w = trainable_leaves(sd, train_encoder=cond_mode == 'point', round_fp16=False)
+        out = forward_train(opt, sd, w, conds, tokens, labels, nf, train_encoder=cond_mode == 'point', exact_fp32=True)
+        out['loss'].backward()
+        ref_loss = g[f'{tag}_loss']
+        assert abs(float(out['loss'].detach()) - ref_loss[0]) < 2e-5 * abs(ref_loss[0])
+        names = [str(n) for n in g[f'{tag}_names']]
+        assert set(names) == set(w), (set(names) ^ set(w))
+        gmax = max(float(g[f'{tag}|{n}|norm']) for n in names)
+        for n in names:
+            got = w[n].grad.double().reshape(-1).numpy()
+            norm = float(g[f'{tag}|{n}|norm'])
+            assert abs(np.linalg.norm(got) - norm) <= 1e-4 * norm + 1e-7 * gmax, (tag, n, np.linalg.norm(got), norm)
+            idx = np.unique(np.linspace(0, got.size - 1, num=min(48, got.size)).astype(np.int64))
+            np.testing.assert_allclose(got[idx], g[f'{tag}|{n}|probe'], rtol=2e-3, atol=2e-6 * gmax, err_msg=f'{tag} {n}')
