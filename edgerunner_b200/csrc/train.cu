@@ -1,20 +1,25 @@
 // Training step of LMM: forward in training mode + backward, on the engine's own fp16 weights.
 //
 // Reference: main.py:160-172 (`out = model(data); accelerator.backward(out['loss'])`) over models.py:147-202 (LMM.forward), modeling_opt.py:253-298
-// (post-LN decoder layer with F.dropout(p = config.dropout) on both branches), :464-517 (lm_head + shifted cross-entropy), with
-// `opt.checkpointing = True` (options.py:126: every decoder layer is re-run in the backward pass) and `opt.freeze_encoder` (options.py:67: True = the
-// point encoder runs under no_grad and the KL term carries no gradient; False, the ArAE preset = both are trained).  The reference autocasts to bf16; this engine computes in fp16 (weights
-// are the engine's fp16 copies, activations fp16, residual stream / LayerNorm / softmax / loss fp32) with a static loss scale on the fp16 activation
-// gradients; weight gradients are accumulated in fp32 by the tensor-core GEMM and exported unscaled.
+// (post-LN decoder layer with F.dropout(p = config.dropout) on both branches), :464-517 (lm_head + shifted cross-entropy), point.py:186-206 (the point
+// encoder, always trained in cond_mode 'point': models.py:54), with `opt.checkpointing = True` (options.py:126: every layer is re-run in the backward
+// pass).  The reference autocasts to bf16; this engine computes in fp16 (weights are the engine's fp16 copies, activations fp16, residual stream /
+// LayerNorm / softmax / loss fp32) with a static loss scale on the fp16 activation gradients; weight gradients are accumulated in fp32 by the
+// tensor-core GEMM and exported unscaled.
 //
-// Structure (B200-first, not autograd): activation checkpoints are the fp32 layer inputs only (25 x M x C floats); each layer's backward re-runs its
-// forward into the dense workspace and then issues, per Linear, one dgrad GEMM (weight transposed on the fly: 2..19 MB) and one wgrad GEMM
-// (both activations transposed to K-major: er_transpose_f16) on the tcgen05 kernel, plus the row kernels of backward.cu.  Everything is
-// deterministic: no float atomics anywhere, the dropout mask is a counter-based function of (seed, site, element).
+// Structure (B200-first, not autograd):
+//   * what a layer's backward needs (LayerAct below) is KEPT from the forward pass — 1.64 GB per layer at 4 x 10 243 rows, 39 GB for 24 layers, next to
+//     the fp32 layer inputs; when device memory is short (or on er_debug_set("train_recompute", 1)) only the fp32 layer inputs are kept and each layer
+//     is re-run in the backward pass as the reference does.  Both modes are bit-identical.
+//   * per Linear one dgrad GEMM (weight transposed on the fly: 2..19 MB) and one wgrad GEMM (both activations transposed to K-major, zero-padded to a
+//     multiple of 64 rows: er_transpose_f16) on the tcgen05 kernel of gemm_tcgen05.cu, plus the row kernels of backward.cu and the flash-attention
+//     backward of attention_bwd_mma.cu (its softmax statistic is written by the forward attention kernel: AttnArgs.lse2).
+//   * everything is deterministic: no float atomics anywhere, fixed-order two-stage column sums, the dropout mask a counter-based function of
+//     (seed, site, element).
 //
 // Gradients are produced for: every decoder layer, lm_head, embd, embed_positions, proj_cond, norm_cond, embed_num_face and — with train_encoder
-// (opt.freeze_encoder = False, the ArAE preset) — the point encoder and the KL term (encoder_bwd below); with the encoder frozen er_grad_get on its
-// keys fails.
+// (opt.freeze_encoder = False: the ArAE preset and the reference's only setting in 'point' mode) — the point encoder and the KL term (encoder_bwd
+// below); with the encoder frozen er_grad_get on its keys fails.
 #include "engine_internal.h"
 
 #include <algorithm>
