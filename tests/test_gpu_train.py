@@ -270,8 +270,6 @@ def test_flat_trainer_steps_reduce_the_loss():
     assert float(ev['loss']) < hist[0]
 
 
-# kept last in the file: the one test of this module that has not yet run on the GPU box (round 2 ran out of GPU minutes); with `pytest -x` a surprise
-# here cannot hide the validated tests above
 def test_attention_seam_is_differentiable():
     """core.transformer.attention.attention() with inputs that require grad (what the reference gets from flash-attn's autograd function)"""
     from core.transformer.attention import attention
