@@ -69,3 +69,4 @@ def test_dp_forward_nccl_two_ranks_bit_exact():
         assert ce == float(single['loss_ce']), (r, ce, float(single['loss_ce']))
         assert kl == float(single['loss_kl']), (r, kl, float(single['loss_kl']))
         assert loss == float(single['loss']), (r, loss, float(single['loss']))
+
