@@ -169,12 +169,13 @@ class Engine:
     # ---- training step ------------------------------------------------------------------------------------------
     def train_step(self, conds: torch.Tensor, tokens: torch.Tensor, labels: torch.Tensor, num_faces, kl_weight: float,
                    masks: Optional[torch.Tensor] = None, dropout_p: float = 0.1, seed: int = 0, loss_scale: Optional[float] = None,
-                   train_encoder: bool = False):
+                   train_encoder: bool = False, loss_scale_mult: float = 1.0):
         """Training-mode forward + backward of LMM.forward on this batch (er_train_step): -> (losses[3] = loss, mean CE, KL; sums[3]).
         The gradients stay in the engine until ``grad(name, ...)`` exports them.  Arguments as ``forward_tf``.  loss_scale: static scale of the fp16
         activation gradients (removed again on export); default: the power of two that puts 4..8 on each supervised row's d loss / d logits
         (the mean over n rows carries 1/n), so the scale does not depend on the batch size.  train_encoder: also back-propagate through the point
-        encoder of cond_mode 'point' and the KL term (opt.freeze_encoder = False); otherwise both are constants (the Options default)."""
+        encoder of cond_mode 'point' and the KL term (opt.freeze_encoder = False); otherwise both are constants (the Options default).
+        loss_scale_mult: factor on the default scale (a trainer's overflow back-off)."""
         B, T = tokens.shape
         is_latent = int(self.opt.cond_mode == 'point_latent')
         conds = conds.to(self.device, torch.float32).contiguous()
@@ -183,7 +184,7 @@ class Engine:
         nf = (C.c_int32 * B)(*[int(x) for x in num_faces])
         if loss_scale is None:
             n_sup = max(1, int((lab[:, 1:] >= 0).sum().item()))
-            loss_scale = float(2 ** int(np.ceil(np.log2(4.0 * n_sup))))
+            loss_scale = float(2 ** int(np.ceil(np.log2(4.0 * n_sup)))) * float(loss_scale_mult)
         losses = torch.zeros(3, dtype=torch.float32, device=self.device)
         sums = torch.zeros(3, dtype=torch.float64, device=self.device)
         m8 = None

@@ -15,7 +15,6 @@ CUDA only — no CPU fallback.
 
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from .dist import FlatGradAllReduce, world
@@ -52,9 +51,13 @@ class FlatTrainer:
         self.step_count = 0
         self.dropout_p = float(model.config.dropout)
         self._rng = torch.Generator().manual_seed(1234 + world()[0])
+        # overflow back-off of the fp16 activation gradients (what accelerate's GradScaler does for the reference's fp16 mode): a step whose global
+        # gradient norm is not finite is skipped and the loss scale halved; it creeps back up after 200 good steps
+        self.scale_mult, self.good_steps, self.skipped_steps = 1.0, 0, 0
 
-    def step(self, data, loss_scale=None):
-        """One optimizer step on this rank's batch -> dict(loss, loss_ce, loss_kl (device scalars), grad_norm, lr)."""
+    def step(self, data, loss_scale=None, check_finite=True):
+        """One optimizer step on this rank's batch -> dict(loss, loss_ce, loss_kl (device scalars), grad_norm, lr, skipped).  check_finite: read the
+        global gradient norm back (one host sync) and skip the update when it is inf / nan (fp16 overflow), halving the loss scale."""
         e, opt = self.engine, self.opt_cfg
         num_faces = data['num_faces'].clone()
         if opt.use_num_face_cond and opt.nof_dropout_ratio > 0:                      # models.py:161-164
@@ -62,16 +65,27 @@ class FlatTrainer:
             num_faces[drop.to(num_faces.device)] = -1
         seed = int(torch.randint(0, 2 ** 62, (1,), generator=self._rng).item())
         losses, _ = e.train_step(data['conds'], data['tokens'], data['labels'], num_faces.tolist(), opt.kl_weight, masks=data.get('masks'),
-                                 dropout_p=self.dropout_p, seed=seed, loss_scale=loss_scale, train_encoder=self.train_encoder)
+                                 dropout_p=self.dropout_p, seed=seed, loss_scale=loss_scale, train_encoder=self.train_encoder,
+                                 loss_scale_mult=self.scale_mult)
         for name, o, n, shp in self.entries:
             e.grad(name, out=self.grad[o:o + n])
         self.reducer.launch().wait()
         lr_scale = cosine_lr_lambda(self.step_count, self.total_steps, warmup_ratio=self.warmup_ratio)
+        if check_finite:
+            norm, _ = self.optim.grad_norm(self.grad, self.gradient_clip if self.gradient_clip else 0.0)
+            if not bool(torch.isfinite(norm)):           # every rank sees the same all-reduced gradient, hence the same decision
+                self.scale_mult *= 0.5
+                self.good_steps = 0
+                self.skipped_steps += 1
+                return {'loss': losses[0], 'loss_ce': losses[1], 'loss_kl': losses[2], 'grad_norm': norm.clone(), 'lr': self.optim.lr * lr_scale, 'skipped': True}
+            self.good_steps += 1
+            if self.good_steps >= 200 and self.scale_mult < 1.0:
+                self.scale_mult, self.good_steps = self.scale_mult * 2.0, 0
         norm = self.optim.step(self.grad, max_norm=self.gradient_clip, lr_scale=lr_scale)
         self.step_count += 1
         # the forward kernels read the engine's fp16 weight arrays: refresh them from the optimizer's fp16 copy
         e.load_state_dict({name: self.param16[o:o + n].view(shp) for name, o, n, shp in self.entries}, persistent=True)
-        return {'loss': losses[0], 'loss_ce': losses[1], 'loss_kl': losses[2], 'grad_norm': norm, 'lr': self.optim.lr * lr_scale}
+        return {'loss': losses[0], 'loss_ce': losses[1], 'loss_kl': losses[2], 'grad_norm': norm, 'lr': self.optim.lr * lr_scale, 'skipped': False}
 
     def sync_to_model(self):
         """copy the master weights back into the module's parameters (checkpointing: accelerator.save_state / safetensors of main.py)"""

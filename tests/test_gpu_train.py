@@ -295,3 +295,24 @@ def test_attention_seam_is_differentiable():
             assert float(err) < 1e-2, (name, float(err))
     with torch.no_grad():                                               # no graph requested: the plain path
         assert not attention(q, k, v, causal=False).requires_grad
+
+
+def test_flat_trainer_skips_a_step_whose_gradient_overflowed():
+    """fp16 overflow back-off: a step run at an absurd loss scale produces a non-finite global gradient norm; the update is skipped (weights and
+    optimizer state untouched), the loss scale halves, and the next ordinary step goes through"""
+    from core.models import LMM
+    from edgerunner_b200.train import FlatTrainer
+    opt = synth.tiny_options(freeze_encoder=True, nof_dropout_ratio=0.0, lr=1e-3, warmup_ratio=0.0)
+    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0)
+    model = LMM(opt)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    conds, tokens, labels, masks, nf = _batch(opt, B=2, T=40)
+    data = {'conds': conds.cuda(), 'tokens': tokens.cuda(), 'labels': labels.cuda(), 'masks': masks.cuda(), 'num_faces': torch.tensor(nf).cuda()}
+    tr = FlatTrainer(model, total_steps=100, max_batch=2, max_tokens=40)
+    before = tr.param.clone()
+    out = tr.step(data, loss_scale=1e30)
+    assert out['skipped'] and not bool(torch.isfinite(out['grad_norm']))
+    assert torch.equal(tr.param, before) and tr.optim.step_count == 0 and tr.step_count == 0 and tr.scale_mult == 0.5 and tr.skipped_steps == 1
+    out = tr.step(data)
+    assert not out['skipped'] and bool(torch.isfinite(out['grad_norm'])) and not torch.equal(tr.param, before)
