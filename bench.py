@@ -223,7 +223,7 @@ def run_teacher_forced(args):
     B, T = 4, (8194 if not args.tiny else 48)
     P, C, NL = opt.num_cond_tokens, opt.hidden_dim, opt.num_layers
     N = P + T
-    sd = synth.synth_state_dict_shared(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
+    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
     with torch.device('meta'):
         model = LMM(opt)
     model.load_state_dict(sd, strict=True, assign=True)
@@ -267,8 +267,6 @@ def run_teacher_forced(args):
         if fg:
             fg.wait()
     barrier()
-    if local_rank == 0:
-        synth.release_shared_state_dicts()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -344,7 +342,7 @@ def run_train(args):
     B, T = (4, 8194) if not args.tiny else (2, 48)
     P, C, NL = opt.num_cond_tokens, opt.hidden_dim, opt.num_layers
     N = P + T
-    sd = synth.synth_state_dict_shared(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
+    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
     with torch.device('meta'):
         model = LMM(opt)
     model.load_state_dict(sd, strict=True, assign=True)
@@ -367,8 +365,6 @@ def run_train(args):
     for _ in range(max(args.warmup, 1)):
         hist.append(float(tr.step(data)['loss']))
     barrier()
-    if local_rank == 0:
-        synth.release_shared_state_dicts()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -556,7 +552,7 @@ def dit_pipeline_leg(dev):
     from core.utils import get_tokenizer
     from edgerunner_b200 import synth
     opt = replace(config_defaults['DiT'], generate_mode='greedy')
-    sd = synth.synth_state_dict_shared(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
+    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
     with torch.device('meta'):
         lmm = LMM(opt)
     lmm.load_state_dict(sd, strict=True, assign=True)
@@ -671,7 +667,7 @@ def main():
     opt, wl, T, nf = workload(args)
     # synthetic checkpoint straight into fp16 (model.half() of infer.py:56 is exact on it); the module is built on the meta device and
     # the tensors are assigned, so that N ranks do not each run a 766 M-parameter random init + a 3 GB fp32 copy on the shared host
-    sd = synth.synth_state_dict_shared(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
+    sd = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
     with torch.device('meta'):
         model = LMM(opt)
     model.load_state_dict(sd, strict=True, assign=True)
@@ -712,8 +708,6 @@ def main():
     for _ in range(args.warmup):
         out = step_device()
     barrier()
-    if local_rank == 0:
-        synth.release_shared_state_dicts()          # every rank has its weights on its GPU by now
     n_tok = int(out['n'].item())
     launches0 = eng.kernel_launches()
     sampler = ClockSampler(local_rank)

@@ -145,48 +145,6 @@ def synth_point_cloud(seed: int = 0, n: int = 8192) -> torch.Tensor:
     return torch.rand((1, n, 3), generator=g) * 1.9 - 0.95
 
 
-def synth_state_dict_shared(opt, seed: int = 0, eos_logit: float | None = -30.0, dtype: torch.dtype = torch.float16, timeout_s: float = 600.0):
-    """``synth_state_dict`` once per NODE: under torchrun every rank needs the same synthetic checkpoint; LOCAL_RANK 0 generates it and parks it in
-    /dev/shm, the other ranks map that file instead of each running a 766 M-element random init on the shared host cores (N = 8: eight concurrent
-    single-threaded generations otherwise).  Without torchrun (or when /dev/shm is unusable) it simply generates.  Values are identical either way."""
-    import hashlib
-    import os
-    import time
-    world = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')))
-    if world <= 1 or not os.path.isdir('/dev/shm'):
-        return synth_state_dict(opt, seed=seed, eos_logit=eos_logit, dtype=dtype)
-    key = hashlib.sha1(repr((sorted(vars(opt).items(), key=lambda kv: kv[0]), seed, eos_logit, str(dtype), os.environ.get('TORCHELASTIC_RUN_ID', ''),
-                             os.environ.get('MASTER_PORT', ''))).encode()).hexdigest()[:16]
-    path = f'/dev/shm/er_synth_{key}.pt'
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    try:
-        if local_rank == 0:
-            sd = synth_state_dict(opt, seed=seed, eos_logit=eos_logit, dtype=dtype)
-            tmp = path + f'.tmp{os.getpid()}'
-            torch.save(sd, tmp)
-            os.replace(tmp, path)                      # atomic: readers see either nothing or the complete file
-            return sd
-        t0 = time.time()
-        while not os.path.exists(path):
-            if time.time() - t0 > timeout_s:
-                raise TimeoutError(path)
-            time.sleep(0.25)
-        return torch.load(path, map_location='cpu', mmap=True, weights_only=True)
-    except Exception:                                  # any file-system surprise: every rank can still generate its own copy
-        return synth_state_dict(opt, seed=seed, eos_logit=eos_logit, dtype=dtype)
-
-
-def release_shared_state_dicts():
-    """remove this run's /dev/shm checkpoint copies (called by LOCAL_RANK 0 once every rank has loaded)"""
-    import glob
-    import os
-    for f in glob.glob('/dev/shm/er_synth_*.pt'):
-        try:
-            os.remove(f)
-        except OSError:
-            pass
-
-
 def tiny_options(**over):
     """A small ArAE-shaped configuration that the CPU oracle finishes in seconds.
 

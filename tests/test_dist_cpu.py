@@ -3,8 +3,6 @@
 import os
 import socket
 
-import pytest
-
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -70,33 +68,3 @@ def test_single_process_fallbacks():
     assert erd.max_over_ranks(3.5) == 3.5
     l, ce, kl = erd.dp_reduce_losses(torch.tensor(6.0), torch.tensor(3.0), torch.tensor(0.5), 2.0)
     assert float(ce) == 2.0 and float(l) == 3.0
-
-
-def test_synthetic_checkpoint_is_shared_per_node(tmp_path):
-    """bench.py under torchrun: LOCAL_RANK 0 generates the synthetic checkpoint once and parks it in /dev/shm, the other local ranks map it
-    (edgerunner_b200.synth.synth_state_dict_shared) — same tensors as a direct generation, file removed afterwards"""
-    import glob
-    import subprocess
-    import sys
-    import textwrap
-    if not os.path.isdir('/dev/shm'):
-        pytest.skip('no /dev/shm')
-    code = textwrap.dedent("""
-        import os, sys, torch
-        sys.path.insert(0, %r)
-        from edgerunner_b200 import synth
-        opt = synth.tiny_options()
-        sd = synth.synth_state_dict_shared(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
-        ref = synth.synth_state_dict(opt, seed=0, eos_logit=-30.0, dtype=torch.float16)
-        assert set(sd) == set(ref) and all(torch.equal(sd[k], ref[k]) for k in ref)
-        print('ok')
-    """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    env = dict(os.environ, WORLD_SIZE='2', LOCAL_WORLD_SIZE='2', MASTER_PORT='29877', TORCHELASTIC_RUN_ID='pytest-%d' % os.getpid())
-    procs = [subprocess.Popen([sys.executable, '-c', code], env=dict(env, LOCAL_RANK=str(r), RANK=str(r)), stdout=subprocess.PIPE,
-                              stderr=subprocess.STDOUT, text=True) for r in (1, 0)]      # the reader starts first and has to wait for the writer
-    outs = [p.communicate(timeout=300)[0] for p in procs]
-    assert all(o.strip().endswith('ok') for o in outs), outs
-    from edgerunner_b200 import synth
-    assert glob.glob('/dev/shm/er_synth_*.pt')
-    synth.release_shared_state_dicts()
-    assert not glob.glob('/dev/shm/er_synth_*.pt')
