@@ -392,7 +392,7 @@ def run_train(args):
     peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
     peak = float(json.load(open(peaks_path)).get('bf16_tflops_sustained', 1400.0)) if os.path.exists(peaks_path) else 1400.0
     tf = flops / (ms_step * 1e-3) / 1e12
-    emit(json.dumps({
+    line = {
         'metric': 'training tokens/sec, ArAE full step seq_len 8192 batch 4/GPU (BASELINE configs[3]; ' + ('decoder trained, point encoder frozen)' if fz else 'all parameters trained)'),
         'value': world * B * T / (ms_step * 1e-3), 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic', 'loss_history': hist,
@@ -407,7 +407,41 @@ def run_train(args):
                      'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)'},
         'e2e': {'value': world * B * T / (ms_step * 1e-3), 'unit': 'tokens/s', 'h2d_bytes_per_step': int(tokens.numel() * 4 + data['labels'].numel() * 8),
                 'd2h_bytes_per_step': 4, 'note': 'FlatTrainer.step(data): tokens / labels uploaded from pinned host memory, loss read back, every step'},
-    }), flush=True)
+    }
+    value = line['value']
+    if world == 1 and not args.tiny:
+        del tr, model
+        torch.cuda.empty_cache()
+        if not args.no_reference_gpu:
+            rg = ref_train_leg('gpu', 2, 1, timeout=900)
+            line['reference_gpu'] = ({'value': rg['tok_s'], 'unit': 'tokens/s', 'kind': 'reference', 'path': rg['path'], 'sample': rg['sample'], 's_per_step': rg['s_per_step_sample'],
+                                      'ours_over_reference_gpu': value / rg['tok_s']} if rg and 'tok_s' in rg else
+                                     {'unavailable': 'oracle/_ref/py absent' if rg is None else rg.get('error', 'failed')})
+        if not args.no_cpu_baseline:
+            rc = ref_train_leg('cpu', 1, 0, timeout=1500)
+            line['cpu_baseline'] = ({'value': rc['tok_s'], 'unit': 'tokens/s', 'cores': rc['threads'], 'kind': 'reference', 'sample': rc['sample'] + '; ' + rc['path'],
+                                     'sample_s_per_step': rc['s_per_step_sample'], 'extrapolated_step_s': rc['extrapolated_c4_step_s']} if rc and 'tok_s' in rc else
+                                    {'unavailable': 'oracle/_ref/py absent' if rc is None else rc.get('error', 'failed')})
+    emit(json.dumps(line), flush=True)
+
+
+def ref_train_leg(kind, steps, warmup, tiny=False, timeout=900):
+    """oracle/ref_train_leg.py in its own process -> dict | None: the reference's OWN training step (torch autograd over its modules, clip, AdamW) on the
+    host cores (bounded sample, extrapolated by model FLOPs) or on the GPU (bf16 autocast + flash-attn at the configs[3] shape)."""
+    if not os.path.isdir(os.path.join(REPO, 'oracle', '_ref', 'py', 'core')):
+        return None
+    cmd = [sys.executable, os.path.join(REPO, 'oracle', 'ref_train_leg.py'), kind, '--steps', str(steps), '--warmup', str(warmup)] + (['--tiny'] if tiny else [])
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'TORCHELASTIC_RUN_ID'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        return {'error': f'reference training {kind} leg timed out after {timeout}s'}
+    for line in out.stdout.splitlines():
+        if line.startswith('REF_TRAIN_LEG '):
+            return json.loads(line[14:])
+    return {'error': (out.stderr or out.stdout)[-400:]}
 
 
 def ref_dit_leg(kind, images, steps, warmup, layers=24, timeout=900):
@@ -597,6 +631,25 @@ def run_dit_reference_arm(args):
                       'cpu_baseline': cb, 'e2e': {'value': v, 'unit': 'denoiser steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
 
 
+def run_train_reference_arm(args):
+    """`--impl reference --workload train`: the reference's own training step on the host cores (oracle/ref_train_leg.py cpu): every bench step = one
+    bounded sample (one sample of 128 tokens + 2049 condition rows through forward, backward, clip, AdamW), extrapolated to the configs[3] step by
+    model FLOPs.  Rank 0 only."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    rc = ref_train_leg('cpu', max(args.steps, 1), min(args.warmup, 1), tiny=args.tiny, timeout=3000)
+    if not rc or 'tok_s' not in rc:
+        emit(json.dumps({'impl': 'reference', 'unavailable': str(rc)[:200]}), flush=True)
+        return
+    cb = {'value': rc['tok_s'], 'unit': 'tokens/s', 'cores': rc['threads'], 'kind': 'reference', 'sample': rc['sample'] + '; ' + rc['path']}
+    emit(json.dumps({'impl': 'reference', 'metric': 'training tokens/sec, ArAE full step seq_len 8192 batch 4/GPU (BASELINE configs[3]; all parameters trained)',
+                      'value': rc['tok_s'], 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+                      'ms_per_step': rc['s_per_step_sample'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                      'data': 'synthetic', 'config': {'workload': 'reference LMM training step, CPU', 'sample': cb['sample'],
+                                                      'note': 'ms_per_step is the measured bounded sample; value extrapolates it to the configs[3] step'},
+                      'cpu_baseline': cb, 'e2e': {'value': rc['tok_s'], 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
+
+
 _STDOUT_FD = None
 
 
@@ -639,7 +692,7 @@ def main():
         k, v = kv.split('=')
         _lib.check(_lib.load().er_debug_set(None, k.encode(), int(v)))
     if args.impl == 'reference':
-        (run_dit_reference_arm if args.workload == 'dit' else run_reference_arm)(args)
+        {'dit': run_dit_reference_arm, 'train': run_train_reference_arm}.get(args.workload, run_reference_arm)(args)
         return
     if args.workload == 'dit':
         run_dit(args)
